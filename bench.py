@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the per-step part-disentanglement path (BASELINE.json metric:
+part-step images/sec, forward + backward, and fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cub|deepfashion|pennaction]
+    python bench.py --impl reference ...      # the CPU restatement of the reference path, host cores
+
+One "step" = forward + backward of the path (TPS warp of the views, part softmax, masks and
+labels, mask_parts + pooling, unpool + inject, and the backward of all of it) on one batch of
+synthetic inputs.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (spatial, K, F, views, per-GPU batch, tps ranges)  — BASELINE.json configs[1..3]
+    "cub": dict(S=128, K=16, F=64, V=3, B=256, use_tps=True,
+                desc="CUB 128x128, K=16, F=64, 3 warped views, batch 256 per GPU (BASELINE.json configs[1])"),
+    "deepfashion": dict(S=256, K=16, F=64, V=2, B=128, use_tps=True,
+                        desc="DeepFashion 256x256, K=16, F=64, 2 warped views, batch 128 per GPU (configs[2])"),
+    "pennaction": dict(S=128, K=16, F=64, V=2, B=512, use_tps=True,
+                       desc="PennAction 128x128, K=16, F=64, 2 per-sample warps, batch 512 per GPU (configs[3])"),
+}
+CPU_SAMPLE_B = 8   # BASELINE.json configs[0]: batch 8 on the host CPU
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(wl, steps, warmup, threads=None):
+    """fwd+bwd of the oracle (CPU restatement of the reference path) on a bounded sample."""
+    import torch
+    from oracle import step as OS
+    from util import make_inputs
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = CPU_SAMPLE_B
+    inp = make_inputs(B, wl["S"], wl["K"], wl["F"], wl["V"], seed=0)
+    cot = dict(inp["cot"], g_warped=None)
+    views = [v for v in inp["views"]]
+
+    def one():
+        OS.step_forward_backward(views, inp["coord"], inp["t_vector"], inp["l0"], inp["l1"], inp["feat"], cot,
+                                 use_tps=wl["use_tps"])
+    for _ in range(warmup):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return B / med, med, cores, f"{steps} fwd+bwd steps of batch {B} at the workload's resolution (median), {cores} torch threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    steps = max(3, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 3))
+    rate, med, cores, sample = cpu_port_rate(wl, steps, warm)
+    line = {
+        "impl": "reference", "metric": "part-step images/sec (fwd+bwd)", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample_batch": CPU_SAMPLE_B},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement (oracle/) of the reference's TF-1.14 op chain; TF itself is not installable here",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Polls NVML (SM clock, throttle reasons) every few ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+KERNEL_BYTES_PER_PX = {
+    # algorithmic (compulsory) bytes per pixel of each C-ABI call, fp32, K parts, F features, C=3
+    "ups_tps_warp_fwd": lambda K, F: 4 * (3 + 3),
+    "ups_step_encode_fwd": lambda K, F: 4 * (K + 3 + K + 3 * K),
+    "ups_step_decode_fwd": lambda K, F: 4 * (K + K + 2 + F + K),
+    "ups_step_decode_bwd": lambda K, F: 4 * ((F + K) + K + K + K),
+    "ups_step_encode_bwd": lambda K, F: 4 * (3 * K + 3 + K + K + K),
+    "ups_tps_warp_bwd": lambda K, F: 4 * (3 + 3),
+}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import ups_b200
+    from ups_b200 import _cabi as C
+    from ups_b200.dp import DataParallelPartStep, init_from_env, rank_seed
+    from util import CUB_TPS, PENN_TPS
+    from oracle import tps as OT   # TPS parameter draws only (host-side, ~50 floats per sample)
+
+    rank, local, world = init_from_env()
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = WORKLOADS[args.workload]
+    S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
+    P = S * S
+    dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev)
+    step = dp.step
+
+    # ---- synthetic shard, resident in HBM (rank-offset seed)
+    g = torch.Generator(device=dev).manual_seed(rank_seed(args.seed, rank))
+    views = torch.rand(V, B, S, S, 3, device=dev, generator=g) * 2 - 1
+    l0 = torch.randn(B, S, S, K, device=dev, generator=g)
+    l1 = torch.randn(B, S, S, K, device=dev, generator=g)
+    feat = torch.randn(B, K, F, device=dev, generator=g)
+    g_inj = torch.randn(B, S, S, F + K, device=dev, generator=g)
+    g_parts = torch.randn(K * B, S, S, 3, device=dev, generator=g)
+    g_pooled = torch.randn(B, K, 3, device=dev, generator=g)
+    g_m0 = torch.randn(B, S, S, K, device=dev, generator=g)
+    g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
+    g_warped = torch.randn(V, B, S, S, 3, device=dev, generator=g) if args.tps_bwd else None
+    tps_kw = CUB_TPS if args.workload == "cub" else PENN_TPS
+    prm = OT.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234 + rank), **tps_kw)
+    coord_h, tv_h = OT.make_input_tps_param(prm)
+    coord, tv = coord_h.to(dev), tv_h.to(dev)
+
+    def one_step():
+        dp.forward(views, coord, tv, l0, l1, feat)
+        dp.backward(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device time, per-call events on the launching stream
+    marks = []
+    raw_call = C.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        raw_call(name, *a)
+        e1.record()
+        marks.append((name, e0, e1))
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    C.launch_count_reset()
+    ups_b200.step.C.call = timed_call
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        one_step()
+    t1.record()
+    barrier()
+    ups_b200.step.C.call = raw_call
+    launches = C.launch_count()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+
+    per_call = {}
+    for name, e0, e1 in marks:
+        per_call.setdefault(name, []).append(e0.elapsed_time(e1))
+    # calls per step of each name (tps_warp_fwd is called twice: 2B views, then the target view)
+    call_ms = {n: sum(v) / args.steps for n, v in per_call.items()}
+    peak, peak_src = load_peaks()
+    dom = max(call_ms, key=call_ms.get)
+    px = {"ups_tps_warp_fwd": V * B * P, "ups_tps_warp_bwd": V * B * P}.get(dom, B * P)
+    dom_bytes = KERNEL_BYTES_PER_PX[dom](K, F) * px if dom in KERNEL_BYTES_PER_PX else None
+    n_dom = len(per_call[dom]) / args.steps
+    dom_launch_ms = call_ms[dom] / n_dom
+    achieved = (dom_bytes / n_dom) / (dom_launch_ms * 1e-3) / 1e9 if dom_bytes else None
+    step_bytes = step.algorithmic_bytes_per_image() * B
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    line = {
+        "metric": "part-step images/sec (fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "spatial": S, "n_parts": K,
+                   "local_app_size": F, "views": V, "tps_backward": bool(args.tps_bwd),
+                   "parallelism": f"dp{world} (batch-sharded; no data-path collective; "
+                                  f"{dp.grads.numel() * 4 / 1e6:.0f} MB fp32 gradient all-reduce per step when N>1)",
+                   "l2": "inputs larger than L2: one step touches %.1f GB per GPU (L2 = 126 MB)" % (step_bytes / 1e9)},
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes / n_dom if dom_bytes else None,
+                     "launch_ms": dom_launch_ms},
+        "step_roofline": {"algorithmic_bytes_per_image": step.algorithmic_bytes_per_image(), "achieved": step_gbs,
+                          "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0},
+        "per_call_ms": {k: round(v, 4) for k, v in sorted(call_ms.items())},
+    }
+
+    # ---- e2e: same metric through the public API with HOST buffers (pinned), copies in the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, dp, dev, world, dict(views=views, coord=coord_h, tv=tv_h, l0=l0, l1=l1, feat=feat,
+                                                              g_inj=g_inj, g_parts=g_parts, g_pooled=g_pooled, g_m0=g_m0,
+                                                              g_m1=g_m1, g_warped=g_warped), B)
+        line["e2e"] = e2e
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, med, cores, sample = cpu_port_rate(wl, steps=5, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, dp, dev, world, t, B):
+    """Host-resident per-step inputs (what the reference feeds through feed_dict each step: the
+    image views, cub/code/SB_model48i/model.py:316-327, plus the TPS parameters drawn on the host)
+    are copied host->device every step from pinned memory; the step's host-visible results (the
+    int64 part labels that evaluation consumes, the pooled part appearances and dfeat) are read
+    back every step.  Logits, part features and cotangents are produced ON the device by the
+    CNNs that surround the path in the real model, so they stay device-resident here too.
+    Copies run on a side stream, double-buffered, so that they overlap the previous step."""
+    views_h = t["views"].cpu().pin_memory()
+    coord_h, tv_h = t["coord"].pin_memory(), t["tv"].pin_memory()
+    step = dp.step
+    lab_h = torch.empty(step.labels0.shape, dtype=torch.int64).pin_memory()
+    pooled_h = torch.empty(step.pooled.shape).pin_memory()
+    dfeat_h = torch.empty(step.dfeat.shape).pin_memory()
+    bufs = [dict(views=torch.empty_like(t["views"]), coord=torch.empty(coord_h.shape, device=dev),
+                 tv=torch.empty(tv_h.shape, device=dev)) for _ in range(2)]
+    copy_s = torch.cuda.Stream(device=dev)
+    main_s = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    h2d = views_h.numel() * 4 + coord_h.numel() * 4 + tv_h.numel() * 4
+    d2h = lab_h.numel() * 8 + pooled_h.numel() * 4 + dfeat_h.numel() * 4
+
+    def stage(i):
+        b = bufs[i % 2]
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(freed[i % 2])
+            b["views"].copy_(views_h, non_blocking=True)
+            b["coord"].copy_(coord_h, non_blocking=True)
+            b["tv"].copy_(tv_h, non_blocking=True)
+            ready[i % 2].record(copy_s)
+
+    def run(n):
+        for ev in freed:
+            ev.record(main_s)
+        stage(0)
+        for i in range(n):
+            if i + 1 < n:
+                stage(i + 1)
+            b = bufs[i % 2]
+            main_s.wait_event(ready[i % 2])
+            dp.forward(b["views"], b["coord"], b["tv"], t["l0"], t["l1"], t["feat"])
+            dp.backward(t["g_inj"], t["g_parts"], t["g_pooled"], t["g_m0"], t["g_m1"], t["g_warped"])
+            freed[i % 2].record(main_s)
+            lab_h.copy_(step.labels0, non_blocking=True)
+            pooled_h.copy_(step.pooled, non_blocking=True)
+            dfeat_h.copy_(step.dfeat, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run(3)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(5, min(args.steps, 50))
+    t0.record()
+    run(n)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    assert int(lab_h.max()) < dp.step.K
+    return {"value": world * B * n / (ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": n, "ms_per_step": ms / n,
+            "boundary": "host: views + TPS params in, int64 labels + pooled + dfeat out; "
+                        "logits/features/cotangents device-resident (CNN outputs in the real model)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cub", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tps-bwd", action="store_true", help="also back-propagate into the input views (K6)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/* ups_b200 — C ABI of the B200-native part-disentanglement hot path.
+ *
+ * The reference (CompVis/unsupervised-part-segmentation) has no FFI: its boundary for this
+ * path is the set of Python helper signatures in {cub,pennaction,deepfashion}/code.  Each
+ * entry point below replaces the TensorFlow op chain behind one of those helpers; the
+ * Python package `ups_b200` binds them with ctypes and re-exposes the reference's
+ * signatures.  Citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a contiguous fp32 buffer unless stated; NHWC;
+ *     `P` = H*W pixels per sample; labels are int64 (tf.argmax's dtype)
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it:
+ *     no allocation, no free, no synchronisation, no host-visible side effect
+ *   - scratch memory is caller-owned: ask ups_workspace_bytes() and pass `ws`
+ *   - return value: 0 on success, negative UPS_E_* otherwise; ups_last_error_string()
+ *     (thread-local) describes the last failure.  Nothing throws.
+ *   - re-entrant and thread-safe: no global mutable state besides the thread-local error
+ */
+#ifndef UPS_B200_H
+#define UPS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPS_OK 0
+#define UPS_E_INVALID (-1)   /* bad shape / null pointer / unsupported size */
+#define UPS_E_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define UPS_E_WORKSPACE (-3) /* workspace too small */
+
+const char* ups_version(void);
+const char* ups_last_error_string(void);
+/* number of kernels this library has launched on the calling thread since the last reset
+ * (bench.py's `gpu_launches`) */
+long long ups_launch_count(void);
+void ups_launch_count_reset(void);
+
+/* ---- workspace sizes --------------------------------------------------------------- */
+enum ups_op {
+    UPS_OP_TPS_SOLVE = 0,   /* none */
+    UPS_OP_POOL = 1,        /* part_pool_fwd / encode_fwd partial sums */
+    UPS_OP_INJECT_BWD = 2,  /* part_inject_bwd / decode_bwd dfeat partial sums */
+    UPS_OP_POOL_BWD = 3,    /* none */
+    UPS_OP_STEP = 4         /* ups_step_* (max over the four fused calls and their unfused stand-ins) */
+};
+size_t ups_workspace_bytes(int op, int B, int P, int K, int F);
+
+/* ---- thin-plate-spline warp -------------------------------------------------------- */
+/* make_input_tps_param(tps_param) — baselines/unsupervised-disentangling/transformations.py:59-77
+ * coord,vector [N,8,2]; offset,offset_2 [N,1,2]; t_scal [N,2]; rot_mat [N,2,2] -> t_vector [N,8,2]
+ * (the returned `coord` is the input coord unchanged). */
+int ups_tps_input_param(const float* coord, const float* vector, const float* offset, const float* offset_2,
+                        const float* t_scal, const float* rot_mat, float* t_vector, int N, void* stream);
+/* ThinPlateSpline._solve_system — transformations.py:215-235 (incl. the ::-1 flip of :95-96)
+ * coord, vector [N,8,2] as passed to ThinPlateSpline -> T [N,2,11]. */
+int ups_tps_solve(const float* coord, const float* vector, float* T, int N, void* stream);
+/* ThinPlateSpline(U, coord, vector, out_size, n_c, move, scal) — transformations.py:93-244
+ * (_meshgrid :171-188, _transform :190-213, _interpolate :114-169).
+ * U [N,H,W,C]; coord [N,8,2]; T [N,2,11] from ups_tps_solve; move [N,1,2] / scal [N,2] or both NULL;
+ * out [N,out_h,out_w,C]; mesh [N,out_h,out_w,2] = (y, x) or NULL. */
+int ups_tps_warp_fwd(const float* U, const float* coord, const float* T, const float* move, const float* scal,
+                     float* out, float* mesh, int N, int H, int W, int C, int out_h, int out_w, void* stream);
+/* gradient of ups_tps_warp_fwd w.r.t. U (4-way scatter-add; floor/clip carry no gradient).
+ * dU [N,H,W,C] is zero-filled by the call. */
+int ups_tps_warp_bwd(const float* g_out, const float* coord, const float* T, const float* move, const float* scal,
+                     float* dU, int N, int H, int W, int C, int out_h, int out_w, void* stream);
+
+/* ---- part-map softmax / hard max / straight-through / argmax ------------------------ */
+/* nn.softmax(x, spatial=False) — cub/code/nn.py:58-62, fused with the consumers at
+ * cub/code/SB_model48i/model.py:426-473: probs, optional int64 argmax labels (first index),
+ * optional straight_through_estimator(hard_max(probs,3), probs).  logits [n_pix,K]. */
+int ups_part_softmax_fwd(const float* logits, float* probs, long long* labels, float* hard_st, long long n_pix,
+                         int K, void* stream);
+/* dx = p*(g - sum_j g_j p_j)  (TF SoftmaxGrad) */
+int ups_part_softmax_bwd(const float* probs, const float* g, float* dlogits, long long n_pix, int K, void* stream);
+/* nn.spatial_softmax — cub/code/nn.py:65-71: softmax over the P axis for every (n, c); x [N,P,C]. */
+int ups_spatial_softmax_fwd(const float* x, float* probs, int N, int P, int C, void* stream);
+int ups_spatial_softmax_bwd(const float* probs, const float* g, float* dx, int N, int P, int C, void* stream);
+/* nn.hard_max(y, axis=last) — cub/code/nn.py:134-136 (every tied maximum gets 1.0) */
+int ups_hard_max_fwd(const float* y, float* out, long long n_pix, int K, void* stream);
+/* nn.straight_through_estimator(y_hard, y) forward value fl(fl(y_hard-y)+y) — cub/code/nn.py:154-168 */
+int ups_straight_through_fwd(const float* y_hard, const float* y, float* out, long long n, void* stream);
+/* tf.argmax(y, 3) — cub/code/SB_model48i/model.py:447,465,470 ; nn.mask2hotmask nn.py:2086-2089 */
+int ups_argmax_fwd(const float* y, long long* labels, long long n_pix, int K, void* stream);
+int ups_one_hot_fwd(const long long* labels, float* out, long long n_pix, int K, void* stream);
+
+/* ---- mask_parts / apply_partwise ---------------------------------------------------- */
+/* mask_parts(image, mask) — cub/code/SB_model48i/model.py:176-187.
+ * image [B,P,C], mask [B,P,K] -> parts.  part_major=0: [B,P,K,C] (the reference's layout);
+ * part_major=1: [K*B,P,C] with row k*B+b, i.e. already folded as nn.apply_partwise does
+ * (cub/code/nn.py:100-103). */
+int ups_mask_parts_fwd(const float* image, const float* mask, float* parts, int B, int P, int K, int C,
+                       int part_major, void* stream);
+/* dimage[b,p,c] = sum_k g*mask ; dmask[b,p,k] = sum_c g*image ; either output may be NULL */
+int ups_mask_parts_bwd(const float* g_parts, const float* image, const float* mask, float* dimage, float* dmask,
+                       int B, int P, int K, int C, int part_major, void* stream);
+/* the two transposes of nn.apply_partwise — cub/code/nn.py:100-103 and :108-112.
+ * fold: x [B,P,K,C] -> y [K*B,P,C];  unfold: y [K*B,P,C] -> x [B,P,K,C]. */
+int ups_partwise_fold(const float* x, float* y, int B, int P, int K, int C, void* stream);
+int ups_partwise_unfold(const float* y, float* x, int B, int P, int K, int C, void* stream);
+
+/* ---- mask-weighted pooling ---------------------------------------------------------- */
+/* grouped=1: pool_features(feature_map, mask) — deepfashion/code/foo.py:287-307
+ *            fmap [B,P,K*Fg], out[b,k,f] = scale * sum_p fmap[b,p,k*Fg+f]*mask[b,p,k]  (scale = 1/P)
+ * grouped=0: get_features(features, part_map, slim=True) — baselines/unsupervised-disentangling/ops.py:182-193
+ *            fmap [B,P,Fg],   out[b,k,f] = scale * sum_p fmap[b,p,f]*mask[b,p,k]
+ * out [B,K,Fg]; ws from ups_workspace_bytes(UPS_OP_POOL, B, P, K, Fg). */
+int ups_part_pool_fwd(const float* fmap, const float* mask, float* out, int B, int P, int K, int Fg, int grouped,
+                      float scale, void* ws, size_t ws_bytes, void* stream);
+/* dfmap / dmask may be NULL */
+int ups_part_pool_bwd(const float* g_out, const float* fmap, const float* mask, float* dfmap, float* dmask, int B,
+                      int P, int K, int Fg, int grouped, float scale, void* stream);
+
+/* ---- unpooling / projection onto the part maps ---------------------------------------- */
+/* unpool_features(feature_vectors, mask) — cub/code/SB_model48i/model.py:225-249,
+ * deepfashion/code/foo.py:462-498: out[b,p,k,f] = mask[b,p,k]*feat[b,k,f]  ([B,P,K,F]). */
+int ups_part_unpool_fwd(const float* feat, const float* mask, float* out, int B, int P, int K, int F, void* stream);
+int ups_part_unpool_bwd(const float* g_out, const float* feat, const float* mask, float* dfeat, float* dmask, int B,
+                        int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+/* reduce_sum(unpool_features(feat, mask), 3) ++ mask — cub/code/SB_model48i/model.py:482-484,
+ * without the [B,P,K,F] intermediate: inj [B,P,F+K]. */
+int ups_part_inject_fwd(const float* feat, const float* mask, float* inj, int B, int P, int K, int F, void* stream);
+/* dmask[b,p,k] = sum_f g[b,p,f]*feat[b,k,f] + g[b,p,F+k] ; dfeat[b,k,f] = sum_p mask[b,p,k]*g[b,p,f] */
+int ups_part_inject_bwd(const float* g_inj, const float* feat, const float* mask, float* dfeat, float* dmask, int B,
+                        int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+/* nn.unpool_features_gathered(feature_vectors, labels) — cub/code/nn.py:2469-2487: out [B,P,F] */
+int ups_part_gather_fwd(const float* feat, const long long* labels, float* out, int B, int P, int K, int F,
+                        void* stream);
+
+/* ---- the fused per-step path (K2..K5; K1/K6 are the TPS calls above) --------
+ * encode side (view 1): m1 = softmax(l1); mh = ST(hard_max(m1)); parts = mask_parts(img1, mh)
+ *   written part-major [K*B,P,3]; pooled[b,k,c] = mean_p mh*img1   — model.py:429,453-455,478, :50-52 */
+int ups_step_encode_fwd(const float* l1, const float* img1, float* m1, float* parts_pm, float* pooled, int B, int P,
+                        int K, void* ws, size_t ws_bytes, void* stream);
+/* decode side (view 0): m0 = softmax(l0); labels0 = argmax(m0); mh = ST(hard_max(m0));
+ *   inj = sum_k unpool(feat, mh) ++ mh   — model.py:426,434-436,447,482-484 */
+int ups_step_decode_fwd(const float* l0, const float* feat, float* m0, long long* labels0, float* inj, int B, int P,
+                        int K, int F, void* stream);
+/* backward of the decode side: dl0 = softmax_bwd(m0, inject_bwd_dmask(g_inj) + g_m0), dfeat.
+ * g_m0 (cotangent arriving at the probabilities from the losses) may be NULL. */
+int ups_step_decode_bwd(const float* g_inj, const float* m0, const float* g_m0, const float* feat, float* dl0,
+                        float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+/* backward of the encode side: dm1 = sum_c img1*(g_parts + g_pooled/P); dl1 = softmax_bwd(m1, dm1 + g_m1);
+ * dimg1 (optional) = sum_k mh*(g_parts + g_pooled/P).  g_pooled, g_m1, dimg1 may be NULL. */
+int ups_step_encode_bwd(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
+                        const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPS_B200_H */

@@ -17,8 +17,9 @@ multiply-add and never a library transcendental:
 * `exp_canon`  — Cephes `expf` (the polynomial Eigen's `pexp<float>` also uses), each
   multiply and add rounded separately.
 * `log_canon`  — Cephes `logf` (Eigen `plog<float>`), same rule.
-* `sum4_tree`  — K-way sum: blocks of 4 consecutive terms summed left to right, block
-  sums combined by a balanced adjacent-pair tree (zero padded to a power of two).
+* `sum_tree`   — K-way sum as a balanced adjacent-pair tree over the terms zero padded
+  to a power of two (invariant under XOR permutations of the leaves, so 1, 2, 4 or 8
+  lanes per pixel with a shuffle butterfly all produce the same bits).
 * `solve_canon` — 11x11 Gauss-Jordan with first-max partial pivoting in float64,
   each multiply/subtract/divide rounded separately.
 
@@ -112,23 +113,18 @@ def log_canon(x: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------- K-way sum
-def sum4_tree(e: torch.Tensor) -> torch.Tensor:
-    """Canonical sum over the last axis: blocks of 4 left-to-right, then adjacent-pair tree."""
+def sum_tree(e: torch.Tensor) -> torch.Tensor:
+    """Canonical sum over the last axis: zero pad to a power of two, add adjacent pairs
+    until one value is left:  ((e0+e1)+(e2+e3)) + ((e4+e5)+(e6+e7)) ..."""
     K = e.shape[-1]
-    pad = (-K) % 4
-    if pad:
-        e = torch.cat([e, e.new_zeros(e.shape[:-1] + (pad,))], dim=-1)
-    g = e.reshape(e.shape[:-1] + (-1, 4))
-    s = ((g[..., 0] + g[..., 1]) + g[..., 2]) + g[..., 3]
-    n = s.shape[-1]
     p2 = 1
-    while p2 < n:
+    while p2 < K:
         p2 *= 2
-    if p2 != n:
-        s = torch.cat([s, s.new_zeros(s.shape[:-1] + (p2 - n,))], dim=-1)
-    while s.shape[-1] > 1:
-        s = s[..., 0::2] + s[..., 1::2]
-    return s[..., 0]
+    if p2 != K:
+        e = torch.cat([e, e.new_zeros(e.shape[:-1] + (p2 - K,))], dim=-1)
+    while e.shape[-1] > 1:
+        e = e[..., 0::2] + e[..., 1::2]
+    return e[..., 0]
 
 
 # ---------------------------------------------------------------- 11x11 solve (float64)

@@ -7,7 +7,7 @@ Pinned against tests/golden/parts_*.npz (reference function bodies run under tf1
 """
 import torch
 
-from .canon import exp_canon, sum4_tree
+from .canon import exp_canon, sum_tree
 
 PARTS_DIM = 3      # cub/code/SB_model48i/model.py:12
 FEATURE_DIM = 4    # cub/code/SB_model48i/model.py:13
@@ -21,7 +21,7 @@ class _SoftmaxCanon(torch.autograd.Function):
     def forward(ctx, x):
         m = x.max(dim=-1, keepdim=True).values
         e = exp_canon(x - m)
-        s = sum4_tree(e)
+        s = sum_tree(e)
         p = e / s[..., None]
         ctx.save_for_backward(p)
         return p

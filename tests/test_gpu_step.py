@@ -1,0 +1,163 @@
+"""-m gpu: the fused forward+backward step (K1..K6) against the chained oracle, plus
+size-independent properties at BASELINE.json's full sizes."""
+import pytest
+import torch
+
+from oracle import step as OS
+from util import PENN_TPS, assert_bitexact, assert_close, cuda, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ups():
+    import ups_b200
+    return ups_b200
+
+
+def _run(B, S, K, F, V, use_tps=True, views_grad=False, ties=False, seed=0, tps=None):
+    from ups_b200.step import PartStep
+    kw = dict(tps=tps) if tps else {}
+    inp = make_inputs(B, S, K, F, V, seed=seed, ties=ties, **kw)
+    c = inp["cot"]
+    cot_o = dict(c, g_warped=c["g_warped"] if views_grad else None)
+    out_o, grad_o = OS.step_forward_backward([v for v in inp["views"]], inp["coord"], inp["t_vector"], inp["l0"],
+                                             inp["l1"], inp["feat"], cot_o, use_tps=use_tps, views_grad=views_grad)
+    step = PartStep(B, S, K, F, n_views=V, use_tps=use_tps, views_grad=views_grad)
+    d = cuda(inp)
+    out = step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    gw = torch.stack(d["cot"]["g_warped"]) if views_grad else None
+    grad = step.backward(d["cot"]["g_inj"], d["cot"]["g_parts"], d["cot"]["g_pooled"], d["cot"]["g_m0"],
+                         d["cot"]["g_m1"], gw)
+    torch.cuda.synchronize()
+    return step, out, grad, out_o, grad_o
+
+
+def _check(out, grad, out_o, grad_o, use_tps=True, views_grad=False):
+    if use_tps:
+        for i, w in enumerate(out_o["warped"]):
+            assert_bitexact(out["warped"][i], w, f"warped[{i}]")
+    assert_bitexact(out["m0"], out_o["m0"], "m0")
+    assert_bitexact(out["m1"], out_o["m1"], "m1")
+    assert out["labels0"].dtype == torch.int64
+    assert torch.equal(out["labels0"].cpu(), out_o["labels0"]), "labels0 must be bit-exact"
+    assert_bitexact(out["parts"], out_o["parts"], "parts (part-major)")
+    assert_close(out["pooled"], out_o["pooled"], "pooled")
+    assert_close(out["inj"], out_o["inj"], "inj")
+    for k in ("dl0", "dl1", "dfeat"):
+        assert_close(grad[k], grad_o[k], k)
+    if views_grad:
+        for i, w in enumerate(grad_o["dviews"]):
+            assert_close(grad["dviews"][i], w, f"dviews[{i}]", atol=2e-5)
+
+
+def test_config1_cub_b8(ups):
+    """BASELINE.json configs[0]: CUB 128x128, K=16, batch 8, 3 views, fixed TPS seed."""
+    step, out, grad, out_o, grad_o = _run(8, 128, 16, 64, 3)
+    assert step.fused
+    _check(out, grad, out_o, grad_o)
+
+
+@pytest.mark.parametrize("B,S,K,F,V", [(1, 32, 8, 16, 3), (3, 96, 32, 32, 2), (2, 64, 16, 64, 2), (5, 16, 16, 64, 3),
+                                       (2, 32, 8, 64, 3), (2, 32, 32, 64, 3)])
+def test_fused_shapes(ups, B, S, K, F, V):
+    step, out, grad, out_o, grad_o = _run(B, S, K, F, V, ties=True, seed=B + K, tps=PENN_TPS if V == 2 else None)
+    assert step.fused
+    _check(out, grad, out_o, grad_o)
+
+
+@pytest.mark.parametrize("B,S,K,F", [(2, 24, 25, 64), (1, 20, 16, 10), (2, 32, 4, 8)])
+def test_unfused_fallback_shapes(ups, B, S, K, F):
+    """n_parts=25 is what the reference ships (train_cub_subset_tps.yaml:132): handled by the
+    generic kernels, same parity bar."""
+    step, out, grad, out_o, grad_o = _run(B, S, K, F, 3, ties=True, seed=K)
+    assert not step.fused
+    _check(out, grad, out_o, grad_o)
+
+
+def test_views_grad_tps_backward(ups):
+    step, out, grad, out_o, grad_o = _run(3, 64, 16, 64, 3, views_grad=True, seed=4)
+    _check(out, grad, out_o, grad_o, views_grad=True)
+
+
+def test_no_tps_deepfashion(ups):
+    """DeepFashion SB_model48c has no TPS (deepfashion/code/SB_model48c/model.py:266-280)."""
+    step, out, grad, out_o, grad_o = _run(2, 64, 16, 64, 2, use_tps=False, seed=6)
+    _check(out, grad, out_o, grad_o, use_tps=False)
+
+
+def test_optional_cotangents(ups):
+    from ups_b200.step import PartStep
+    B, S, K, F = 2, 32, 16, 64
+    inp = make_inputs(B, S, K, F, 3, seed=9)
+    cot = dict(inp["cot"], g_pooled=torch.zeros(B, K, 3), g_m0=torch.zeros(B, S, S, K), g_m1=torch.zeros(B, S, S, K),
+               g_warped=None)
+    _, grad_o = OS.step_forward_backward([v for v in inp["views"]], inp["coord"], inp["t_vector"], inp["l0"],
+                                         inp["l1"], inp["feat"], cot)
+    d = cuda(inp)
+    step = PartStep(B, S, K, F)
+    step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    grad = step.backward(d["cot"]["g_inj"], d["cot"]["g_parts"])
+    for k in ("dl0", "dl1", "dfeat"):
+        assert_close(grad[k], grad_o[k], k)
+
+
+def test_run_to_run_determinism(ups):
+    from ups_b200.step import PartStep
+    B, S, K, F = 4, 64, 16, 64
+    d = cuda(make_inputs(B, S, K, F, 3, seed=1))
+    step = PartStep(B, S, K, F)
+    res = []
+    for _ in range(2):
+        step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+        g = step.backward(d["cot"]["g_inj"], d["cot"]["g_parts"], d["cot"]["g_pooled"], d["cot"]["g_m0"], d["cot"]["g_m1"])
+        torch.cuda.synchronize()
+        res.append({k: v.clone() for k, v in dict(g, pooled=step.pooled, inj=step.inj).items()})
+    for k in res[0]:
+        assert torch.equal(res[0][k], res[1][k]), f"{k} differs between two runs (no atomics on this path)"
+
+
+def test_full_size_properties_cub_b256(ups):
+    """BASELINE.json configs[1] (CUB 128x128, K=16, batch 256): too big for the CPU oracle, so
+    check size-independent identities on the device, and exact agreement of a B=8 slice with a
+    B=8 run (every op on the path is per-sample)."""
+    from ups_b200.step import PartStep
+    B, S, K, F = 256, 128, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    views = torch.rand(3, B, S, S, 3, device="cuda", generator=g) * 2 - 1
+    l0 = torch.randn(B, S, S, K, device="cuda", generator=g)
+    l1 = torch.randn(B, S, S, K, device="cuda", generator=g)
+    feat = torch.randn(B, K, F, device="cuda", generator=g)
+    small = make_inputs(B, 8, K, F, 3, seed=0)          # only for 2B sets of TPS parameters
+    coord, tv = small["coord"].cuda(), small["t_vector"].cuda()
+    step = PartStep(B, S, K, F)
+    out = step.forward(views, coord, tv, l0, l1, feat)
+    g_inj = torch.randn(B, S, S, F + K, device="cuda", generator=g)
+    g_parts = torch.randn(K * B, S, S, 3, device="cuda", generator=g)
+    grad = step.backward(g_inj, g_parts)
+    torch.cuda.synchronize()
+    m0, m1, lab = out["m0"], out["m1"], out["labels0"]
+    assert torch.equal(lab, torch.argmax(m0, 3))                       # labels = first argmax of probs
+    assert (m0.sum(-1) - 1).abs().max() < 1e-6 and (m1.sum(-1) - 1).abs().max() < 1e-6
+    mh0 = out["inj"][..., F:]
+    assert torch.equal(mh0 != 0, m0 == m0.max(-1, keepdim=True).values)  # hard mask marks exactly the maxima
+    sel = feat[torch.arange(B, device="cuda")[:, None, None], lab] * mh0.max(-1, keepdim=True).values
+    single = (mh0 != 0).sum(-1) == 1
+    assert torch.equal(out["inj"][..., :F][single], sel[single])       # one-hot rows: inj == mon*feat[label]
+    parts = out["parts"].view(K, B, S, S, 3)
+    mh1 = (m1 == m1.max(-1, keepdim=True).values)
+    assert torch.equal(parts != 0, (mh1.permute(3, 0, 1, 2)[..., None] & (out["warped"][1] != 0)[None]))
+    assert (grad["dl0"].sum(-1).abs().max() < 1e-3) and (grad["dl1"].sum(-1).abs().max() < 1e-3)  # softmax-bwd rows sum to 0
+    # per-sample independence: rerun the first 8 samples alone, results must be bit-identical
+    s8 = PartStep(8, S, K, F)
+    c8 = torch.cat([coord[:8], coord[B:B + 8]])
+    t8 = torch.cat([tv[:8], tv[B:B + 8]])
+    o8 = s8.forward(views[:, :8].contiguous(), c8, t8, l0[:8].contiguous(), l1[:8].contiguous(), feat[:8].contiguous())
+    g8 = s8.backward(g_inj[:8].contiguous(), g_parts.view(K, B, S, S, 3)[:, :8].reshape(K * 8, S, S, 3).contiguous())
+    torch.cuda.synchronize()
+    for k in ("m0", "m1", "labels0", "inj"):
+        assert torch.equal(o8[k], out[k][:8]), k
+    assert torch.equal(o8["warped"][0], out["warped"][0][:8])
+    assert torch.equal(g8["dl0"], grad["dl0"][:8]) and torch.equal(g8["dl1"], grad["dl1"][:8])
+    assert_close(g8["dfeat"], grad["dfeat"][:8].cpu(), "dfeat slice")   # split count differs with B
+    assert_close(o8["pooled"], out["pooled"][:8].cpu(), "pooled slice")

@@ -1,0 +1,93 @@
+"""ctypes binding of libups_b200.so (include/ups_b200.h).  No fallback: if the library is
+missing or a call fails, this raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+c_f = ctypes.c_void_p      # device pointers travel as integers
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_sz = ctypes.c_size_t
+c_fl = ctypes.c_float
+
+_SIGS = {
+    "ups_tps_input_param": [c_f] * 7 + [c_i, c_f],
+    "ups_tps_solve": [c_f, c_f, c_f, c_i, c_f],
+    "ups_tps_warp_fwd": [c_f] * 7 + [c_i] * 6 + [c_f],
+    "ups_tps_warp_bwd": [c_f] * 6 + [c_i] * 6 + [c_f],
+    "ups_part_softmax_fwd": [c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_part_softmax_bwd": [c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_spatial_softmax_fwd": [c_f, c_f, c_i, c_i, c_i, c_f],
+    "ups_spatial_softmax_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
+    "ups_hard_max_fwd": [c_f, c_f, c_ll, c_i, c_f],
+    "ups_straight_through_fwd": [c_f, c_f, c_f, c_ll, c_f],
+    "ups_argmax_fwd": [c_f, c_f, c_ll, c_i, c_f],
+    "ups_one_hot_fwd": [c_f, c_f, c_ll, c_i, c_f],
+    "ups_mask_parts_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f],
+    "ups_mask_parts_bwd": [c_f] * 5 + [c_i] * 5 + [c_f],
+    "ups_partwise_fold": [c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "ups_partwise_unfold": [c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "ups_part_pool_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f],
+    "ups_part_pool_bwd": [c_f] * 5 + [c_i] * 5 + [c_fl, c_f],
+    "ups_part_unpool_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "ups_part_unpool_bwd": [c_f] * 5 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_part_inject_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "ups_part_inject_bwd": [c_f] * 5 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_part_gather_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "ups_step_encode_fwd": [c_f] * 5 + [c_i] * 3 + [c_f, c_sz, c_f],
+    "ups_step_decode_fwd": [c_f] * 5 + [c_i] * 4 + [c_f],
+    "ups_step_decode_bwd": [c_f] * 6 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_step_encode_bwd": [c_f] * 7 + [c_i] * 3 + [c_f],
+}
+
+OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP = 0, 1, 2, 3, 4
+
+
+class UpsError(RuntimeError):
+    pass
+
+
+def _load():
+    path = os.environ.get("UPS_B200_LIB", _build.LIB)
+    if not os.path.exists(path):
+        raise UpsError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(path)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_i
+    lib.ups_version.restype = ctypes.c_char_p
+    lib.ups_last_error_string.restype = ctypes.c_char_p
+    lib.ups_launch_count.restype = c_ll
+    lib.ups_launch_count_reset.restype = None
+    lib.ups_workspace_bytes.argtypes = [c_i] * 5
+    lib.ups_workspace_bytes.restype = c_sz
+    return lib, path
+
+
+lib, LIB_PATH = _load()
+
+
+def call(name, *args):
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise UpsError(f"{name} -> {rc}: {lib.ups_last_error_string().decode()}")
+
+
+def version():
+    return lib.ups_version().decode()
+
+
+def launch_count():
+    return int(lib.ups_launch_count())
+
+
+def launch_count_reset():
+    lib.ups_launch_count_reset()
+
+
+def workspace_bytes(op, B, P, K, F):
+    return int(lib.ups_workspace_bytes(op, B, P, K, F))

@@ -1,0 +1,79 @@
+"""Drop-in for the module-level helpers of the reference's model files
+(cub/code/SB_model48i/model.py, pennaction/code/SB_model48i/model.py,
+deepfashion/code/SB_model48c/model.py) that sit on the part-disentanglement path."""
+import torch
+
+from . import nn, ops
+from . import tps as _tps
+
+PARTS_DIM = 3      # cub/code/SB_model48i/model.py:12
+FEATURE_DIM = 4    # cub/code/SB_model48i/model.py:13
+
+
+def mask_parts(image, mask):
+    """cub/code/SB_model48i/model.py:176-187 — [B,H,W,3],[B,H,W,parts] -> [B,H,W,parts,3]."""
+    bs, h, w, n_features = image.shape
+    mshape = list(mask.shape)
+    assert mshape[0] == bs and mshape[1] == h and mshape[2] == w, mshape
+    return ops.mask_parts(image, mask, False)
+
+
+def mask_parts_partmajor(image, mask):
+    """mask_parts followed by nn.apply_partwise's fold (cub/code/nn.py:100-103) in one pass:
+    [B,H,W,3],[B,H,W,parts] -> [parts*B,H,W,3] with row k*B+b."""
+    bs, h, w, _ = image.shape
+    mshape = list(mask.shape)
+    assert mshape[0] == bs and mshape[1] == h and mshape[2] == w, mshape
+    return ops.mask_parts(image, mask, True)
+
+
+def encode_parts(part_image, encoder):
+    """cub/code/SB_model48i/model.py:214-222 — [B,H,W,parts,3] -> [B,parts,features]."""
+    b, h, w, parts, channels = part_image.shape
+    part_encodings = nn.apply_partwise(part_image, encoder)
+    part_encodings = part_encodings.reshape(b, parts, -1)
+    out_shape = list(part_encodings.shape)
+    assert out_shape[0] == b and out_shape[1] == parts
+    return part_encodings
+
+
+def unpool_features(feature_vectors, mask, reshape=False):
+    """cub/code/SB_model48i/model.py:225-249 ; deepfashion/code/foo.py:462-498 (`reshape`).
+    feature_vectors [B,parts,F], mask [B,h,w,parts] -> [B,h,w,parts,F]."""
+    bs, h, w, n_parts = mask.shape
+    fshape = list(feature_vectors.shape)
+    assert len(fshape) == 3, fshape
+    assert fshape[0] == bs and fshape[1] == n_parts, fshape
+    out = ops.part_unpool(feature_vectors, mask)
+    if reshape:
+        out = out.reshape(bs, h, w, n_parts * fshape[2])
+    return out
+
+
+def inject_features(feature_vectors, mask):
+    """tf.concat([tf.reduce_sum(unpool_features(f, m), 3), m], 3) — the three lines at
+    cub/code/SB_model48i/model.py:482-484 (and :493-500) without the [B,h,w,parts,F]
+    intermediate: -> [B,h,w,F+parts]."""
+    bs, h, w, n_parts = mask.shape
+    fshape = list(feature_vectors.shape)
+    assert len(fshape) == 3, fshape
+    assert fshape[0] == bs and fshape[1] == n_parts, fshape
+    return ops.part_inject(feature_vectors, mask)
+
+
+def make_tps(views, tps_parameters, generator=None):
+    """TrainModel.make_tps — cub/code/SB_model48i/model.py:282-311 (3 views; the target view
+    re-uses the first-half parameters) / pennaction/code/SB_model48i/model.py:281-303 (2 views)."""
+    bs = views[0].shape[0]
+    img_batch = torch.cat(list(views[:2]), dim=0)
+    bs_doubled = img_batch.shape[0]
+    tps_param_dict = _tps.tps_parameters(bs_doubled, generator=generator, device=img_batch.device,
+                                         **tps_parameters)
+    coord, vector = _tps.make_input_tps_param(tps_param_dict)
+    t_images, t_mesh = _tps.ThinPlateSpline(img_batch, coord, vector, img_batch.shape[1], img_batch.shape[-1])
+    augmented_views = list(torch.split(t_images, bs, dim=0))
+    if len(views) > 2:
+        t_images, t_mesh = _tps.ThinPlateSpline(views[2], coord[:bs], vector[:bs], views[2].shape[1],
+                                                views[2].shape[-1])
+        augmented_views.append(t_images)
+    return augmented_views

@@ -1,0 +1,424 @@
+"""PyTorch custom operators `ups::*` over the C ABI (include/ups_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams and records the autograd graph;
+every numeric result comes from the sm_100a kernels in csrc/.  There is no CPU
+implementation: a CPU tensor raises.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi as C
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: Tensor, name="tensor") -> Tensor:
+    if not t.is_cuda:
+        raise C.UpsError(f"ups_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != torch.float32:
+        raise C.UpsError(f"ups_b200: {name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, like: Tensor) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=like.device)
+
+
+def _op(name, schema_fn, fake_fn, backward=None, setup=None):
+    op = torch.library.custom_op(f"ups::{name}", mutates_args=())(schema_fn)
+    op.register_fake(fake_fn)
+    if backward is not None:
+        op.register_autograd(backward, setup_context=setup)
+    return op
+
+
+# ------------------------------------------------------------------ TPS
+def _tps_input_param(coord: Tensor, vector: Tensor, offset: Tensor, offset_2: Tensor, t_scal: Tensor,
+                     rot_mat: Tensor) -> Tensor:
+    a = [_f32(t) for t in (coord, vector, offset, offset_2, t_scal, rot_mat)]
+    N = a[0].shape[0]
+    out = torch.empty_like(a[0])
+    C.call("ups_tps_input_param", *[t.data_ptr() for t in a], out.data_ptr(), N, _stream())
+    return out
+
+
+tps_input_param = _op("tps_input_param", _tps_input_param, lambda c, v, o, o2, s, r: torch.empty_like(c))
+
+
+def _tps_solve(coord: Tensor, vector: Tensor) -> Tensor:
+    coord, vector = _f32(coord), _f32(vector)
+    N = coord.shape[0]
+    T = torch.empty(N, 2, 11, dtype=torch.float32, device=coord.device)
+    C.call("ups_tps_solve", coord.data_ptr(), vector.data_ptr(), T.data_ptr(), N, _stream())
+    return T
+
+
+tps_solve = _op("tps_solve", _tps_solve, lambda c, v: c.new_empty(c.shape[0], 2, 11))
+
+
+def _tps_warp(U: Tensor, coord: Tensor, T: Tensor, out_size: int, move: Optional[Tensor],
+              scal: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    U, coord, T = _f32(U, "U"), _f32(coord, "coord"), _f32(T, "T")
+    move = None if move is None else _f32(move, "move")
+    scal = None if scal is None else _f32(scal, "scal")
+    N, H, W, Cc = U.shape
+    out = torch.empty(N, out_size, out_size, Cc, dtype=torch.float32, device=U.device)
+    mesh = torch.empty(N, out_size, out_size, 2, dtype=torch.float32, device=U.device)
+    C.call("ups_tps_warp_fwd", U.data_ptr(), coord.data_ptr(), T.data_ptr(), _ptr(move), _ptr(scal),
+           out.data_ptr(), mesh.data_ptr(), N, H, W, Cc, out_size, out_size, _stream())
+    return out, mesh
+
+
+def _tps_warp_fake(U, coord, T, out_size, move, scal):
+    N, H, W, Cc = U.shape
+    return U.new_empty(N, out_size, out_size, Cc), U.new_empty(N, out_size, out_size, 2)
+
+
+def _tps_warp_setup(ctx, inputs, output):
+    U, coord, T, out_size, move, scal = inputs
+    ctx.save_for_backward(coord, T, *([move, scal] if move is not None else []))
+    ctx.has_move = move is not None
+    ctx.shape = tuple(U.shape)
+    ctx.out_size = out_size
+
+
+def _tps_warp_bwd(ctx, g_out, g_mesh):
+    saved = ctx.saved_tensors
+    coord, T = saved[0], saved[1]
+    move, scal = (saved[2], saved[3]) if ctx.has_move else (None, None)
+    dU = tps_warp_grad(g_out, coord, T, list(ctx.shape), ctx.out_size, move, scal)
+    return dU, None, None, None, None, None
+
+
+def _tps_warp_grad(g_out: Tensor, coord: Tensor, T: Tensor, shape: list[int], out_size: int,
+                   move: Optional[Tensor], scal: Optional[Tensor]) -> Tensor:
+    g_out = _f32(g_out, "g_out")
+    N, H, W, Cc = shape
+    dU = torch.empty(N, H, W, Cc, dtype=torch.float32, device=g_out.device)
+    C.call("ups_tps_warp_bwd", g_out.data_ptr(), coord.data_ptr(), T.data_ptr(), _ptr(move), _ptr(scal),
+           dU.data_ptr(), N, H, W, Cc, out_size, out_size, _stream())
+    return dU
+
+
+tps_warp_grad = _op("tps_warp_grad", _tps_warp_grad,
+                    lambda g, c, T, shape, o, m, s: g.new_empty(shape))
+tps_warp = _op("tps_warp", _tps_warp, _tps_warp_fake, _tps_warp_bwd, _tps_warp_setup)
+
+
+# ------------------------------------------------------------------ softmax family
+def _part_softmax_full(logits: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    x = _f32(logits, "logits")
+    K = x.shape[-1]
+    n_pix = x.numel() // K
+    probs = torch.empty_like(x)
+    hard = torch.empty_like(x)
+    labels = torch.empty(x.shape[:-1], dtype=torch.int64, device=x.device)
+    C.call("ups_part_softmax_fwd", x.data_ptr(), probs.data_ptr(), labels.data_ptr(), hard.data_ptr(), n_pix, K,
+           _stream())
+    return probs, labels, hard
+
+
+def _part_softmax(logits: Tensor) -> Tensor:
+    x = _f32(logits, "logits")
+    K = x.shape[-1]
+    probs = torch.empty_like(x)
+    C.call("ups_part_softmax_fwd", x.data_ptr(), probs.data_ptr(), None, None, x.numel() // K, K, _stream())
+    return probs
+
+
+def _part_softmax_grad(probs: Tensor, g: Tensor) -> Tensor:
+    probs, g = _f32(probs), _f32(g)
+    K = probs.shape[-1]
+    dx = torch.empty_like(probs)
+    C.call("ups_part_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), probs.numel() // K, K, _stream())
+    return dx
+
+
+part_softmax_grad = _op("part_softmax_grad", _part_softmax_grad, lambda p, g: torch.empty_like(p))
+part_softmax = _op("part_softmax", _part_softmax, lambda x: torch.empty_like(x),
+                   lambda ctx, g: part_softmax_grad(ctx.saved_tensors[0], g),
+                   lambda ctx, inputs, output: ctx.save_for_backward(output))
+
+
+def _psf_bwd(ctx, g_probs, g_labels, g_hard):
+    # straight-through: the hard mask passes its cotangent unchanged to the probabilities
+    (p,) = ctx.saved_tensors
+    g = g_probs if g_hard is None else (g_hard if g_probs is None else g_probs + g_hard)
+    return part_softmax_grad(p, g)
+
+
+part_softmax_full = _op(
+    "part_softmax_full", _part_softmax_full,
+    lambda x: (torch.empty_like(x), x.new_empty(x.shape[:-1], dtype=torch.int64), torch.empty_like(x)),
+    _psf_bwd, lambda ctx, inputs, output: ctx.save_for_backward(output[0]))
+
+
+def _spatial_softmax(x: Tensor) -> Tensor:
+    x = _f32(x)
+    N, H, W, Cc = x.shape
+    out = torch.empty_like(x)
+    C.call("ups_spatial_softmax_fwd", x.data_ptr(), out.data_ptr(), N, H * W, Cc, _stream())
+    return out
+
+
+def _spatial_softmax_grad(probs: Tensor, g: Tensor) -> Tensor:
+    probs, g = _f32(probs), _f32(g)
+    N, H, W, Cc = probs.shape
+    dx = torch.empty_like(probs)
+    C.call("ups_spatial_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), N, H * W, Cc, _stream())
+    return dx
+
+
+spatial_softmax_grad = _op("spatial_softmax_grad", _spatial_softmax_grad, lambda p, g: torch.empty_like(p))
+spatial_softmax = _op("spatial_softmax", _spatial_softmax, lambda x: torch.empty_like(x),
+                      lambda ctx, g: spatial_softmax_grad(ctx.saved_tensors[0], g),
+                      lambda ctx, inputs, output: ctx.save_for_backward(output))
+
+
+def _hard_max(y: Tensor) -> Tensor:
+    y = _f32(y)
+    K = y.shape[-1]
+    out = torch.empty_like(y)
+    C.call("ups_hard_max_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream())
+    return out
+
+
+hard_max = _op("hard_max", _hard_max, lambda y: torch.empty_like(y))   # tf.equal: no gradient
+
+
+def _straight_through(y_hard: Tensor, y: Tensor) -> Tensor:
+    y_hard, y = _f32(y_hard), _f32(y)
+    out = torch.empty_like(y)
+    C.call("ups_straight_through_fwd", y_hard.data_ptr(), y.data_ptr(), out.data_ptr(), y.numel(), _stream())
+    return out
+
+
+straight_through = _op("straight_through", _straight_through, lambda h, y: torch.empty_like(y),
+                       lambda ctx, g: (None, g), lambda ctx, inputs, output: None)
+
+
+def _argmax(y: Tensor) -> Tensor:
+    y = _f32(y)
+    K = y.shape[-1]
+    out = torch.empty(y.shape[:-1], dtype=torch.int64, device=y.device)
+    C.call("ups_argmax_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream())
+    return out
+
+
+argmax = _op("argmax", _argmax, lambda y: y.new_empty(y.shape[:-1], dtype=torch.int64))
+
+
+def _one_hot(labels: Tensor, depth: int) -> Tensor:
+    labels = labels.contiguous()
+    out = torch.empty(*labels.shape, depth, dtype=torch.float32, device=labels.device)
+    C.call("ups_one_hot_fwd", labels.data_ptr(), out.data_ptr(), labels.numel(), depth, _stream())
+    return out
+
+
+one_hot = _op("one_hot", _one_hot, lambda l, d: l.new_empty(*l.shape, d, dtype=torch.float32))
+
+
+# ------------------------------------------------------------------ mask_parts / apply_partwise
+def _dims_bpk(image: Tensor, mask: Tensor):
+    B = image.shape[0]
+    P = image.numel() // (B * image.shape[-1]) if B else 0
+    return B, P, mask.shape[-1], image.shape[-1]
+
+
+def _mask_parts(image: Tensor, mask: Tensor, part_major: bool) -> Tensor:
+    image, mask = _f32(image, "image"), _f32(mask, "mask")
+    B, P, K, Cc = _dims_bpk(image, mask)
+    sp = image.shape[1:-1]
+    out = torch.empty((K * B, *sp, Cc) if part_major else (B, *sp, K, Cc), dtype=torch.float32, device=image.device)
+    C.call("ups_mask_parts_fwd", image.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, Cc, int(part_major),
+           _stream())
+    return out
+
+
+def _mask_parts_fake(image, mask, part_major):
+    B, K, Cc = image.shape[0], mask.shape[-1], image.shape[-1]
+    sp = image.shape[1:-1]
+    return image.new_empty((K * B, *sp, Cc) if part_major else (B, *sp, K, Cc))
+
+
+def _mask_parts_grad(g: Tensor, image: Tensor, mask: Tensor, part_major: bool) -> Tuple[Tensor, Tensor]:
+    g, image, mask = _f32(g), _f32(image), _f32(mask)
+    B, P, K, Cc = _dims_bpk(image, mask)
+    dimage, dmask = torch.empty_like(image), torch.empty_like(mask)
+    C.call("ups_mask_parts_bwd", g.data_ptr(), image.data_ptr(), mask.data_ptr(), dimage.data_ptr(), dmask.data_ptr(),
+           B, P, K, Cc, int(part_major), _stream())
+    return dimage, dmask
+
+
+mask_parts_grad = _op("mask_parts_grad", _mask_parts_grad,
+                      lambda g, i, m, pm: (torch.empty_like(i), torch.empty_like(m)))
+
+
+def _mask_parts_bwd(ctx, g):
+    image, mask = ctx.saved_tensors
+    di, dm = mask_parts_grad(g, image, mask, ctx.pm)
+    return di, dm, None
+
+
+def _mask_parts_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.pm = inputs[2]
+
+
+mask_parts = _op("mask_parts", _mask_parts, _mask_parts_fake, _mask_parts_bwd, _mask_parts_setup)
+
+
+def _partwise_fold(x: Tensor) -> Tensor:
+    x = _f32(x)
+    B, K, Cc = x.shape[0], x.shape[-2], x.shape[-1]
+    sp = x.shape[1:-2]
+    P = x.numel() // (B * K * Cc) if B else 0
+    y = torch.empty(K * B, *sp, Cc, dtype=torch.float32, device=x.device)
+    C.call("ups_partwise_fold", x.data_ptr(), y.data_ptr(), B, P, K, Cc, _stream())
+    return y
+
+
+def _partwise_unfold(y: Tensor, parts: int) -> Tensor:
+    y = _f32(y)
+    KB, Cc = y.shape[0], y.shape[-1]
+    B = KB // parts
+    sp = y.shape[1:-1]
+    P = y.numel() // (KB * Cc) if KB else 0
+    x = torch.empty(B, *sp, parts, Cc, dtype=torch.float32, device=y.device)
+    C.call("ups_partwise_unfold", y.data_ptr(), x.data_ptr(), B, P, parts, Cc, _stream())
+    return x
+
+
+partwise_fold = _op("partwise_fold", _partwise_fold,
+                    lambda x: x.new_empty(x.shape[-2] * x.shape[0], *x.shape[1:-2], x.shape[-1]),
+                    lambda ctx, g: partwise_unfold(g, ctx.parts),
+                    lambda ctx, inputs, output: setattr(ctx, "parts", inputs[0].shape[-2]))
+partwise_unfold = _op("partwise_unfold", _partwise_unfold,
+                      lambda y, parts: y.new_empty(y.shape[0] // parts, *y.shape[1:-1], parts, y.shape[-1]),
+                      lambda ctx, g: (partwise_fold(g), None), lambda ctx, inputs, output: None)
+
+
+# ------------------------------------------------------------------ pooling
+def _part_pool(fmap: Tensor, mask: Tensor, grouped: bool, scale: float) -> Tensor:
+    fmap, mask = _f32(fmap, "feature_map"), _f32(mask, "mask")
+    B, K, nf = fmap.shape[0], mask.shape[-1], fmap.shape[-1]
+    P = mask.numel() // (B * K) if B else 0
+    Fg = nf // K if grouped else nf
+    out = torch.empty(B, K, Fg, dtype=torch.float32, device=fmap.device)
+    ws = _ws(C.workspace_bytes(C.OP_POOL, B, P, K, Fg), fmap)
+    C.call("ups_part_pool_fwd", fmap.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, Fg, int(grouped), scale,
+           ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def _part_pool_fake(fmap, mask, grouped, scale):
+    K = mask.shape[-1]
+    return fmap.new_empty(fmap.shape[0], K, fmap.shape[-1] // K if grouped else fmap.shape[-1])
+
+
+def _part_pool_grad(g: Tensor, fmap: Tensor, mask: Tensor, grouped: bool, scale: float) -> Tuple[Tensor, Tensor]:
+    g, fmap, mask = _f32(g), _f32(fmap), _f32(mask)
+    B, K, nf = fmap.shape[0], mask.shape[-1], fmap.shape[-1]
+    P = mask.numel() // (B * K) if B else 0
+    Fg = nf // K if grouped else nf
+    dfmap, dmask = torch.empty_like(fmap), torch.empty_like(mask)
+    C.call("ups_part_pool_bwd", g.data_ptr(), fmap.data_ptr(), mask.data_ptr(), dfmap.data_ptr(), dmask.data_ptr(),
+           B, P, K, Fg, int(grouped), scale, _stream())
+    return dfmap, dmask
+
+
+part_pool_grad = _op("part_pool_grad", _part_pool_grad,
+                     lambda g, f, m, gr, s: (torch.empty_like(f), torch.empty_like(m)))
+
+
+def _part_pool_bwd(ctx, g):
+    fmap, mask = ctx.saved_tensors
+    df, dm = part_pool_grad(g, fmap, mask, ctx.grouped, ctx.scale)
+    return df, dm, None, None
+
+
+def _part_pool_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.grouped, ctx.scale = inputs[2], inputs[3]
+
+
+part_pool = _op("part_pool", _part_pool, _part_pool_fake, _part_pool_bwd, _part_pool_setup)
+
+
+# ------------------------------------------------------------------ unpool / inject / gather
+def _bpkf(feat: Tensor, mask: Tensor):
+    B, K, F = feat.shape
+    P = mask.numel() // (B * K) if B else 0
+    return B, P, K, F
+
+
+def _part_unpool(feat: Tensor, mask: Tensor) -> Tensor:
+    feat, mask = _f32(feat, "feature_vectors"), _f32(mask, "mask")
+    B, P, K, F = _bpkf(feat, mask)
+    out = torch.empty(*mask.shape, F, dtype=torch.float32, device=feat.device)
+    C.call("ups_part_unpool_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    return out
+
+
+def _part_unpool_grad(g: Tensor, feat: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    g, feat, mask = _f32(g), _f32(feat), _f32(mask)
+    B, P, K, F = _bpkf(feat, mask)
+    dfeat, dmask = torch.empty_like(feat), torch.empty_like(mask)
+    ws = _ws(C.workspace_bytes(C.OP_POOL, B, P, K, F), feat)
+    C.call("ups_part_unpool_bwd", g.data_ptr(), feat.data_ptr(), mask.data_ptr(), dfeat.data_ptr(), dmask.data_ptr(),
+           B, P, K, F, ws.data_ptr(), ws.numel(), _stream())
+    return dfeat, dmask
+
+
+part_unpool_grad = _op("part_unpool_grad", _part_unpool_grad,
+                       lambda g, f, m: (torch.empty_like(f), torch.empty_like(m)))
+part_unpool = _op("part_unpool", _part_unpool, lambda f, m: m.new_empty(*m.shape, f.shape[-1]),
+                  lambda ctx, g: part_unpool_grad(g, *ctx.saved_tensors),
+                  lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+def _part_inject(feat: Tensor, mask: Tensor) -> Tensor:
+    feat, mask = _f32(feat, "feature_vectors"), _f32(mask, "mask")
+    B, P, K, F = _bpkf(feat, mask)
+    out = torch.empty(*mask.shape[:-1], F + K, dtype=torch.float32, device=feat.device)
+    C.call("ups_part_inject_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    return out
+
+
+def _part_inject_grad(g: Tensor, feat: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    g, feat, mask = _f32(g), _f32(feat), _f32(mask)
+    B, P, K, F = _bpkf(feat, mask)
+    dfeat, dmask = torch.empty_like(feat), torch.empty_like(mask)
+    ws = _ws(C.workspace_bytes(C.OP_INJECT_BWD, B, P, K, F), feat)
+    C.call("ups_part_inject_bwd", g.data_ptr(), feat.data_ptr(), mask.data_ptr(), dfeat.data_ptr(), dmask.data_ptr(),
+           B, P, K, F, ws.data_ptr(), ws.numel(), _stream())
+    return dfeat, dmask
+
+
+part_inject_grad = _op("part_inject_grad", _part_inject_grad,
+                       lambda g, f, m: (torch.empty_like(f), torch.empty_like(m)))
+part_inject = _op("part_inject", _part_inject,
+                  lambda f, m: m.new_empty(*m.shape[:-1], f.shape[-1] + m.shape[-1]),
+                  lambda ctx, g: part_inject_grad(g, *ctx.saved_tensors),
+                  lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+def _part_gather(feat: Tensor, labels: Tensor) -> Tensor:
+    feat = _f32(feat, "feature_vectors")
+    labels = labels.to(torch.int64).contiguous()
+    B, K, F = feat.shape
+    P = labels.numel() // B if B else 0
+    out = torch.empty(*labels.shape, F, dtype=torch.float32, device=feat.device)
+    C.call("ups_part_gather_fwd", feat.data_ptr(), labels.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    return out
+
+
+part_gather = _op("part_gather", _part_gather, lambda f, l: f.new_empty(*l.shape, f.shape[-1]))

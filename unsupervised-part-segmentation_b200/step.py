@@ -1,0 +1,165 @@
+"""The fused per-step part-disentanglement path (forward + backward) on one GPU.
+
+What the reference builds per training step in TrainModel.define_graph
+(cub/code/SB_model48i/model.py:337,426-485) and differentiates with tf.gradients:
+
+    warped          = make_tps(views)                                   model.py:282-311
+    m0, m1          = softmax(l0), softmax(l1)                          model.py:426-430
+    labels0         = argmax(m0, 3)                                     model.py:447,470
+    m0h, m1h        = ST(hard_max(m0)), ST(hard_max(m1))                model.py:434-436,453-455
+    parts           = apply_partwise-fold(mask_parts(warped[1], m1h))   model.py:478 ; nn.py:100-103
+    pooled          = mean_hw(parts)        (tail of e_alpha)           model.py:50-52
+    inj             = concat(sum_k unpool_features(feat, m0h), m0h)     model.py:482-484
+
+The CNNs between those pieces are not part of the path: `l0`, `l1` (mask decoder output) and
+`feat` (appearance encoder output) are inputs, and the cotangents of every output are inputs
+to `backward`.  All buffers are allocated once in __init__ (180 GB HBM: the B=256 CUB step
+holds ~3.6 GB); forward/backward only enqueue kernels on the current stream.
+"""
+import torch
+
+from . import _cabi as C
+
+
+def _cur_stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class PartStep:
+    def __init__(self, batch_size, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
+                 views_grad=False, device="cuda"):
+        B, S, K, F, V = int(batch_size), int(spatial_size), int(n_parts), int(local_app_size), int(n_views)
+        self.B, self.S, self.K, self.F, self.V = B, S, K, F, V
+        self.P = S * S
+        self.use_tps = bool(use_tps) and V >= 2
+        self.views_grad = bool(views_grad)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise C.UpsError("PartStep needs a CUDA device: there is no CPU path")
+        self.fused = K in (8, 16, 32) and F in (16, 32, 64) and self.P % 32 == 0
+        f32 = dict(dtype=torch.float32, device=self.device)
+        e = torch.empty
+        self.T = e(2 * B, 2, 11, **f32)
+        self.warped = e(max(V, 2), B, S, S, 3, **f32) if self.use_tps else None
+        self.m0, self.m1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
+        self.labels0 = e(B, S, S, dtype=torch.int64, device=self.device)
+        self.parts = e(K * B, S, S, 3, **f32)
+        self.pooled = e(B, K, 3, **f32)
+        self.inj = e(B, S, S, F + K, **f32)
+        self.dl0, self.dl1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
+        self.dfeat = e(B, K, F, **f32)
+        nws = C.workspace_bytes(C.OP_STEP, B, self.P, K, F)
+        self.ws = e(nws, dtype=torch.uint8, device=self.device)
+        if self.views_grad:
+            self.dimg1 = e(B, S, S, 3, **f32)
+            self.dviews = e(max(V, 2), B, S, S, 3, **f32)
+            self.gw = e(max(V, 2), B, S, S, 3, **f32)
+        if not self.fused:
+            self.mh0, self.mh1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
+            self.dm = e(B, S, S, K, **f32)
+            self.dm2 = e(B, S, S, K, **f32)
+            self.dfm = e(B, S, S, 3, **f32)
+        self._img1 = None
+        self._feat = None
+        self._coord = None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, views, coord, t_vector, l0, l1, feat):
+        """views [V,B,S,S,3] (view0, view1[, view0_target]); coord, t_vector [2B,8,2] from
+        make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict of views into
+        the step's persistent output buffers."""
+        B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
+        st = _cur_stream()
+        assert views.is_contiguous() and l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
+        assert tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
+        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        if self.use_tps:
+            assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
+            C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
+            C.call("ups_tps_warp_fwd", views.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                   self.warped.data_ptr(), None, 2 * B, S, S, 3, S, S, st)
+            if V > 2:  # the target view shares view0's warp (model.py:306-309)
+                C.call("ups_tps_warp_fwd", views[2].data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                       self.warped[2].data_ptr(), None, B, S, S, 3, S, S, st)
+            warped = self.warped
+            self._coord = coord
+        else:
+            warped = views
+        img1 = warped[1]
+        self._img1, self._feat = img1, feat
+        if self.fused:
+            C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+                   self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
+            C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
+                   self.inj.data_ptr(), B, P, K, F, st)
+        else:
+            C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
+            C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
+            C.call("ups_part_pool_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.pooled.data_ptr(), B, P, K, 3, 0,
+                   1.0 / P, self.ws.data_ptr(), self.ws.numel(), st)
+            C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
+                   self.mh0.data_ptr(), B * P, K, st)
+            C.call("ups_part_inject_fwd", feat.data_ptr(), self.mh0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
+        return dict(warped=warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
+                    pooled=self.pooled, inj=self.inj)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None):
+        """Cotangents: g_inj [B,S,S,F+K], g_parts [K*B,S,S,3] (part-major), g_pooled [B,K,3],
+        g_m0/g_m1 [B,S,S,K] (from the mask losses), g_warped [V,B,S,S,3] (views_grad only).
+        Returns dict(dl0, dl1, dfeat[, dviews])."""
+        B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
+        st = _cur_stream()
+        img1, feat = self._img1, self._feat
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        want_dimg = self.views_grad
+        if self.fused:
+            C.call("ups_step_decode_bwd", g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
+                   self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
+            C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
+                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
+        else:
+            C.call("ups_part_inject_bwd", g_inj.data_ptr(), feat.data_ptr(), self.mh0.data_ptr(),
+                   self.dfeat.data_ptr(), self.dm.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
+            g0 = self.dm if g_m0 is None else self.dm.add_(g_m0)
+            C.call("ups_part_softmax_bwd", self.m0.data_ptr(), g0.data_ptr(), self.dl0.data_ptr(), B * P, K, st)
+            C.call("ups_mask_parts_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
+                   self.dimg1.data_ptr() if want_dimg else None, self.dm.data_ptr(), B, P, K, 3, 1, st)
+            if g_pooled is not None:
+                C.call("ups_part_pool_bwd", g_pooled.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
+                       self.dfm.data_ptr() if want_dimg else None, self.dm2.data_ptr(), B, P, K, 3, 0, 1.0 / P, st)
+                self.dm.add_(self.dm2)
+                if want_dimg:
+                    self.dimg1.add_(self.dfm)
+            if g_m1 is not None:
+                self.dm.add_(g_m1)
+            C.call("ups_part_softmax_bwd", self.m1.data_ptr(), self.dm.data_ptr(), self.dl1.data_ptr(), B * P, K, st)
+        out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
+        if self.views_grad:
+            if self.use_tps:
+                if g_warped is None:
+                    self.gw.zero_()
+                else:
+                    self.gw.copy_(g_warped)
+                self.gw[1].add_(self.dimg1)
+                coord = self._coord
+                C.call("ups_tps_warp_bwd", self.gw.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                       self.dviews.data_ptr(), 2 * B, S, S, 3, S, S, st)
+                if V > 2:
+                    C.call("ups_tps_warp_bwd", self.gw[2].data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                           self.dviews[2].data_ptr(), B, S, S, 3, S, S, st)
+                out["dviews"] = self.dviews
+            else:
+                self.dviews.zero_()
+                if g_warped is not None:
+                    self.dviews.copy_(g_warped)
+                self.dviews[1].add_(self.dimg1)
+                out["dviews"] = self.dviews
+        return out
+
+    # kernels enqueued by one forward+backward (bench.py's gpu_launches is counted, not assumed)
+    def algorithmic_bytes_per_image(self):
+        """SURVEY.md 8d / BASELINE.md 4: 4*P*(6V + 18K + 2F + 5 [+6V]) + 12*K*F + 8*K*C."""
+        V = self.V if self.use_tps else 0
+        per_px = 6 * V + 18 * self.K + 2 * self.F + 5 + (6 * V if self.views_grad else 0)
+        return 4 * self.P * per_px + 12 * self.K * self.F + 8 * self.K * 3
