@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -116,7 +116,7 @@ class ClockSampler(threading.Thread):
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -128,7 +128,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.004)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
@@ -153,8 +153,7 @@ def run_gpu(args):
     import ups_b200
     from ups_b200 import _cabi as C
     from ups_b200.dp import DataParallelPartStep, init_from_env, rank_seed
-    from util import CUB_TPS, PENN_TPS
-    from oracle import tps as OT   # TPS parameter draws only (host-side, ~50 floats per sample)
+    from util import CUB_TPS, PENN_TPS  # parameter ranges only (tests/util.py constants)
 
     rank, local, world = init_from_env()
     assert world == args.gpus or world == 1, (world, args.gpus)
@@ -179,9 +178,9 @@ def run_gpu(args):
     g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
     g_warped = torch.randn(V, B, S, S, 3, device=dev, generator=g) if args.tps_bwd else None
     tps_kw = CUB_TPS if args.workload == "cub" else PENN_TPS
-    prm = OT.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234 + rank), **tps_kw)
-    coord_h, tv_h = OT.make_input_tps_param(prm)
-    coord, tv = coord_h.to(dev), tv_h.to(dev)
+    prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234 + rank), device=dev, **tps_kw)
+    coord, tv = ups_b200.make_input_tps_param(prm)
+    coord_h, tv_h = coord.cpu(), tv.cpu()
 
     def one_step():
         dp.forward(views, coord, tv, l0, l1, feat)

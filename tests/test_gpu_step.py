@@ -159,5 +159,7 @@ def test_full_size_properties_cub_b256(ups):
         assert torch.equal(o8[k], out[k][:8]), k
     assert torch.equal(o8["warped"][0], out["warped"][0][:8])
     assert torch.equal(g8["dl0"], grad["dl0"][:8]) and torch.equal(g8["dl1"], grad["dl1"][:8])
-    assert_close(g8["dfeat"], grad["dfeat"][:8].cpu(), "dfeat slice")   # split count differs with B
+    # the number of pixel splits (hence the fp32 summation order of ~1000 O(1) terms per entry)
+    # depends on B: entries agree to summation rounding, ~1e-6 of the column scale (~30)
+    assert_close(g8["dfeat"], grad["dfeat"][:8].cpu(), "dfeat slice", atol=1e-4)
     assert_close(o8["pooled"], out["pooled"][:8].cpu(), "pooled slice")

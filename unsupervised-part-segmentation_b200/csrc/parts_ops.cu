@@ -220,9 +220,10 @@ constexpr int POOL_WARPS = 8;
 template <int NACC>
 __global__ void __launch_bounds__(POOL_WARPS * 32) part_pool_partial_kernel(
     const float* __restrict__ fmap, const float* __restrict__ mask, float* __restrict__ partial, int P, int K, int Fg,
-    int grouped, int fmap_stride, int splits) {
-    extern __shared__ float sm[];  // POOL_WARPS * KF
-    const int KF = K * Fg;
+    int grouped, int fmap_stride, int splits, int k0, int kc) {
+    // this launch covers parts [k0, k0+kc): KFc = kc*Fg <= 32*NACC (k,f) pairs
+    extern __shared__ float sm[];  // POOL_WARPS * KFc
+    const int KF = K * Fg, KFc = kc * Fg;
     const int b = blockIdx.y, sp = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (P + splits - 1) / splits;
@@ -233,24 +234,24 @@ __global__ void __launch_bounds__(POOL_WARPS * 32) part_pool_partial_kernel(
     for (int a = 0; a < NACC; ++a) {
         acc[a] = 0.f;
         const int j = lane + 32 * a;
-        kk[a] = j < KF ? j / Fg : 0;
-        ff[a] = j < KF ? (grouped ? j : j % Fg) : 0;
+        kk[a] = j < KFc ? k0 + j / Fg : 0;
+        ff[a] = j < KFc ? (grouped ? k0 * Fg + j : j % Fg) : 0;
     }
     for (int p = p0 + warp; p < p1; p += POOL_WARPS) {
         const float* fr = fmap + ((size_t)b * P + p) * fmap_stride;
         const float* mr = mask + ((size_t)b * P + p) * K;
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
-            if (lane + 32 * a < KF) acc[a] = fmaf(__ldg(fr + ff[a]), __ldg(mr + kk[a]), acc[a]);
+            if (lane + 32 * a < KFc) acc[a] = fmaf(__ldg(fr + ff[a]), __ldg(mr + kk[a]), acc[a]);
     }
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
-        if (lane + 32 * a < KF) sm[warp * KF + lane + 32 * a] = acc[a];
+        if (lane + 32 * a < KFc) sm[warp * KFc + lane + 32 * a] = acc[a];
     __syncthreads();
-    for (int j = threadIdx.x; j < KF; j += POOL_WARPS * 32) {
+    for (int j = threadIdx.x; j < KFc; j += POOL_WARPS * 32) {
         float s = sm[j];
-        for (int w = 1; w < POOL_WARPS; ++w) s += sm[w * KF + j];
-        partial[((size_t)b * splits + sp) * KF + j] = s;
+        for (int w = 1; w < POOL_WARPS; ++w) s += sm[w * KFc + j];
+        partial[((size_t)b * splits + sp) * KF + k0 * Fg + j] = s;
     }
 }
 
@@ -530,7 +531,7 @@ size_t pool_ws_bytes(int B, int P, int KF) { return (size_t)B * pool_splits(B, P
 int run_pool(const float* fmap, const float* mask, float* out, int B, int P, int K, int Fg, int grouped,
              int fmap_stride, float scale, int divide_by, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int KF = K * Fg;
-    UPS_REQUIRE(KF <= 1024, "pooling: K*F = %d > 1024 unsupported", KF);
+    UPS_REQUIRE(Fg <= 1024, "pooling: %d features per part > 1024 unsupported", Fg);
     UPS_REQUIRE(B <= 65535, "pooling: B=%d exceeds grid.y limit", B);
     const int splits = pool_splits(B, P);
     if (ws_bytes < pool_ws_bytes(B, P, KF) || !ws) {
@@ -539,19 +540,24 @@ int run_pool(const float* fmap, const float* mask, float* out, int B, int P, int
     }
     float* partial = static_cast<float*>(ws);
     dim3 grid(splits, B);
-    const size_t sm = (size_t)POOL_WARPS * KF * sizeof(float);
-    const int nacc = (int)cdiv(KF, 32);
+    const int kchunk = 1024 / Fg;  // parts per launch: at most 1024 (k,f) pairs in registers
+    for (int k0 = 0; k0 < K; k0 += kchunk) {
+        const int kc = (K - k0 < kchunk) ? (K - k0) : kchunk;
+        const int KFc = kc * Fg;
+        const size_t sm = (size_t)POOL_WARPS * KFc * sizeof(float);
+        const int nacc = (int)cdiv(KFc, 32);
 #define UPS_POOL(N)                                                                                                  \
     part_pool_partial_kernel<N><<<grid, POOL_WARPS * 32, sm, s>>>(fmap, mask, partial, P, K, Fg, grouped, fmap_stride, \
-                                                                  splits)
-    if (nacc <= 1) UPS_POOL(1);
-    else if (nacc <= 2) UPS_POOL(2);
-    else if (nacc <= 4) UPS_POOL(4);
-    else if (nacc <= 8) UPS_POOL(8);
-    else if (nacc <= 16) UPS_POOL(16);
-    else UPS_POOL(32);
+                                                                  splits, k0, kc)
+        if (nacc <= 1) UPS_POOL(1);
+        else if (nacc <= 2) UPS_POOL(2);
+        else if (nacc <= 4) UPS_POOL(4);
+        else if (nacc <= 8) UPS_POOL(8);
+        else if (nacc <= 16) UPS_POOL(16);
+        else UPS_POOL(32);
 #undef UPS_POOL
-    if (int rc = after_launch("part_pool_partial_kernel")) return rc;
+        if (int rc = after_launch("part_pool_partial_kernel")) return rc;
+    }
     const long long n = (long long)B * KF;
     pool_finalize_kernel<<<nblk(n, 128), 128, 0, s>>>(partial, out, KF, splits, scale, divide_by, n);
     return after_launch("pool_finalize_kernel");
