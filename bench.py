@@ -139,6 +139,8 @@ class ClockSampler(threading.Thread):
 KERNEL_BYTES_PER_PX = {
     # algorithmic (compulsory) bytes per pixel of each C-ABI call, fp32, K parts, F features, C=3
     "ups_tps_warp_fwd": lambda K, F: 4 * (3 + 3),
+    "ups_tps_warp_pair_fwd": lambda K, F: 4 * (3 + 3),
+    "ups_tps_warp_pair_bwd": lambda K, F: 4 * (3 + 3),
     "ups_step_encode_fwd": lambda K, F: 4 * (K + 3 + K + 3 * K),
     "ups_step_decode_fwd": lambda K, F: 4 * (K + K + 2 + F + K),
     "ups_step_decode_bwd": lambda K, F: 4 * ((F + K) + K + K + K),
@@ -235,7 +237,7 @@ def run_gpu(args):
     call_ms = {n: sum(v) / args.steps for n, v in per_call.items()}
     peak, peak_src = load_peaks()
     dom = max(call_ms, key=call_ms.get)
-    px = {"ups_tps_warp_fwd": V * B * P, "ups_tps_warp_bwd": V * B * P}.get(dom, B * P)
+    px = V * B * P if dom.startswith("ups_tps_warp") else B * P
     dom_bytes = KERNEL_BYTES_PER_PX[dom](K, F) * px if dom in KERNEL_BYTES_PER_PX else None
     n_dom = len(per_call[dom]) / args.steps
     dom_launch_ms = call_ms[dom] / n_dom

@@ -67,6 +67,14 @@ int ups_tps_warp_fwd(const float* U, const float* coord, const float* T, const f
 int ups_tps_warp_bwd(const float* g_out, const float* coord, const float* T, const float* move, const float* scal,
                      float* dU, int N, int H, int W, int C, int out_h, int out_w, void* stream);
 
+/* TrainModel.make_tps — cub/code/SB_model48i/model.py:298-310: view0 and view0_target are warped with
+ * the SAME parameters.  The pair calls warp U [N,...] and, for the first N2 samples, a second image
+ * set U2 [N2,...] at the same sample positions (the radial-basis grid is evaluated once). */
+int ups_tps_warp_pair_fwd(const float* U, const float* U2, const float* coord, const float* T, float* out, float* out2,
+                          int N, int N2, int H, int W, int C, int out_h, int out_w, void* stream);
+int ups_tps_warp_pair_bwd(const float* g_out, const float* g_out2, const float* coord, const float* T, float* dU,
+                          float* dU2, int N, int N2, int H, int W, int C, int out_h, int out_w, void* stream);
+
 /* ---- part-map softmax / hard max / straight-through / argmax ------------------------ */
 /* nn.softmax(x, spatial=False) — cub/code/nn.py:58-62, fused with the consumers at
  * cub/code/SB_model48i/model.py:426-473: probs, optional int64 argmax labels (first index),

@@ -17,6 +17,8 @@ multiply-add and never a library transcendental:
 * `exp_canon`  — Cephes `expf` (the polynomial Eigen's `pexp<float>` also uses), each
   multiply and add rounded separately.
 * `log_canon`  — Cephes `logf` (Eigen `plog<float>`), same rule.
+* softmax normalisation — p_k = e_k * fl(1/sum): ONE correctly rounded reciprocal per pixel,
+  then one multiply per part (oracle/parts.py::_SoftmaxCanon).
 * `sum_tree`   — K-way sum as a balanced adjacent-pair tree over the terms zero padded
   to a power of two (invariant under XOR permutations of the leaves, so 1, 2, 4 or 8
   lanes per pixel with a shuffle butterfly all produce the same bits).

@@ -14,15 +14,17 @@ FEATURE_DIM = 4    # cub/code/SB_model48i/model.py:13
 
 
 class _SoftmaxCanon(torch.autograd.Function):
-    """tf.nn.softmax over the last axis: p = exp(x - max) / sum.  Backward is TF's
-    SoftmaxGrad formula dx = p * (g - sum_j g_j p_j) evaluated on the saved output."""
+    """tf.nn.softmax over the last axis: p = exp(x - max) * (1 / sum) — the reciprocal-multiply
+    form of TF's Eigen CPU kernel (its CUDA kernel divides; a 1-ulp matter).  Backward is
+    TF's SoftmaxGrad formula dx = p * (g - sum_j g_j p_j) evaluated on the saved output."""
 
     @staticmethod
     def forward(ctx, x):
         m = x.max(dim=-1, keepdim=True).values
         e = exp_canon(x - m)
         s = sum_tree(e)
-        p = e / s[..., None]
+        r = torch.ones_like(s) / s                  # correctly rounded reciprocal
+        p = e * r[..., None]
         ctx.save_for_backward(p)
         return p
 

@@ -16,6 +16,8 @@ _SIGS = {
     "ups_tps_solve": [c_f, c_f, c_f, c_i, c_f],
     "ups_tps_warp_fwd": [c_f] * 7 + [c_i] * 6 + [c_f],
     "ups_tps_warp_bwd": [c_f] * 6 + [c_i] * 6 + [c_f],
+    "ups_tps_warp_pair_fwd": [c_f] * 6 + [c_i] * 7 + [c_f],
+    "ups_tps_warp_pair_bwd": [c_f] * 6 + [c_i] * 7 + [c_f],
     "ups_part_softmax_fwd": [c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
     "ups_part_softmax_bwd": [c_f, c_f, c_f, c_ll, c_i, c_f],
     "ups_spatial_softmax_fwd": [c_f, c_f, c_i, c_i, c_i, c_f],

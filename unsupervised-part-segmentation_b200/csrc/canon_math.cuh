@@ -20,6 +20,7 @@
 #define UPS_FADD(a, b) __fadd_rn((a), (b))
 #define UPS_FSUB(a, b) __fsub_rn((a), (b))
 #define UPS_FDIV(a, b) __fdiv_rn((a), (b))
+#define UPS_FRCP(a) __frcp_rn(a)
 #define UPS_DMUL(a, b) __dmul_rn((a), (b))
 #define UPS_DSUB(a, b) __dsub_rn((a), (b))
 #define UPS_DDIV(a, b) __ddiv_rn((a), (b))
@@ -30,6 +31,7 @@
 #define UPS_FADD(a, b) ((a) + (b))
 #define UPS_FSUB(a, b) ((a) - (b))
 #define UPS_FDIV(a, b) ((a) / (b))
+#define UPS_FRCP(a) (1.0f / (a))
 #define UPS_DMUL(a, b) ((a) * (b))
 #define UPS_DSUB(a, b) ((a) - (b))
 #define UPS_DDIV(a, b) ((a) / (b))
@@ -226,7 +228,7 @@ UPS_HD float bilinear_mix(const Bilinear& b, float Ia, float Ib, float Ic, float
 }
 
 // Generic-K softmax row in canonical order (oracle/parts.py::_SoftmaxCanon.forward):
-// p = exp_canon(x - max) / sum_tree(e).  `e` is scratch with capacity >= next pow2 of K.
+// p = exp_canon(x - max) * fl(1 / sum_tree(e)).  `e` is scratch with capacity >= next pow2 of K.
 constexpr int KMAX = 64;
 UPS_HD int next_pow2(int k) { int p = 1; while (p < k) p <<= 1; return p; }
 
@@ -238,9 +240,9 @@ UPS_HD float softmax_row_canon(const float* x, float* p, float* e, int K) {
     for (int k = K; k < P2; ++k) e[k] = 0.0f;
     for (int w = P2 >> 1; w >= 1; w >>= 1)
         for (int i = 0; i < w; ++i) e[i] = UPS_FADD(e[2 * i], e[2 * i + 1]);
-    const float s = e[0];
+    const float rs = UPS_FRCP(e[0]);
     float pmax = 0.0f;
-    for (int k = 0; k < K; ++k) { p[k] = UPS_FDIV(p[k], s); pmax = p[k] > pmax ? p[k] : pmax; }
+    for (int k = 0; k < K; ++k) { p[k] = UPS_FMUL(p[k], rs); pmax = p[k] > pmax ? p[k] : pmax; }
     return pmax;
 }
 

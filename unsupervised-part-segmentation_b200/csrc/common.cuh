@@ -93,11 +93,12 @@ __device__ __forceinline__ float4 softmax4(float4 v, int c, float& pmax, int& ar
     e.w = exp_canon(__fsub_rn(v.w, m));
     float s = __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w));
     s = group_sum_canon<LPP>(s);
+    const float rs = __frcp_rn(s);
     float4 p;
-    p.x = __fdiv_rn(e.x, s);
-    p.y = __fdiv_rn(e.y, s);
-    p.z = __fdiv_rn(e.z, s);
-    p.w = __fdiv_rn(e.w, s);
+    p.x = __fmul_rn(e.x, rs);
+    p.y = __fmul_rn(e.y, rs);
+    p.z = __fmul_rn(e.z, rs);
+    p.w = __fmul_rn(e.w, rs);
     pmax = group_max<LPP>(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w)));
     int a = 1 << 30;
     a = (p.w == pmax) ? 4 * c + 3 : a;

@@ -30,16 +30,43 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ============================================================================ K3 decode fwd
+// general rows (tied maxima somewhere in these PW pixels): sum over parts in ascending k
 template <int LPP>
+__device__ __noinline__ void inject_rows_general(float4 mh, const float4* fs4, float* rows, int NF4, int FK, int lane) {
+    constexpr int K = 4 * LPP, PW = 32 / LPP;
+    const int nf_it = (NF4 + 31) >> 5;
+    for (int pix_l = 0; pix_l < PW; ++pix_l) {
+        for (int it = 0; it < nf_it; ++it) {
+            const int f4 = it * 32 + lane;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int src = pix_l * LPP + (k >> 2);
+                const float comp = ((k & 3) == 0) ? mh.x : ((k & 3) == 1) ? mh.y : ((k & 3) == 2) ? mh.z : mh.w;
+                const float mk = __shfl_sync(FULL, comp, src);
+                if (mk != 0.f && f4 < NF4) {
+                    const float4 fv = fs4[k * NF4 + f4];
+                    acc.x = fmaf(mk, fv.x, acc.x); acc.y = fmaf(mk, fv.y, acc.y);
+                    acc.z = fmaf(mk, fv.z, acc.z); acc.w = fmaf(mk, fv.w, acc.w);
+                }
+            }
+            if (f4 < NF4) st4_stream(rows + (size_t)pix_l * FK + 4 * f4, acc);
+        }
+    }
+}
+
+// FT = compile-time F (0: run-time F) so that the row/column split of the inject store is shifts
+template <int LPP, int FT>
 __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __restrict__ l0,
                                                                const float* __restrict__ feat,
                                                                float* __restrict__ m0,
                                                                long long* __restrict__ labels0,
-                                                               float* __restrict__ inj, int P, int F,
+                                                               float* __restrict__ inj, int P, int Frt,
                                                                int pix_per_cta) {
     constexpr int K = 4 * LPP, PW = 32 / LPP;
     extern __shared__ float4 fs4[];  // feat[b] as [K][F/4] float4
     const int b = blockIdx.y;
+    const int F = FT > 0 ? FT : Frt;
     const int NF4 = F >> 2, FK = F + K;
     for (int i = threadIdx.x; i < K * NF4; i += FTPB) fs4[i] = ld4(feat + (size_t)b * K * F + 4 * i);
     __syncthreads();
@@ -54,18 +81,18 @@ __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __re
             v[s] = ld4_stream(l0 + (((size_t)b * P + pg + s * PW + plq) * LPP + c) * 4);
 #pragma unroll
         for (int s = 0; s < LPP; ++s) {
-            const int p = pg + s * PW + plq;
-            const size_t gi = ((size_t)b * P + p) * LPP + c;
+            const size_t pix = (size_t)b * P + pg + s * PW + plq;
             float pmax; int arg, nmax;
             const float4 p4 = softmax4<LPP>(v[s], c, pmax, arg, nmax);
-            st4(m0 + 4 * gi, p4);
-            if (c == 0) labels0[(size_t)b * P + p] = arg;
+            st4(m0 + (pix * LPP + c) * 4, p4);
+            if (c == 0) labels0[pix] = arg;
             const float4 mh = hard_st4(p4, pmax);
-            st4_stream(inj + ((size_t)b * P + p) * FK + F + 4 * c, mh);
+            st4_stream(inj + pix * FK + F + 4 * c, mh);
             const float mon = st_value(1.0f, pmax);
             float* rows = inj + ((size_t)b * P + pg + s * PW) * FK;
             if (!__any_sync(FULL, nmax > 1)) {
                 // one-hot fast path: row = mon * feat[arg, :]
+#pragma unroll 4
                 for (int it = 0; it < n_it; ++it) {
                     const int idx = it * 32 + lane;
                     const bool valid = idx < n_items;
@@ -80,26 +107,7 @@ __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __re
                     }
                 }
             } else {
-                // tied maxima somewhere in these PW pixels: general sum over parts (ascending k)
-                const int nf_it = (NF4 + 31) >> 5;
-                for (int pix_l = 0; pix_l < PW; ++pix_l) {
-                    for (int it = 0; it < nf_it; ++it) {
-                        const int f4 = it * 32 + lane;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int src = pix_l * LPP + (k >> 2);
-                            const float comp = ((k & 3) == 0) ? mh.x : ((k & 3) == 1) ? mh.y : ((k & 3) == 2) ? mh.z : mh.w;
-                            const float mk = __shfl_sync(FULL, comp, src);
-                            if (mk != 0.f && f4 < NF4) {
-                                const float4 fv = fs4[k * NF4 + f4];
-                                acc.x = fmaf(mk, fv.x, acc.x); acc.y = fmaf(mk, fv.y, acc.y);
-                                acc.z = fmaf(mk, fv.z, acc.z); acc.w = fmaf(mk, fv.w, acc.w);
-                            }
-                        }
-                        if (f4 < NF4) st4_stream(rows + (size_t)pix_l * FK + 4 * f4, acc);
-                    }
-                }
+                inject_rows_general<LPP>(mh, fs4, rows, NF4, FK, lane);
             }
         }
     }
@@ -472,12 +480,15 @@ extern "C" int ups_step_decode_fwd(const float* l0, const float* feat, float* m0
     dim3 grid((unsigned)cdiv(P, per), B);
     const size_t sm = (size_t)K * F * sizeof(float);
     cudaStream_t s = as_stream(stream);
-#define UPS_DEC_FWD(LPP)                                                                            \
-    {                                                                                               \
-        if (int rc = set_smem(step_decode_fwd_kernel<LPP>, sm)) return rc;                          \
-        step_decode_fwd_kernel<LPP><<<grid, FTPB, sm, s>>>(l0, feat, m0, labels0, inj, P, F, per);  \
+#define UPS_DEC_FWD2(LPP, FT)                                                                           \
+    {                                                                                                   \
+        if (int rc = set_smem(step_decode_fwd_kernel<LPP, FT>, sm)) return rc;                          \
+        step_decode_fwd_kernel<LPP, FT><<<grid, FTPB, sm, s>>>(l0, feat, m0, labels0, inj, P, F, per);  \
     }
+#define UPS_DEC_FWD(LPP) \
+    { if (F == 64) UPS_DEC_FWD2(LPP, 64) else if (F == 32) UPS_DEC_FWD2(LPP, 32) else if (F == 16) UPS_DEC_FWD2(LPP, 16) else UPS_DEC_FWD2(LPP, 0) }
     if (K == 4) UPS_DEC_FWD(1) else if (K == 8) UPS_DEC_FWD(2) else if (K == 16) UPS_DEC_FWD(4) else UPS_DEC_FWD(8)
+#undef UPS_DEC_FWD2
 #undef UPS_DEC_FWD
     return after_launch("step_decode_fwd_kernel");
 }

@@ -26,26 +26,73 @@ __global__ void tps_input_param_kernel(const float* __restrict__ coord, const fl
 }
 
 // ------------------------------------------------------------------ a3(ii): _solve_system
-// One thread per sample; the 11x13 augmented system lives in shared memory interleaved by
-// thread (element e of thread t at [e*SOLVE_TPB + t]) so every access is conflict-free.
-constexpr int SOLVE_TPB = 32;
-struct SmemAcc {
-    double* base;
-    __device__ __forceinline__ double& operator()(int i, int j) const { return base[(i * 13 + j) * SOLVE_TPB]; }
-};
+// One WARP per sample: lane r < 11 holds row r of the augmented 11x13 system in registers.
+// Every row operation is the canonical one of canon_math.cuh::tps_solve / oracle solve_canon
+// (same operands, same single-rounded mul / sub / div), only executed by 11 lanes at once, so
+// the result is bit-identical to the sequential form (tests/test_canon_host.py pins that form).
+constexpr int SOLVE_WARPS = 4;
 
-__global__ void __launch_bounds__(SOLVE_TPB) tps_solve_kernel(const float* __restrict__ coord,
-                                                              const float* __restrict__ vector,
-                                                              float* __restrict__ T, int N) {
-    __shared__ double A[11 * 13 * SOLVE_TPB];
-    const int b = blockIdx.x * SOLVE_TPB + threadIdx.x;
-    if (b >= N) return;
-    float c[16], v[16], t[22];
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) tps_solve_kernel(const float* __restrict__ coord,
+                                                                     const float* __restrict__ vector,
+                                                                     float* __restrict__ T, int N) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SOLVE_WARPS + (threadIdx.x >> 5);
+    if (b >= N) return;  // warp-uniform
+    float qx[8], qy[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { c[i] = coord[b * 16 + i]; v[i] = vector[b * 16 + i]; }
-    tps_solve(c, v, SmemAcc{A + threadIdx.x}, t);
+    for (int i = 0; i < 8; ++i) { qx[i] = __ldg(coord + b * 16 + 2 * i + 1); qy[i] = __ldg(coord + b * 16 + 2 * i); }
+    double row[13];
 #pragma unroll
-    for (int i = 0; i < 22; ++i) T[b * 22 + i] = t[i];
+    for (int j = 0; j < 13; ++j) row[j] = 0.0;
+    if (lane < 8) {
+        float mx = 0.f, my = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i == lane) { mx = qx[i]; my = qy[i]; }
+        row[0] = 1.0; row[1] = (double)mx; row[2] = (double)my;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d0 = __fsub_rn(1.0f, 1.0f);
+            const float d1 = __fsub_rn(mx, qx[j]);
+            const float d2_ = __fsub_rn(my, qy[j]);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2_, d2_));
+            row[3 + j] = (double)tps_rbf(d2);
+        }
+        row[11] = (double)__fadd_rn(mx, __ldg(vector + b * 16 + 2 * lane + 1));
+        row[12] = (double)__fadd_rn(my, __ldg(vector + b * 16 + 2 * lane));
+    } else if (lane < 11) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[3 + j] = (lane == 8) ? 1.0 : (lane == 9 ? (double)qx[j] : (double)qy[j]);
+    }
+    int pos = lane;  // logical row index of the row this lane holds (rows swap by swapping pos)
+#pragma unroll
+    for (int c = 0; c < 11; ++c) {
+        // first-max partial pivoting over logical rows >= c
+        double bv = (lane < 11 && pos >= c) ? fabs(row[c]) : -1.0;
+        int bp = pos;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULLM, bv, o);
+            const int op = __shfl_xor_sync(FULLM, bp, o);
+            if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; }
+        }
+        if (pos == bp) pos = c; else if (pos == c) pos = bp;
+        const int pl = __ffs(__ballot_sync(FULLM, lane < 11 && pos == c)) - 1;  // lane holding the pivot row
+        const double piv = __shfl_sync(FULLM, row[c], pl);
+        const double f = (lane != pl) ? __ddiv_rn(row[c], piv) : 0.0;
+#pragma unroll
+        for (int j = c + 1; j < 13; ++j) {
+            const double pj = __shfl_sync(FULLM, row[j], pl);
+            if (lane != pl) row[j] = __dsub_rn(row[j], __dmul_rn(f, pj));
+        }
+    }
+    if (lane < 11) {
+        double d = row[0];
+#pragma unroll
+        for (int j = 1; j < 11; ++j) if (j == pos) d = row[j];
+        T[b * 22 + pos] = (float)__ddiv_rn(row[11], d);
+        T[b * 22 + 11 + pos] = (float)__ddiv_rn(row[12], d);
+    }
 }
 
 // ------------------------------------------------------------------ a3(iii-v): grid + sample
@@ -83,76 +130,98 @@ __device__ __forceinline__ void sample_position(const SampleConst& k, bool has_m
     }
 }
 
+// One thread per output pixel.  A second image set U2 (first N2 samples) can ride on the same
+// sample positions: CUB warps view0 and view0_target with the same parameters
+// (cub/code/SB_model48i/model.py:306-309), so the 8 radial-basis evaluations are paid once.
 template <int C>
 __global__ void __launch_bounds__(WARP_TPB) tps_warp_fwd_kernel(const float* __restrict__ U,
+                                                                const float* __restrict__ U2,
                                                                 const float* __restrict__ coord,
                                                                 const float* __restrict__ T,
                                                                 const float* __restrict__ move,
                                                                 const float* __restrict__ scal,
-                                                                float* __restrict__ out, float* __restrict__ mesh,
-                                                                int H, int W, int Crt, int oh, int ow) {
+                                                                float* __restrict__ out, float* __restrict__ out2,
+                                                                float* __restrict__ mesh, int N2, int H, int W,
+                                                                int Crt, int oh, int ow) {
     __shared__ float sm_const[42];
-    extern __shared__ float sm_out[];  // WARP_TPB * C floats
+    extern __shared__ float sm_out[];  // 2 * WARP_TPB * C floats
     const int Cc = (C > 0) ? C : Crt;
     const int b = blockIdx.y;
     SampleConst k;
     load_sample_const(k, sm_const, coord, T, move, scal, b);
     const bool has_move = (move != nullptr);
+    const bool second = (U2 != nullptr) && (b < N2);
     const float step_w = lin_step(ow), step_h = lin_step(oh);
     const int OP = oh * ow;
     const float* Ub = U + (size_t)b * H * W * Cc;
+    const float* Ub2 = second ? U2 + (size_t)b * H * W * Cc : nullptr;
+    float* sm_out2 = sm_out + WARP_TPB * Cc;
     const int tile0 = blockIdx.x * (WARP_TPB * WARP_PPT);
 #pragma unroll 1
     for (int it = 0; it < WARP_PPT; ++it) {
         const int base = tile0 + it * WARP_TPB;
         if (base >= OP) break;
         const int pix = base + threadIdx.x;
-        const bool live = pix < OP;
-        if (live) {
+        if (pix < OP) {
             const int i = pix / ow, j = pix - i * ow;
             float x_s, y_s;
             sample_position(k, has_move, i, j, step_h, step_w, x_s, y_s);
             if (mesh) reinterpret_cast<float2*>(mesh)[(size_t)b * OP + pix] = make_float2(y_s, x_s);
             const Bilinear s = bilinear_stencil(x_s, y_s, W, H);
-            const float* pa = Ub + (size_t)(s.y0 * W + s.x0) * Cc;
-            const float* pb = Ub + (size_t)(s.y1 * W + s.x0) * Cc;
-            const float* pc = Ub + (size_t)(s.y0 * W + s.x1) * Cc;
-            const float* pd = Ub + (size_t)(s.y1 * W + s.x1) * Cc;
+            const int oa = (s.y0 * W + s.x0) * Cc, ob = (s.y1 * W + s.x0) * Cc;
+            const int oc = (s.y0 * W + s.x1) * Cc, od = (s.y1 * W + s.x1) * Cc;
             if (C > 0) {
 #pragma unroll
                 for (int c = 0; c < (C > 0 ? C : 1); ++c)
-                    sm_out[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(pa + c), __ldg(pb + c), __ldg(pc + c), __ldg(pd + c));
+                    sm_out[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(Ub + oa + c), __ldg(Ub + ob + c), __ldg(Ub + oc + c), __ldg(Ub + od + c));
+                if (second) {
+#pragma unroll
+                    for (int c = 0; c < (C > 0 ? C : 1); ++c)
+                        sm_out2[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(Ub2 + oa + c), __ldg(Ub2 + ob + c), __ldg(Ub2 + oc + c), __ldg(Ub2 + od + c));
+                }
             } else {
                 for (int c = 0; c < Cc; ++c)
-                    sm_out[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(pa + c), __ldg(pb + c), __ldg(pc + c), __ldg(pd + c));
+                    sm_out[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(Ub + oa + c), __ldg(Ub + ob + c), __ldg(Ub + oc + c), __ldg(Ub + od + c));
+                if (second)
+                    for (int c = 0; c < Cc; ++c)
+                        sm_out2[threadIdx.x * Cc + c] = bilinear_mix(s, __ldg(Ub2 + oa + c), __ldg(Ub2 + ob + c), __ldg(Ub2 + oc + c), __ldg(Ub2 + od + c));
             }
         }
         __syncthreads();
         // coalesced write of the tile: WARP_TPB*C contiguous floats
         const int n_live = min(WARP_TPB, OP - base) * Cc;
-        float* ob = out + ((size_t)b * OP + base) * Cc;
-        for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob + e, sm_out[e]);
+        float* ob_ = out + ((size_t)b * OP + base) * Cc;
+        for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob_ + e, sm_out[e]);
+        if (second) {
+            float* ob2 = out2 + ((size_t)b * OP + base) * Cc;
+            for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob2 + e, sm_out2[e]);
+        }
         __syncthreads();
     }
 }
 
 template <int C>
 __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __restrict__ g_out,
+                                                                const float* __restrict__ g_out2,
                                                                 const float* __restrict__ coord,
                                                                 const float* __restrict__ T,
                                                                 const float* __restrict__ move,
                                                                 const float* __restrict__ scal, float* __restrict__ dU,
-                                                                int H, int W, int Crt, int oh, int ow) {
+                                                                float* __restrict__ dU2, int N2, int H, int W, int Crt,
+                                                                int oh, int ow) {
     __shared__ float sm_const[42];
-    extern __shared__ float sm_g[];  // WARP_TPB * C floats
+    extern __shared__ float sm_g[];  // 2 * WARP_TPB * C floats
     const int Cc = (C > 0) ? C : Crt;
     const int b = blockIdx.y;
     SampleConst k;
     load_sample_const(k, sm_const, coord, T, move, scal, b);
     const bool has_move = (move != nullptr);
+    const bool second = (g_out2 != nullptr) && (b < N2);
     const float step_w = lin_step(ow), step_h = lin_step(oh);
     const int OP = oh * ow;
     float* Ub = dU + (size_t)b * H * W * Cc;
+    float* Ub2 = second ? dU2 + (size_t)b * H * W * Cc : nullptr;
+    float* sm_g2 = sm_g + WARP_TPB * Cc;
     const int tile0 = blockIdx.x * (WARP_TPB * WARP_PPT);
 #pragma unroll 1
     for (int it = 0; it < WARP_PPT; ++it) {
@@ -161,6 +230,10 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
         const int n_live = min(WARP_TPB, OP - base) * Cc;
         const float* gb = g_out + ((size_t)b * OP + base) * Cc;
         for (int e = threadIdx.x; e < n_live; e += WARP_TPB) sm_g[e] = __ldcs(gb + e);
+        if (second) {
+            const float* gb2 = g_out2 + ((size_t)b * OP + base) * Cc;
+            for (int e = threadIdx.x; e < n_live; e += WARP_TPB) sm_g2[e] = __ldcs(gb2 + e);
+        }
         __syncthreads();
         const int pix = base + threadIdx.x;
         if (pix < OP) {
@@ -168,18 +241,23 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
             float x_s, y_s;
             sample_position(k, has_move, i, j, step_h, step_w, x_s, y_s);
             const Bilinear s = bilinear_stencil(x_s, y_s, W, H);
-            float* pa = Ub + (size_t)(s.y0 * W + s.x0) * Cc;
-            float* pb = Ub + (size_t)(s.y1 * W + s.x0) * Cc;
-            float* pc = Ub + (size_t)(s.y0 * W + s.x1) * Cc;
-            float* pd = Ub + (size_t)(s.y1 * W + s.x1) * Cc;
+            const int oa = (s.y0 * W + s.x0) * Cc, ob = (s.y1 * W + s.x0) * Cc;
+            const int oc = (s.y0 * W + s.x1) * Cc, od = (s.y1 * W + s.x1) * Cc;
             for (int c = 0; c < Cc; ++c) {
-                const float g = sm_g[threadIdx.x * Cc + c];
                 // out-of-range samples have coinciding clipped corners whose weights cancel:
                 // keep all four adds so that the sum matches autodiff of the forward exactly.
-                atomicAdd(pa + c, s.wa * g);
-                atomicAdd(pb + c, s.wb * g);
-                atomicAdd(pc + c, s.wc * g);
-                atomicAdd(pd + c, s.wd * g);
+                const float g = sm_g[threadIdx.x * Cc + c];
+                atomicAdd(Ub + oa + c, s.wa * g);
+                atomicAdd(Ub + ob + c, s.wb * g);
+                atomicAdd(Ub + oc + c, s.wc * g);
+                atomicAdd(Ub + od + c, s.wd * g);
+                if (second) {
+                    const float g2 = sm_g2[threadIdx.x * Cc + c];
+                    atomicAdd(Ub2 + oa + c, s.wa * g2);
+                    atomicAdd(Ub2 + ob + c, s.wb * g2);
+                    atomicAdd(Ub2 + oc + c, s.wc * g2);
+                    atomicAdd(Ub2 + od + c, s.wd * g2);
+                }
             }
         }
         __syncthreads();
@@ -205,7 +283,7 @@ extern "C" int ups_tps_solve(const float* coord, const float* vector, float* T, 
     UPS_REQUIRE(coord && vector && T, "tps_solve: null pointer");
     UPS_REQUIRE(N >= 0, "tps_solve: N=%d", N);
     if (N == 0) return UPS_OK;
-    tps_solve_kernel<<<(unsigned)cdiv(N, SOLVE_TPB), SOLVE_TPB, 0, as_stream(stream)>>>(coord, vector, T, N);
+    tps_solve_kernel<<<(unsigned)cdiv(N, SOLVE_WARPS), SOLVE_WARPS * 32, 0, as_stream(stream)>>>(coord, vector, T, N);
     return after_launch("tps_solve_kernel");
 }
 
@@ -221,34 +299,65 @@ static int check_warp_args(const void* U, const void* coord, const void* T, cons
     return UPS_OK;
 }
 
-extern "C" int ups_tps_warp_fwd(const float* U, const float* coord, const float* T, const float* move,
-                                const float* scal, float* out, float* mesh, int N, int H, int W, int C, int out_h,
-                                int out_w, void* stream) {
+static int launch_warp_fwd(const float* U, const float* U2, const float* coord, const float* T, const float* move,
+                           const float* scal, float* out, float* out2, float* mesh, int N, int N2, int H, int W, int C,
+                           int out_h, int out_w, void* stream) {
     int rc = check_warp_args(U, coord, T, move, scal, out, N, H, W, C, out_h, out_w);
     if (rc) return rc;
+    UPS_REQUIRE((U2 == nullptr) == (out2 == nullptr), "tps_warp_fwd: U2 and out2 must be given together");
+    UPS_REQUIRE(N2 >= 0 && N2 <= N, "tps_warp_fwd: N2=%d not in [0, N=%d]", N2, N);
     if (N == 0) return UPS_OK;
     UPS_REQUIRE(mesh == nullptr || (reinterpret_cast<uintptr_t>(mesh) & 7u) == 0, "tps_warp_fwd: mesh must be 8-byte aligned");
     dim3 grid((unsigned)cdiv((long long)out_h * out_w, WARP_TPB * WARP_PPT), (unsigned)N);
-    const size_t sm = (size_t)WARP_TPB * C * sizeof(float);
+    const size_t sm = (size_t)2 * WARP_TPB * C * sizeof(float);
     if (C == 3)
-        tps_warp_fwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(U, coord, T, move, scal, out, mesh, H, W, C, out_h, out_w);
+        tps_warp_fwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(U, U2, coord, T, move, scal, out, out2, mesh, N2, H, W, C, out_h, out_w);
     else
-        tps_warp_fwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(U, coord, T, move, scal, out, mesh, H, W, C, out_h, out_w);
+        tps_warp_fwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(U, U2, coord, T, move, scal, out, out2, mesh, N2, H, W, C, out_h, out_w);
     return after_launch("tps_warp_fwd_kernel");
+}
+
+static int launch_warp_bwd(const float* g_out, const float* g_out2, const float* coord, const float* T,
+                           const float* move, const float* scal, float* dU, float* dU2, int N, int N2, int H, int W,
+                           int C, int out_h, int out_w, void* stream) {
+    int rc = check_warp_args(g_out, coord, T, move, scal, dU, N, H, W, C, out_h, out_w);
+    if (rc) return rc;
+    UPS_REQUIRE((g_out2 == nullptr) == (dU2 == nullptr), "tps_warp_bwd: g_out2 and dU2 must be given together");
+    UPS_REQUIRE(N2 >= 0 && N2 <= N, "tps_warp_bwd: N2=%d not in [0, N=%d]", N2, N);
+    if (N == 0) return UPS_OK;
+    UPS_CUDA(cudaMemsetAsync(dU, 0, (size_t)N * H * W * C * sizeof(float), as_stream(stream)));
+    if (dU2 && N2 > 0) UPS_CUDA(cudaMemsetAsync(dU2, 0, (size_t)N2 * H * W * C * sizeof(float), as_stream(stream)));
+    dim3 grid((unsigned)cdiv((long long)out_h * out_w, WARP_TPB * WARP_PPT), (unsigned)N);
+    const size_t sm = (size_t)2 * WARP_TPB * C * sizeof(float);
+    if (C == 3)
+        tps_warp_bwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w);
+    else
+        tps_warp_bwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w);
+    return after_launch("tps_warp_bwd_kernel");
+}
+
+extern "C" int ups_tps_warp_fwd(const float* U, const float* coord, const float* T, const float* move,
+                                const float* scal, float* out, float* mesh, int N, int H, int W, int C, int out_h,
+                                int out_w, void* stream) {
+    return launch_warp_fwd(U, nullptr, coord, T, move, scal, out, nullptr, mesh, N, 0, H, W, C, out_h, out_w, stream);
 }
 
 extern "C" int ups_tps_warp_bwd(const float* g_out, const float* coord, const float* T, const float* move,
                                 const float* scal, float* dU, int N, int H, int W, int C, int out_h, int out_w,
                                 void* stream) {
-    int rc = check_warp_args(g_out, coord, T, move, scal, dU, N, H, W, C, out_h, out_w);
-    if (rc) return rc;
-    if (N == 0) return UPS_OK;
-    UPS_CUDA(cudaMemsetAsync(dU, 0, (size_t)N * H * W * C * sizeof(float), as_stream(stream)));
-    dim3 grid((unsigned)cdiv((long long)out_h * out_w, WARP_TPB * WARP_PPT), (unsigned)N);
-    const size_t sm = (size_t)WARP_TPB * C * sizeof(float);
-    if (C == 3)
-        tps_warp_bwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, coord, T, move, scal, dU, H, W, C, out_h, out_w);
-    else
-        tps_warp_bwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, coord, T, move, scal, dU, H, W, C, out_h, out_w);
-    return after_launch("tps_warp_bwd_kernel");
+    return launch_warp_bwd(g_out, nullptr, coord, T, move, scal, dU, nullptr, N, 0, H, W, C, out_h, out_w, stream);
+}
+
+extern "C" int ups_tps_warp_pair_fwd(const float* U, const float* U2, const float* coord, const float* T, float* out,
+                                     float* out2, int N, int N2, int H, int W, int C, int out_h, int out_w,
+                                     void* stream) {
+    UPS_REQUIRE(U2 && out2, "tps_warp_pair_fwd: null pointer");
+    return launch_warp_fwd(U, U2, coord, T, nullptr, nullptr, out, out2, nullptr, N, N2, H, W, C, out_h, out_w, stream);
+}
+
+extern "C" int ups_tps_warp_pair_bwd(const float* g_out, const float* g_out2, const float* coord, const float* T,
+                                     float* dU, float* dU2, int N, int N2, int H, int W, int C, int out_h, int out_w,
+                                     void* stream) {
+    UPS_REQUIRE(g_out2 && dU2, "tps_warp_pair_bwd: null pointer");
+    return launch_warp_bwd(g_out, g_out2, coord, T, nullptr, nullptr, dU, dU2, N, N2, H, W, C, out_h, out_w, stream);
 }

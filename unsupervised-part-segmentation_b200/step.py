@@ -76,11 +76,12 @@ class PartStep:
         if self.use_tps:
             assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
             C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
-            C.call("ups_tps_warp_fwd", views.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
-                   self.warped.data_ptr(), None, 2 * B, S, S, 3, S, S, st)
-            if V > 2:  # the target view shares view0's warp (model.py:306-309)
-                C.call("ups_tps_warp_fwd", views[2].data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
-                       self.warped[2].data_ptr(), None, B, S, S, 3, S, S, st)
+            if V > 2:  # the target view shares view0's warp (model.py:306-309): one launch, shared grid
+                C.call("ups_tps_warp_pair_fwd", views.data_ptr(), views[2].data_ptr(), coord.data_ptr(),
+                       self.T.data_ptr(), self.warped.data_ptr(), self.warped[2].data_ptr(), 2 * B, B, S, S, 3, S, S, st)
+            else:
+                C.call("ups_tps_warp_fwd", views.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                       self.warped.data_ptr(), None, 2 * B, S, S, 3, S, S, st)
             warped = self.warped
             self._coord = coord
         else:
@@ -143,11 +144,12 @@ class PartStep:
                     self.gw.copy_(g_warped)
                 self.gw[1].add_(self.dimg1)
                 coord = self._coord
-                C.call("ups_tps_warp_bwd", self.gw.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
-                       self.dviews.data_ptr(), 2 * B, S, S, 3, S, S, st)
                 if V > 2:
-                    C.call("ups_tps_warp_bwd", self.gw[2].data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
-                           self.dviews[2].data_ptr(), B, S, S, 3, S, S, st)
+                    C.call("ups_tps_warp_pair_bwd", self.gw.data_ptr(), self.gw[2].data_ptr(), coord.data_ptr(),
+                           self.T.data_ptr(), self.dviews.data_ptr(), self.dviews[2].data_ptr(), 2 * B, B, S, S, 3, S, S, st)
+                else:
+                    C.call("ups_tps_warp_bwd", self.gw.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
+                           self.dviews.data_ptr(), 2 * B, S, S, 3, S, S, st)
                 out["dviews"] = self.dviews
             else:
                 self.dviews.zero_()
