@@ -144,6 +144,7 @@ KERNEL_BYTES_PER_PX = {
     "ups_step_encode_fwd": lambda K, F: 4 * (K + 3 + K + 3 * K),
     "ups_step_decode_fwd": lambda K, F: 4 * (K + K + 2 + F + K),
     "ups_step_decode_bwd": lambda K, F: 4 * ((F + K) + K + K + K),
+    "ups_step_decode_bwd_tc": lambda K, F: 4 * ((F + K) + K + K + K),
     "ups_step_encode_bwd": lambda K, F: 4 * (3 * K + 3 + K + K + K),
     "ups_tps_warp_bwd": lambda K, F: 4 * (3 + 3),
 }
@@ -164,7 +165,8 @@ def run_gpu(args):
     wl = WORKLOADS[args.workload]
     S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
     P = S * S
-    dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev)
+    dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev,
+                              decode_bwd=args.decode_bwd)
     step = dp.step
 
     # ---- synthetic shard, resident in HBM (rank-offset seed)
@@ -250,7 +252,7 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "spatial": S, "n_parts": K,
-                   "local_app_size": F, "views": V, "tps_backward": bool(args.tps_bwd),
+                   "local_app_size": F, "views": V, "tps_backward": bool(args.tps_bwd), "decode_bwd": step.decode_bwd,
                    "parallelism": f"dp{world} (batch-sharded; no data-path collective; "
                                   f"{dp.grads.numel() * 4 / 1e6:.0f} MB fp32 gradient all-reduce per step when N>1)",
                    "l2": "inputs larger than L2: one step touches %.1f GB per GPU (L2 = 126 MB)" % (step_bytes / 1e9)},
@@ -367,6 +369,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tps-bwd", action="store_true", help="also back-propagate into the input views (K6)")
+    ap.add_argument("--decode-bwd", default="auto", choices=["auto", "tc", "simt"],
+                    help="K4 variant: tcgen05 tensor-core kernel or CUDA-core kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

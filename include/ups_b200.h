@@ -150,6 +150,10 @@ int ups_step_decode_fwd(const float* l0, const float* feat, float* m0, long long
  * g_m0 (cotangent arriving at the probabilities from the losses) may be NULL. */
 int ups_step_decode_bwd(const float* g_inj, const float* m0, const float* g_m0, const float* feat, float* dl0,
                         float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+/* Same contract as ups_step_decode_bwd with both contractions on the tcgen05 tensor cores
+ * (3xTF32 split, fp32 accumulation in TMEM).  Needs K in {16,32}, F == 64, P % 128 == 0. */
+int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const float* g_m0, const float* feat, float* dl0,
+                           float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
 /* backward of the encode side: dm1 = sum_c img1*(g_parts + g_pooled/P); dl1 = softmax_bwd(m1, dm1 + g_m1);
  * dimg1 (optional) = sum_k mh*(g_parts + g_pooled/P).  g_pooled, g_m1, dimg1 may be NULL. */
 int ups_step_encode_bwd(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,

@@ -163,3 +163,43 @@ def test_full_size_properties_cub_b256(ups):
     # depends on B: entries agree to summation rounding, ~1e-6 of the column scale (~30)
     assert_close(g8["dfeat"], grad["dfeat"][:8].cpu(), "dfeat slice", atol=1e-4)
     assert_close(o8["pooled"], out["pooled"][:8].cpu(), "pooled slice")
+
+
+@pytest.mark.parametrize("B,S,K,seed", [(2, 32, 16, 0), (3, 64, 16, 1), (1, 128, 16, 2), (2, 32, 32, 3), (40, 64, 16, 4)])
+def test_decode_bwd_tensor_core_path(ups, B, S, K, seed):
+    """K4 on tcgen05 (3xTF32, TMEM accumulators) against the oracle and against the SIMT kernel."""
+    from oracle import parts as OP
+    from ups_b200 import _cabi as C
+    F, P = 64, S * S
+    g = torch.Generator().manual_seed(seed)
+    l0 = torch.randn(B, S, S, K, generator=g)
+    l0[:, 0] = torch.round(l0[:, 0])                      # tied maxima -> several non-zeros in the hard mask
+    feat = torch.randn(B, K, F, generator=g)
+    g_inj = torch.randn(B, S, S, F + K, generator=g)
+    g_m0 = torch.randn(B, S, S, K, generator=g)
+    lo = l0.clone().requires_grad_(True)
+    fo = feat.clone().requires_grad_(True)
+    m0 = OP.softmax(lo)
+    inj = OP.inject(fo, OP.straight_through_estimator(OP.hard_max(m0, 3), m0))
+    dl0_o, dfeat_o = torch.autograd.grad([inj, m0], [lo, fo], [g_inj, g_m0])
+    m0c, featc, g_injc, g_m0c = m0.detach().cuda(), feat.cuda(), g_inj.cuda(), g_m0.cuda()
+    ws = torch.empty(C.workspace_bytes(C.OP_STEP, B, P, K, F), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for name in ("ups_step_decode_bwd_tc", "ups_step_decode_bwd"):
+        dl0 = torch.full((B, S, S, K), float("nan"), device="cuda")
+        dfeat = torch.full((B, K, F), float("nan"), device="cuda")
+        C.call(name, g_injc.data_ptr(), m0c.data_ptr(), g_m0c.data_ptr(), featc.data_ptr(), dl0.data_ptr(),
+               dfeat.data_ptr(), B, P, K, F, ws.data_ptr(), ws.numel(), st)
+        torch.cuda.synchronize()
+        res[name] = (dl0, dfeat)
+        assert_close(dl0, dl0_o, f"{name} dl0")
+        assert_close(dfeat, dfeat_o, f"{name} dfeat")
+    # without the external cotangent
+    dl0 = torch.empty(B, S, S, K, device="cuda")
+    dfeat = torch.empty(B, K, F, device="cuda")
+    C.call("ups_step_decode_bwd_tc", g_injc.data_ptr(), m0c.data_ptr(), None, featc.data_ptr(), dl0.data_ptr(),
+           dfeat.data_ptr(), B, P, K, F, ws.data_ptr(), ws.numel(), st)
+    m0b = OP.softmax(lo)
+    (dl0_o2,) = torch.autograd.grad(OP.inject(feat, OP.straight_through_estimator(OP.hard_max(m0b, 3), m0b)), lo, g_inj)
+    assert_close(dl0, dl0_o2, "tc dl0 (no g_m0)")

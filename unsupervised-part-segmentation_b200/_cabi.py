@@ -40,6 +40,7 @@ _SIGS = {
     "ups_step_encode_fwd": [c_f] * 5 + [c_i] * 3 + [c_f, c_sz, c_f],
     "ups_step_decode_fwd": [c_f] * 5 + [c_i] * 4 + [c_f],
     "ups_step_decode_bwd": [c_f] * 6 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_step_decode_bwd_tc": [c_f] * 6 + [c_i] * 4 + [c_f, c_sz, c_f],
     "ups_step_encode_bwd": [c_f] * 7 + [c_i] * 3 + [c_f],
 }
 

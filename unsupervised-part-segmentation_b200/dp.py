@@ -88,11 +88,13 @@ class DataParallelPartStep:
     e_pi + e_alpha + dv + dd + discriminators)."""
 
     def __init__(self, per_gpu_batch, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, n_grad_params=33_300_000, bucket_bytes=32 << 20, device="cuda"):
+                 views_grad=False, n_grad_params=33_300_000, bucket_bytes=32 << 20, device="cuda",
+                 decode_bwd="auto"):
         from .step import PartStep
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device)
+        self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device,
+                             decode_bwd=decode_bwd)
         self.grads = torch.zeros(int(n_grad_params), dtype=torch.float32, device=device)
         self.reducer = GradAllReducer(self.grads, bucket_bytes, self.world)
 

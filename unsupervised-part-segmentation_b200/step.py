@@ -27,7 +27,7 @@ def _cur_stream():
 
 class PartStep:
     def __init__(self, batch_size, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, device="cuda"):
+                 views_grad=False, device="cuda", decode_bwd="auto"):
         B, S, K, F, V = int(batch_size), int(spatial_size), int(n_parts), int(local_app_size), int(n_views)
         self.B, self.S, self.K, self.F, self.V = B, S, K, F, V
         self.P = S * S
@@ -37,6 +37,12 @@ class PartStep:
         if self.device.type != "cuda":
             raise C.UpsError("PartStep needs a CUDA device: there is no CPU path")
         self.fused = K in (8, 16, 32) and F in (16, 32, 64) and self.P % 32 == 0
+        # K4 variant: "tc" = tcgen05/TMEM + mma.sync tensor-core kernel, "simt" = CUDA-core kernel
+        tc_ok = self.fused and K in (16, 32) and F == 64 and self.P % 128 == 0
+        assert decode_bwd in ("auto", "tc", "simt")
+        if decode_bwd == "tc" and not tc_ok:
+            raise C.UpsError("decode_bwd='tc' needs K in {16,32}, F == 64 and H*W % 128 == 0")
+        self.decode_bwd = "tc" if (tc_ok and decode_bwd != "simt") else "simt"
         f32 = dict(dtype=torch.float32, device=self.device)
         e = torch.empty
         self.T = e(2 * B, 2, 11, **f32)
@@ -115,7 +121,8 @@ class PartStep:
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         want_dimg = self.views_grad
         if self.fused:
-            C.call("ups_step_decode_bwd", g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
+            C.call("ups_step_decode_bwd_tc" if self.decode_bwd == "tc" else "ups_step_decode_bwd",
+                   g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
                    self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
             C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
                    p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
