@@ -1,8 +1,8 @@
 // K4 on the tensor cores, for K in {16, 32}, F = 64, P % 128 == 0.
 //
-//   GEMM1  dmask[128 px, K] = G[128 px, 64 f] . feat^T[64 f, K]     tcgen05.mma kind::tf32, M=128, N=K,
+//   GEMM1  dmask[64 px, K] = G[64 px, 64 f] . feat^T[64 f, K]       tcgen05.mma kind::tf32, M=64, N=K,
 //                                                                   8 k-steps, fp32 accumulator in TMEM
-//   GEMM2  dfeat[K, 64 f] += mh^T[K, 128 px] . G[128 px, 64 f]      warp-level mma.sync m16n8k8 tf32,
+//   GEMM2  dfeat[K, 64 f] += mh^T[K, 64 px] . G[64 px, 64 f]        warp-level mma.sync m16n8k8 tf32,
 //                                                                   fp32 accumulators in registers
 // GEMM2 contracts over the pixel axis, along which neither operand is contiguous in memory ("TN"
 // weight-gradient shape).  tcgen05 accepts MN-major tf32 operands only in the 128B_BASE32B swizzled
@@ -21,15 +21,15 @@
 //
 // Shared-memory operand layout (no TMA descriptors needed): the canonical SWIZZLE_NONE "interleave"
 // layout of 8x16-byte core matrices, written directly by 16-byte cp.async:
-//   16-byte chunk j (4 floats along f) of pixel row r  ->  (r/8)*2048 + j*128 + (r%8)*16
-// Read K-major (rows = pixels, K = f): LBO = 128 (next 4 f), SBO = 2048 (next 8 pixels) -> GEMM1 A;
+//   16-byte chunk j (4 floats along f) of pixel row r  ->  j*LBO + (r/8)*128 + (r%8)*16
+// Read K-major (rows = pixels, K = f): LBO (next 4 f), SBO = 128 (next 8 pixels) -> GEMM1 A;
 // the same bytes are read as mma.sync B fragments by GEMM2, so ONE copy of the g_inj tile feeds both.
 #include "common.cuh"
 
 namespace ups {
 namespace tc {
 
-constexpr int TILE = 128;      // pixels per tile = UMMA M of GEMM1
+constexpr int TILE = 64;       // pixels per tile = UMMA M of GEMM1
 constexpr int F = 64;
 constexpr int TPB = 128;
 
@@ -118,30 +118,36 @@ __device__ __forceinline__ void sts4(uint32_t a, float4 v) {
 template <int K>
 struct Smem {
     static constexpr int NCH = K / 4;                 // 16-byte chunks per [.,K] row
-    static constexpr int A_BYTES = TILE * F * 4;      // 32 KB
-    static constexpr int ROWT = TILE * K * 4;         // one [128][K] tile
+    // G tile in the SWIZZLE_NONE core-matrix layout, chunk-block major with a 64-byte pad per block:
+    //   16-byte chunk j (4 floats along f) of pixel row r -> j*A_LBO + (r/8)*128 + (r%8)*16
+    // UMMA K-major descriptor: LBO = A_LBO (next 4 f), SBO = 128 (next 8 pixels).  The pad makes the
+    // mma.sync fragment reads of GEMM2 (8 features x 4 pixels per load) hit 32 distinct banks.
+    static constexpr int A_LBO = TILE * 16 + 64;      // 1088
+    static constexpr int A_BYTES = 16 * A_LBO;        // 17 KB
+    static constexpr int ROWT = TILE * K * 4;         // one [TILE][K] tile
     static constexpr int B_BYTES = K * F * 4;
-    static constexpr int MHS = 132;                   // row stride (floats) of the transposed hard-mask tile
+    static constexpr int MHS = TILE + 4;              // row stride (floats) of the transposed hard-mask tile
     static constexpr int MH_BYTES = K * MHS * 4;
-    static constexpr int A_HI = 0, A_LO = A_BYTES, TAIL = 2 * A_BYTES, PT = TAIL + ROWT, GT = PT + ROWT,
-                         MH = GT + ROWT, B_HI = MH + MH_BYTES, B_LO = B_HI + B_BYTES, BAR = B_LO + B_BYTES,
-                         TOTAL = BAR + 64;
+    static constexpr int A_HI = 0, A_LO = A_BYTES, PT = 2 * A_BYTES, GT = PT + ROWT, MH = GT + ROWT,
+                         B_HI = MH + MH_BYTES, B_LO = B_HI + B_BYTES, BAR = B_LO + B_BYTES, TOTAL = BAR + 32;
 };
 
+// 128 threads, one 64-pixel tile at a time, 53 KB of shared memory (K=16): four CTAs per SM keep
+// four tiles (4 x 26 KB of loads) in flight, which is what hides the HBM latency here - the phases
+// of one tile (load, split, GEMM1, epilogue, GEMM2, store) are serial within a CTA.
 template <int K>
-__global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __restrict__ g_inj,
-                                                                 const float* __restrict__ m0,
-                                                                 const float* __restrict__ g_m0,
-                                                                 const float* __restrict__ feat,
-                                                                 float* __restrict__ dl0, float* __restrict__ partial,
-                                                                 int P, int pix_per_cta, float* __restrict__ dbg,
-                                                                 int /*variant*/) {
+__global__ void __launch_bounds__(TPB, (K == 16) ? 4 : 3) step_decode_bwd_tc_kernel(
+    const float* __restrict__ g_inj, const float* __restrict__ m0, const float* __restrict__ g_m0,
+    const float* __restrict__ feat, float* __restrict__ dl0, float* __restrict__ partial, int P, int pix_per_cta,
+    float* __restrict__ dbg) {
     using L = Smem<K>;
     constexpr int NCH = L::NCH, FK = F + K;
     constexpr int SH = (NCH == 4) ? 1 : 0;            // row-major [.,K] tiles: chunk j of row r at j ^ ((r>>SH)&(NCH-1))
     constexpr uint32_t TMEM_COLS = 32;
     constexpr int MT = K / 16;                        // m-tiles (16 parts each) of GEMM2
-    constexpr uint32_t IDESC1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(K >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr int RG = TILE / 8;                      // 8-row groups per tile
+    constexpr int KS2 = TILE / 8;                     // k-steps of GEMM2
+    constexpr uint32_t IDESC1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(K >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sb = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -183,29 +189,39 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
             for (int i = 0; i < 4; ++i) acc2[a][n][i] = 0.f;
 
     const int p_begin = blockIdx.x * pix_per_cta, p_end = min(P, p_begin + pix_per_cta);
+    // epilogue mapping: UMMA M=64 puts accumulator row r in TMEM lane (r/16)*32 + r%16, so lane l < 16 of
+    // warp w owns pixel row 16w + l; the upper half-warp idles in the epilogue
+    const bool epi = lane < 16;
+    const int er = warp * 16 + (lane & 15);
     uint32_t phase = 0;
     for (int pt = p_begin; pt < p_end; pt += TILE) {
         const float* grow = g_inj + ((size_t)b * P + pt) * FK;
-        // ---- (1) async loads: G (16 chunks/row -> UMMA layout), tail, probabilities, external cotangent
+        // ---- (1) async loads: G (16 chunks/row -> UMMA layout), probabilities, external cotangent
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int rg = warp * 4 + (q >> 2), j = (q & 3) * 4 + (lane >> 3), r = rg * 8 + (lane & 7);
-            cp_async16(sb + L::A_HI + rg * 2048 + j * 128 + (lane & 7) * 16, grow + (size_t)r * FK + 4 * j);
+        for (int q = 0; q < RG; ++q) {   // each warp: RG/4 row-groups x 4 passes of (8 rows x 4 chunks)
+            const int rg = warp * (RG / 4) + (q >> 2), j = (q & 3) * 4 + (lane >> 3), r = rg * 8 + (lane & 7);
+            cp_async16(sb + L::A_HI + j * L::A_LBO + rg * 128 + (lane & 7) * 16, grow + (size_t)r * FK + 4 * j);
         }
 #pragma unroll
-        for (int it = 0; it < NCH; ++it) {
+        for (int it = 0; it < (TILE * NCH) / TPB; ++it) {
             const int c = it * TPB + tid, r = c / NCH, j = c % NCH;
             const uint32_t off = r * (16 * NCH) + ((j ^ ((r >> SH) & (NCH - 1))) * 16);
-            cp_async16(sb + L::TAIL + off, grow + (size_t)r * FK + F + 4 * j);
             cp_async16(sb + L::PT + off, m0 + ((size_t)b * P + pt + r) * K + 4 * j);
             if (g_m0) cp_async16(sb + L::GT + off, g_m0 + ((size_t)b * P + pt + r) * K + 4 * j);
+        }
+        // the K tail columns g_inj[..., F:F+K] of the thread's own pixel row go straight to registers
+        float4 tail[NCH];
+        if (epi) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) tail[j] = ld4_stream(grow + (size_t)er * FK + F + 4 * j);
         }
         cp_async_commit_wait_all();
         __syncthreads();
         // ---- (2) 3xTF32 split of G, elementwise (layout-agnostic): hi in place, lo beside it
 #pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-            const uint32_t off = (uint32_t)(it * TPB + tid) * 16;
+        for (int it = 0; it < (TILE * 16) / TPB; ++it) {
+            const int c = it * TPB + tid;                                  // chunk id: block j = c / TILE, then row
+            const uint32_t off = (uint32_t)(c / TILE) * L::A_LBO + (uint32_t)(c % TILE) * 16;
             const float4 v = lds4(sb + L::A_HI + off);
             const float4 hi = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
             const float4 lo = make_float4(rna_tf32(v.x - hi.x), rna_tf32(v.y - hi.y), rna_tf32(v.z - hi.z), rna_tf32(v.w - hi.w));
@@ -215,13 +231,13 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        // ---- (3) GEMM1: D1[128, K] = G . feat^T   (one thread issues; 8 k-steps x 3 split terms)
+        // ---- (3) GEMM1: D1[TILE, K] = G . feat^T   (one thread issues; 8 k-steps x 3 split terms)
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const uint64_t a_hi = make_desc(sb + L::A_HI + s * 256, 128, 2048);
-                const uint64_t a_lo = make_desc(sb + L::A_LO + s * 256, 128, 2048);
+                const uint64_t a_hi = make_desc(sb + L::A_HI + s * 2 * L::A_LBO, L::A_LBO, 128);
+                const uint64_t a_lo = make_desc(sb + L::A_LO + s * 2 * L::A_LBO, L::A_LBO, 128);
                 const uint64_t b_hi = make_desc(sb + L::B_HI + s * 256, 128, 2048);
                 const uint64_t b_lo = make_desc(sb + L::B_LO + s * 256, 128, 2048);
                 umma_tf32(D1, a_hi, b_hi, IDESC1, s > 0 ? 1u : 0u);
@@ -232,47 +248,47 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
         }
         mbar_wait(bar1, phase);
         tc_fence_after();
-        // ---- (4) epilogue, thread = pixel row (TMEM lane): softmax backward + hard mask for GEMM2
+        // ---- (4) epilogue, thread = pixel row: softmax backward + transposed hard mask for GEMM2
         {
-            const int r = tid;
-            float dm[K], pr[K], gp[K];
+            float dm[K];
 #pragma unroll
             for (int c0 = 0; c0 < K; c0 += 16) tmem_ld16(D1 + ((uint32_t)(warp * 32) << 16) + c0, dm + c0);
-            const uint32_t rowoff = r * (16 * NCH);
-            const int sw = (r >> SH) & (NCH - 1);
-            float dot = 0.f, pmax = 0.f;
+            if (epi) {
+                const int r = er;
+                float pr[K], gp[K];
+                const uint32_t rowoff = r * (16 * NCH);
+                const int sw = (r >> SH) & (NCH - 1);
+                float dot = 0.f, pmax = 0.f;
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                const uint32_t off = rowoff + ((j ^ sw) * 16);
-                const float4 p4 = lds4(sb + L::PT + off);
-                const float4 t4 = lds4(sb + L::TAIL + off);
-                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g_m0) g4 = lds4(sb + L::GT + off);
-                pr[4 * j] = p4.x; pr[4 * j + 1] = p4.y; pr[4 * j + 2] = p4.z; pr[4 * j + 3] = p4.w;
-                gp[4 * j] = dm[4 * j] + t4.x + g4.x;
-                gp[4 * j + 1] = dm[4 * j + 1] + t4.y + g4.y;
-                gp[4 * j + 2] = dm[4 * j + 2] + t4.z + g4.z;
-                gp[4 * j + 3] = dm[4 * j + 3] + t4.w + g4.w;
-            }
+                for (int j = 0; j < NCH; ++j) {
+                    const uint32_t off = rowoff + ((j ^ sw) * 16);
+                    const float4 p4 = lds4(sb + L::PT + off);
+                    const float4 t4 = tail[j];
+                    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g_m0) g4 = lds4(sb + L::GT + off);
+                    pr[4 * j] = p4.x; pr[4 * j + 1] = p4.y; pr[4 * j + 2] = p4.z; pr[4 * j + 3] = p4.w;
+                    gp[4 * j] = dm[4 * j] + t4.x + g4.x;
+                    gp[4 * j + 1] = dm[4 * j + 1] + t4.y + g4.y;
+                    gp[4 * j + 2] = dm[4 * j + 2] + t4.z + g4.z;
+                    gp[4 * j + 3] = dm[4 * j + 3] + t4.w + g4.w;
+                }
 #pragma unroll
-            for (int k = 0; k < K; ++k) { dot = fmaf(gp[k], pr[k], dot); pmax = fmaxf(pmax, pr[k]); }
+                for (int k = 0; k < K; ++k) { dot = fmaf(gp[k], pr[k], dot); pmax = fmaxf(pmax, pr[k]); }
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                float4 d, m;
-                d.x = pr[4 * j] * (gp[4 * j] - dot);
-                d.y = pr[4 * j + 1] * (gp[4 * j + 1] - dot);
-                d.z = pr[4 * j + 2] * (gp[4 * j + 2] - dot);
-                d.w = pr[4 * j + 3] * (gp[4 * j + 3] - dot);
-                sts4(sb + L::GT + rowoff + ((j ^ sw) * 16), d);
-                m.x = rna_tf32(st_value(pr[4 * j] == pmax ? 1.f : 0.f, pr[4 * j]));
-                m.y = rna_tf32(st_value(pr[4 * j + 1] == pmax ? 1.f : 0.f, pr[4 * j + 1]));
-                m.z = rna_tf32(st_value(pr[4 * j + 2] == pmax ? 1.f : 0.f, pr[4 * j + 2]));
-                m.w = rna_tf32(st_value(pr[4 * j + 3] == pmax ? 1.f : 0.f, pr[4 * j + 3]));
-                // transposed hard-mask tile mhT[k][pixel] (A operand of GEMM2), row stride 132 floats
-                sts1(sb + L::MH + ((4 * j + 0) * L::MHS + r) * 4, m.x);
-                sts1(sb + L::MH + ((4 * j + 1) * L::MHS + r) * 4, m.y);
-                sts1(sb + L::MH + ((4 * j + 2) * L::MHS + r) * 4, m.z);
-                sts1(sb + L::MH + ((4 * j + 3) * L::MHS + r) * 4, m.w);
+                for (int j = 0; j < NCH; ++j) {
+                    float4 d;
+                    d.x = pr[4 * j] * (gp[4 * j] - dot);
+                    d.y = pr[4 * j + 1] * (gp[4 * j + 1] - dot);
+                    d.z = pr[4 * j + 2] * (gp[4 * j + 2] - dot);
+                    d.w = pr[4 * j + 3] * (gp[4 * j + 3] - dot);
+                    sts4(sb + L::GT + rowoff + ((j ^ sw) * 16), d);
+                    // transposed hard-mask tile mhT[k][pixel] (A operand of GEMM2)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float pv = pr[4 * j + i];
+                        sts1(sb + L::MH + ((4 * j + i) * L::MHS + r) * 4, rna_tf32(st_value(pv == pmax ? 1.f : 0.f, pv)));
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
         {
             const int g = lane >> 2, t = lane & 3;
 #pragma unroll 4
-            for (int s = 0; s < 16; ++s) {
+            for (int s = 0; s < KS2; ++s) {
                 uint32_t af[MT][4];
 #pragma unroll
                 for (int a = 0; a < MT; ++a) {
@@ -294,7 +310,7 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
 #pragma unroll
                 for (int n = 0; n < 2; ++n) {
                     const int f = warp * 16 + n * 8 + g;
-                    const uint32_t off = s * 2048 + (f >> 2) * 128 + t * 16 + (f & 3) * 4;
+                    const uint32_t off = (f >> 2) * L::A_LBO + s * 128 + t * 16 + (f & 3) * 4;
                     const uint32_t bh0 = lds1(sb + L::A_HI + off), bh1 = lds1(sb + L::A_HI + off + 64);
                     const uint32_t bl0 = lds1(sb + L::A_LO + off), bl1 = lds1(sb + L::A_LO + off + 64);
 #pragma unroll
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
         }
         // ---- (6) coalesced store of the dl0 tile
 #pragma unroll
-        for (int it = 0; it < NCH; ++it) {
+        for (int it = 0; it < (TILE * NCH) / TPB; ++it) {
             const int c = it * TPB + tid, r = c / NCH, j = c % NCH;
             const float4 v = lds4(sb + L::GT + r * (16 * NCH) + ((j ^ ((r >> SH) & (NCH - 1))) * 16));
             st4_stream(dl0 + ((size_t)b * P + pt + r) * K + 4 * j, v);
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(TPB) step_decode_bwd_tc_kernel(const float* __
                 dst[(k + 8) * F + f + 1] = acc2[a][n][3];
             }
     }
-    if (dbg) {  // bring-up aid: raw TMEM [128 lanes][2K cols] then the last MH tile
+    if (dbg) {  // bring-up aid: raw TMEM [128 lanes][32 cols]
         float t[16];
         for (int c0 = 0; c0 < 32; c0 += 16) {
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, t);
@@ -380,11 +396,11 @@ static int decode_bwd_tc_impl(const float* g_inj, const float* m0, const float* 
     if (K == 16) {
         const size_t sm = tc::Smem<16>::TOTAL;
         UPS_CUDA(cudaFuncSetAttribute(tc::step_decode_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tc::step_decode_bwd_tc_kernel<16><<<grid, tc::TPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per, dbg, variant);
+        tc::step_decode_bwd_tc_kernel<16><<<grid, tc::TPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per, dbg);
     } else {
         const size_t sm = tc::Smem<32>::TOTAL;
         UPS_CUDA(cudaFuncSetAttribute(tc::step_decode_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tc::step_decode_bwd_tc_kernel<32><<<grid, tc::TPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per, dbg, variant);
+        tc::step_decode_bwd_tc_kernel<32><<<grid, tc::TPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per, dbg);
     }
     if (int rc = after_launch("step_decode_bwd_tc_kernel")) return rc;
     const long long n = (long long)B * K * F;
