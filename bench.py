@@ -150,6 +150,25 @@ KERNEL_BYTES_PER_PX = {
 }
 
 
+CALL_KERNEL = {  # C-ABI call -> the kernel that dominates it (profiles/ncu_traffic.json keys)
+    "ups_tps_warp_fwd": "tps_warp_fwd_kernel", "ups_tps_warp_pair_fwd": "tps_warp_fwd_kernel",
+    "ups_step_encode_fwd": "step_encode_fwd_kernel", "ups_step_decode_fwd": "step_decode_fwd_kernel",
+    "ups_step_decode_bwd": "step_decode_bwd_kernel", "ups_step_decode_bwd_tc": "step_decode_bwd_tc_kernel",
+    "ups_step_encode_bwd": "step_encode_bwd_kernel",
+}
+
+
+def ncu_traffic(call, workload, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    if d.get("workload") != workload or d.get("B") != B:
+        return None, None
+    return d["bytes_per_launch"].get(CALL_KERNEL.get(call, "")), d.get("source")
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +266,7 @@ def run_gpu(args):
     step_bytes = step.algorithmic_bytes_per_image() * B
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
 
+    traffic, traffic_src = ncu_traffic(dom, args.workload, B)
     line = {
         "metric": "part-step images/sec (fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -259,7 +279,8 @@ def run_gpu(args):
         "clocks": clocks,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes / n_dom if dom_bytes else None,
                      "launch_ms": dom_launch_ms},
         "step_roofline": {"algorithmic_bytes_per_image": step.algorithmic_bytes_per_image(), "achieved": step_gbs,
