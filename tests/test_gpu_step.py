@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import step as OS
-from util import PENN_TPS, assert_bitexact, assert_close, cuda, make_inputs
+from util import PENN_TPS, assert_bitexact, assert_close, cuda, make_inputs, reduce_atol
 
 pytestmark = pytest.mark.gpu
 
@@ -44,8 +44,10 @@ def _check(out, grad, out_o, grad_o, use_tps=True, views_grad=False):
     assert_bitexact(out["parts"], out_o["parts"], "parts (part-major)")
     assert_close(out["pooled"], out_o["pooled"], "pooled")
     assert_close(out["inj"], out_o["inj"], "inj")
-    for k in ("dl0", "dl1", "dfeat"):
+    for k in ("dl0", "dl1"):
         assert_close(grad[k], grad_o[k], k)
+    P = out_o["m0"].shape[1] * out_o["m0"].shape[2]
+    assert_close(grad["dfeat"], grad_o["dfeat"], "dfeat", atol=reduce_atol(P))
     if views_grad:
         for i, w in enumerate(grad_o["dviews"]):
             assert_close(grad["dviews"][i], w, f"dviews[{i}]", atol=2e-5)
@@ -165,7 +167,8 @@ def test_full_size_properties_cub_b256(ups):
     assert_close(o8["pooled"], out["pooled"][:8].cpu(), "pooled slice")
 
 
-@pytest.mark.parametrize("B,S,K,seed", [(2, 32, 16, 0), (3, 64, 16, 1), (1, 128, 16, 2), (2, 32, 32, 3), (40, 64, 16, 4)])
+@pytest.mark.parametrize("B,S,K,seed", [(2, 32, 16, 0), (3, 64, 16, 1), (1, 128, 16, 2), (2, 32, 32, 3), (40, 64, 16, 4),
+                                        (100, 64, 16, 5), (30, 128, 16, 6), (90, 64, 32, 7), (1, 16, 16, 8)])
 def test_decode_bwd_tensor_core_path(ups, B, S, K, seed):
     """K4 on tcgen05 (3xTF32, TMEM accumulators) against the oracle and against the SIMT kernel."""
     from oracle import parts as OP
@@ -194,7 +197,7 @@ def test_decode_bwd_tensor_core_path(ups, B, S, K, seed):
         torch.cuda.synchronize()
         res[name] = (dl0, dfeat)
         assert_close(dl0, dl0_o, f"{name} dl0")
-        assert_close(dfeat, dfeat_o, f"{name} dfeat")
+        assert_close(dfeat, dfeat_o, f"{name} dfeat", atol=reduce_atol(P))
     # without the external cotangent
     dl0 = torch.empty(B, S, S, K, device="cuda")
     dfeat = torch.empty(B, K, F, device="cuda")

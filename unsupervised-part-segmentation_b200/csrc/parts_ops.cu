@@ -574,7 +574,9 @@ extern "C" size_t ups_workspace_bytes(int op, int B, int P, int K, int F) {
             const size_t splits = (size_t)cdiv(P, fused_pix_per_cta(B, P));
             const size_t fused = (size_t)B * splits * K * (F > 3 ? F : 3) * sizeof(float);
             const size_t unfused = pool_ws_bytes(B, P, K * (F > 3 ? F : 3));
-            return (fused > unfused ? fused : unfused) + 256;
+            const size_t tc = (K == 16 || K == 32) && F == 64 ? decode_bwd_tma_ws_bytes(B, P, K, F) : 0;
+            const size_t m = fused > unfused ? fused : unfused;
+            return (m > tc ? m : tc) + 256;
         }
         default:
             return 0;

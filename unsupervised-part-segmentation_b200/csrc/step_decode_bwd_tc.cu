@@ -408,7 +408,7 @@ static int decode_bwd_tc_impl(const float* g_inj, const float* m0, const float* 
     return after_launch("split_finalize_kernel");
 }
 
-extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const float* g_m0, const float* feat,
+extern "C" int ups_step_decode_bwd_tc1(const float* g_inj, const float* m0, const float* g_m0, const float* feat,
                                       float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes,
                                       void* stream) {
     return decode_bwd_tc_impl(g_inj, m0, g_m0, feat, dl0, dfeat, B, P, K, F, ws, ws_bytes, stream, nullptr, 0);
