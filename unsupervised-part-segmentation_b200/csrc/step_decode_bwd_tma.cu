@@ -133,6 +133,15 @@ __device__ __forceinline__ float2 lds2(uint32_t a) {
 __device__ __forceinline__ void sts2(uint32_t a, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
 }
+// predicated variants (warp-uniform predicate): skipped accesses cost no shared-memory bandwidth
+__device__ __forceinline__ void lds2_if(float2& v, uint32_t a, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.f32 {%0,%1}, [%2];\n\t}\n"
+                 : "+f"(v.x), "+f"(v.y) : "r"(a), "r"(pred));
+}
+__device__ __forceinline__ void sts2_if(uint32_t a, float2 v, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f32 [%0], {%1,%2};\n\t}\n"
+                 ::"r"(a), "f"(v.x), "f"(v.y), "r"(pred) : "memory");
+}
 __device__ __forceinline__ float4 lds4(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -348,27 +357,65 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             const uint32_t acc_lane = accw + lane * 8;
 #pragma unroll 1
             for (int r8 = 0; r8 < ROWS / 8; ++r8) {
+                // (a) 8 rows of the tile: all loads first (the asm statements keep program order), then lo
                 float2 g[8], ri[8];
+                uint32_t off[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = sw * ROWS + r8 * 8 + i;         // r & 7 == i
-                    const uint32_t off = r * 128 + ((lch ^ i) * 16) + lane_off;
-                    g[i] = lds2(hi_base + off);
-                    ri[i] = lds2(rinfo + (r8 * 8 + i) * 8);
-                    sts2(lo_base + off, make_float2(g[i].x - tf32_hi(g[i].x), g[i].y - tf32_hi(g[i].y)));
+                    off[i] = r * 128 + ((lch ^ i) * 16) + lane_off;
+                    g[i] = lds2(hi_base + off[i]);
                 }
 #pragma unroll
+                for (int i = 0; i < 8; ++i) ri[i] = lds2(rinfo + (r8 * 8 + i) * 8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    sts2(lo_base + off[i], make_float2(g[i].x - tf32_hi(g[i].x), g[i].y - tf32_hi(g[i].y)));
+                // (b) dfeat[label] += mon * g.  Rows of the batch that share a label are first combined in
+                // registers (every pair compared once, warp-uniform), so that each label is read-modified-
+                // written once and the 8 smem round trips overlap instead of chaining.
+                int kk[8];
+                bool simple = true;
+#pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    uint32_t mb = __float_as_uint(ri[i].x);
-                    const float mo = ri[i].y;
-                    while (mb) {                       // one iteration unless the row has tied maxima
-                        const int k = __ffs(mb) - 1;
-                        mb &= mb - 1;
-                        const uint32_t a = acc_lane + k * (F * 4);
-                        float2 v = lds2(a);
-                        v.x = fmaf(mo, g[i].x, v.x);
-                        v.y = fmaf(mo, g[i].y, v.y);
-                        sts2(a, v);
+                    const uint32_t mb = __float_as_uint(ri[i].x);
+                    kk[i] = __ffs(mb) - 1;
+                    simple = simple && (mb != 0u) && ((mb & (mb - 1u)) == 0u);
+                }
+                if (simple) {
+                    float2 cc[8];
+                    uint32_t alive[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cc[i] = make_float2(ri[i].y * g[i].x, ri[i].y * g[i].y);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        alive[i] = 1u;
+#pragma unroll
+                        for (int jj = 0; jj < i; ++jj)
+                            if (kk[i] == kk[jj]) { cc[jj].x += cc[i].x; cc[jj].y += cc[i].y; alive[i] = 0u; }
+                    }
+                    float2 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] = make_float2(0.f, 0.f); lds2_if(v[i], acc_lane + kk[i] * (F * 4), alive[i]); }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        sts2_if(acc_lane + kk[i] * (F * 4), make_float2(v[i].x + cc[i].x, v[i].y + cc[i].y), alive[i]);
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {          // tied maxima somewhere in these rows: plain sequential form
+                        const float2 rii = lds2(rinfo + (r8 * 8 + i) * 8);
+                        uint32_t mb = __float_as_uint(rii.x);
+                        const float mo = rii.y;
+                        const float2 gi = lds2(hi_base + (sw * ROWS + r8 * 8 + i) * 128 + ((lch ^ i) * 16) + lane_off);
+                        while (mb) {
+                            const int k = __ffs(mb) - 1;
+                            mb &= mb - 1;
+                            const uint32_t a = acc_lane + k * (F * 4);
+                            float2 t = lds2(a);
+                            t.x = fmaf(mo, gi.x, t.x);
+                            t.y = fmaf(mo, gi.y, t.y);
+                            sts2(a, t);
+                        }
                     }
                 }
             }
