@@ -145,7 +145,6 @@ KERNEL_BYTES_PER_PX = {
     "ups_step_decode_fwd": lambda K, F: 4 * (K + K + 2 + F + K),
     "ups_step_decode_bwd": lambda K, F: 4 * ((F + K) + K + K + K),
     "ups_step_decode_bwd_tc": lambda K, F: 4 * ((F + K) + K + K + K),
-    "ups_step_decode_bwd_tc1": lambda K, F: 4 * ((F + K) + K + K + K),
     "ups_step_encode_bwd": lambda K, F: 4 * (3 * K + 3 + K + K + K),
     "ups_tps_warp_bwd": lambda K, F: 4 * (3 + 3),
 }
@@ -155,7 +154,6 @@ CALL_KERNEL = {  # C-ABI call -> the kernel that dominates it (profiles/ncu_traf
     "ups_tps_warp_fwd": "tps_warp_fwd_kernel", "ups_tps_warp_pair_fwd": "tps_warp_fwd_kernel",
     "ups_step_encode_fwd": "step_encode_fwd_kernel", "ups_step_decode_fwd": "step_decode_fwd_kernel",
     "ups_step_decode_bwd": "step_decode_bwd_kernel", "ups_step_decode_bwd_tc": "step_decode_bwd_tma_kernel",
-    "ups_step_decode_bwd_tc1": "step_decode_bwd_tc_kernel",
     "ups_step_encode_bwd": "step_encode_bwd_kernel",
 }
 
@@ -392,7 +390,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tps-bwd", action="store_true", help="also back-propagate into the input views (K6)")
-    ap.add_argument("--decode-bwd", default="auto", choices=["auto", "tc", "tc1", "simt"],
+    ap.add_argument("--decode-bwd", default="auto", choices=["auto", "tc", "simt"],
                     help="K4 variant: tcgen05 tensor-core kernel or CUDA-core kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

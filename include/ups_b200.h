@@ -150,8 +150,10 @@ int ups_step_decode_fwd(const float* l0, const float* feat, float* m0, long long
  * g_m0 (cotangent arriving at the probabilities from the losses) may be NULL. */
 int ups_step_decode_bwd(const float* g_inj, const float* m0, const float* g_m0, const float* feat, float* dl0,
                         float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
-/* Same contract as ups_step_decode_bwd with both contractions on the tcgen05 tensor cores
- * (3xTF32 split, fp32 accumulation in TMEM).  Needs K in {16,32}, F == 64, P % 128 == 0. */
+/* Same contract as ups_step_decode_bwd as a persistent TMA + tcgen05 pipeline: the (P x F).(F x K)
+ * contraction on the tensor cores (kind::tf32, 3xTF32 split, fp32 accumulation in TMEM), dfeat as a
+ * deterministic scatter-add.  Needs K in {16,32}, F == 64, P % 128 == 0, B*P < 2^31.
+ * ws from ups_workspace_bytes(UPS_OP_STEP, ...) (holds the per-chunk dfeat partials and the chunk counter). */
 int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const float* g_m0, const float* feat, float* dl0,
                            float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
 /* backward of the encode side: dm1 = sum_c img1*(g_parts + g_pooled/P); dl1 = softmax_bwd(m1, dm1 + g_m1);

@@ -7,10 +7,10 @@ timeout 600 python -m pytest tests/test_gpu_step.py -x -q -k "decode_bwd_tensor_
 tail -25 $O/${TAG}_pytest.log
 if grep -q "pytest rc=0" $O/${TAG}_pytest.log; then
   timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu --no-e2e > $O/${TAG}_bench_tc.json 2> $O/${TAG}_bench_tc.err
-  timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu --no-e2e --decode-bwd tc1 > $O/${TAG}_bench_tc1.json 2> $O/${TAG}_bench_tc1.err
+  timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu --no-e2e --decode-bwd simt > $O/${TAG}_bench_simt.json 2> $O/${TAG}_bench_simt.err
   python - <<PY
 import json
-for n in ("tc","tc1"):
+for n in ("tc","simt"):
     try:
         d=json.loads(open("$O/${TAG}_bench_%s.json"%n).read().strip().splitlines()[-1]); print(n, round(d["value"]), d["ms_per_step"], d["per_call_ms"])
     except Exception as e: print(n,"ERR",e, open("$O/${TAG}_bench_%s.err"%n).read()[-1500:])

@@ -62,9 +62,6 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = c_i
-    if hasattr(lib, "ups_step_decode_bwd_tc1"):   # previous-generation K4 kept for A/B timing only (not in the header)
-        lib.ups_step_decode_bwd_tc1.argtypes = _SIGS["ups_step_decode_bwd_tc"]
-        lib.ups_step_decode_bwd_tc1.restype = c_i
     lib.ups_version.restype = ctypes.c_char_p
     lib.ups_last_error_string.restype = ctypes.c_char_p
     lib.ups_launch_count.restype = c_ll

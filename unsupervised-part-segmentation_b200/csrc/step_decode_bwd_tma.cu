@@ -55,7 +55,7 @@ struct Cfg {
     static constexpr int ACC = DM + DM_BYTES;
     static constexpr int RINFO = ACC + ACC_BYTES;       // 128 rows x (mask, mon)
     static constexpr int BAR = RINFO + 1024;
-    static constexpr int TOTAL = BAR + 256;
+    static constexpr int TOTAL = BAR + 512;
     static constexpr uint32_t TMEM_COLS = 4 * K;       // 2 accumulator buffers of 2K columns (64 / 128)
 };
 
@@ -159,37 +159,70 @@ __device__ __forceinline__ float lds1(uint32_t a) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // ------------------------------------------------------------------ schedule shared by all roles
-// chunk ch -> sample b = ch / splits, tiles [sp*CHUNK_TILES, min(tps, +CHUNK_TILES)) of that sample
-struct TileIter {
-    int ch, ch_end, splits, tps;   // tps = tiles per sample
-    int t, t_begin, t_end, b;
-    __device__ __forceinline__ void set_chunk() {
-        b = ch / splits;
-        const int sp = ch - b * splits;
-        t_begin = sp * CHUNK_TILES;
-        t_end = min(tps, t_begin + CHUNK_TILES);
-        t = t_begin;
+// Work unit = chunk: ch -> sample b = ch / splits, tiles [sp*CHUNK_TILES, min(tps, +CHUNK_TILES)) of that
+// sample.  Chunks are handed out dynamically: the TMA producer lane draws chunk ids from a global counter
+// (atomicAdd) and publishes them through a small shared-memory ring guarded by mbarriers; every other role
+// reads the same sequence from the ring.  A CTA that loses its SM to another kernel for a while (NCCL's
+// all-reduce runs beside this kernel in the data-parallel step) simply draws fewer chunks.
+constexpr int NSLOT = 8;
+
+struct ChunkRing {
+    uint32_t ring, bar_sfull, bar_sempty;   // shared-memory addresses
+    uint32_t idx;                           // chunks drawn / consumed so far by this role
+    int n_chunks;
+    // producer lane only
+    __device__ __forceinline__ int draw(unsigned int* counter) {
+        const uint32_t slot = idx % NSLOT, ph = (idx / NSLOT) & 1;
+        mbar_wait(bar_sempty + 8 * slot, ph ^ 1);
+        int v = (int)atomicAdd(counter, 1u);
+        if (v > n_chunks) v = n_chunks;
+        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(ring + 4 * slot), "r"(v) : "memory");
+        mbar_arrive(bar_sfull + 8 * slot);
+        ++idx;
+        return v;
     }
-    __device__ __forceinline__ void init(int c0, int c1, int splits_, int tps_) {
-        ch = c0; ch_end = c1; splits = splits_; tps = tps_;
-        t = t_begin = t_end = b = 0;
-        if (ch < ch_end) set_chunk();
-    }
-    __device__ __forceinline__ bool valid() const { return ch < ch_end; }
-    __device__ __forceinline__ long long row0() const { return ((long long)b * tps + t) * TILE; }
-    __device__ __forceinline__ bool first_in_chunk() const { return t == t_begin; }
-    __device__ __forceinline__ bool last_in_chunk() const { return t + 1 == t_end; }
-    __device__ __forceinline__ void next() {
-        if (++t == t_end) { ++ch; if (ch < ch_end) set_chunk(); }
+    // consumers: `collective` = the whole warp calls this (lane 0 signals for the warp)
+    __device__ __forceinline__ int take(bool collective, int lane) {
+        const uint32_t slot = idx % NSLOT, ph = (idx / NSLOT) & 1;
+        mbar_wait(bar_sfull + 8 * slot, ph);
+        int v;
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(v) : "r"(ring + 4 * slot) : "memory");
+        if (collective) __syncwarp();
+        if (!collective || lane == 0) mbar_arrive(bar_sempty + 8 * slot);
+        ++idx;
+        return v;
     }
 };
 
+struct TileIter {
+    int ch, n_chunks, splits, tps;   // tps = tiles per sample
+    int t, t_begin, t_end, b;
+    __device__ __forceinline__ void set_chunk(int c, int n_chunks_, int splits_, int tps_) {
+        ch = c; n_chunks = n_chunks_; splits = splits_; tps = tps_;
+        t = t_begin = t_end = b = 0;
+        if (ch < n_chunks) {
+            b = ch / splits;
+            const int sp = ch - b * splits;
+            t_begin = sp * CHUNK_TILES;
+            t_end = min(tps, t_begin + CHUNK_TILES);
+            t = t_begin;
+        }
+    }
+    __device__ __forceinline__ bool valid() const { return ch < n_chunks; }
+    __device__ __forceinline__ long long row0() const { return ((long long)b * tps + t) * TILE; }
+    __device__ __forceinline__ bool first_in_chunk() const { return t == t_begin; }
+    __device__ __forceinline__ bool last_in_chunk() const { return t + 1 == t_end; }
+    // consumer roles: step to the next tile, taking the next chunk from the ring at a chunk boundary
+    __device__ __forceinline__ void next(ChunkRing& cr, bool collective, int lane) {
+        if (++t == t_end) set_chunk(cr.take(collective, lane), n_chunks, splits, tps);
+    }
+};
 
 template <int K>
 __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
     const __grid_constant__ CUtensorMap tmap_g, const float* __restrict__ g_inj, const float* __restrict__ m0,
     const float* __restrict__ g_m0, const float* __restrict__ feat, float* __restrict__ dl0,
-    float* __restrict__ partial, int n_chunks, int splits, int tps) {
+    float* __restrict__ partial, unsigned int* __restrict__ chunk_counter, int n_chunks, int splits, int tps) {
     using L = Cfg<K>;
     constexpr int NST = L::NST, FK = F + K, NSPL = L::NSPL, W_TMA = L::W_TMA, W_MMA = L::W_MMA;
     constexpr int LPP = K / 4;            // lanes per pixel in the coalesced [px][K] mapping
@@ -209,7 +242,10 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
     const uint32_t bar_lo_free = bar_lo_ready + 16;        // [2]    MMA commit -> splitter
     const uint32_t bar_tm_full = bar_lo_free + 16;         // [2]    MMA commit -> epilogue
     const uint32_t bar_tm_empty = bar_tm_full + 16;        // [2]    epilogue -> MMA
-    const uint32_t slot = bar_tm_empty + 16;
+    const uint32_t bar_sfull = bar_tm_empty + 16;          // [NSLOT] chunk ring: producer -> consumers
+    const uint32_t bar_sempty = bar_sfull + 8 * NSLOT;     // [NSLOT] consumers -> producer
+    const uint32_t ring = bar_sempty + 8 * NSLOT;          // [NSLOT] chunk ids
+    const uint32_t slot = ring + 4 * NSLOT;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot), "r"(L::TMEM_COLS) : "memory");
@@ -223,6 +259,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             mbar_init(bar_tm_full + 8 * i, 1);
             mbar_init(bar_tm_empty + 8 * i, 128);
         }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_sfull + 8 * i, 1); mbar_init(bar_sempty + 8 * i, 4 + NSPL + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid == W_TMA * 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmap_g)) : "memory");
@@ -232,21 +269,30 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(tmem_base) : "r"(slot));
 
-    const int c0 = (int)((long long)n_chunks * blockIdx.x / gridDim.x);
-    const int c1 = (int)((long long)n_chunks * (blockIdx.x + 1) / gridDim.x);
+    ChunkRing cr;
+    cr.ring = ring; cr.bar_sfull = bar_sfull; cr.bar_sempty = bar_sempty; cr.idx = 0; cr.n_chunks = n_chunks;
     TileIter ti;
-    ti.init(c0, c1, splits, tps);
 
     if (warp == W_TMA) {
         // ================================================================= TMA producer
         if (lane == 0) {
-            for (uint32_t it = 0; ti.valid(); ti.next(), ++it) {
-                const uint32_t s = it % NST, n = it / NST;
-                mbar_wait(bar_empty + 8 * s, (n & 1) ^ 1);
-                mbar_expect_tx(bar_full + 8 * s, L::G_BYTES);
-                const int row = (int)ti.row0();
-                tma_load_2d(sb + L::STAGE0 + s * L::G_BYTES, &tmap_g, 0, row, bar_full + 8 * s);
-                tma_load_2d(sb + L::STAGE0 + s * L::G_BYTES + L::BLK, &tmap_g, 32, row, bar_full + 8 * s);
+            // one chunk of look-ahead: the id of the next chunk is published before this chunk's loads are
+            // issued, so consumers that prefetch across a chunk boundary never wait for the producer
+            int cur = cr.draw(chunk_counter);
+            int nxt = cur < n_chunks ? cr.draw(chunk_counter) : n_chunks;
+            uint32_t it = 0;
+            while (cur < n_chunks) {
+                ti.set_chunk(cur, n_chunks, splits, tps);
+                for (; ti.t < ti.t_end; ++ti.t, ++it) {
+                    const uint32_t s = it % NST, n = it / NST;
+                    mbar_wait(bar_empty + 8 * s, (n & 1) ^ 1);
+                    mbar_expect_tx(bar_full + 8 * s, L::G_BYTES);
+                    const int row = (int)ti.row0();
+                    tma_load_2d(sb + L::STAGE0 + s * L::G_BYTES, &tmap_g, 0, row, bar_full + 8 * s);
+                    tma_load_2d(sb + L::STAGE0 + s * L::G_BYTES + L::BLK, &tmap_g, 32, row, bar_full + 8 * s);
+                }
+                cur = nxt;
+                if (cur < n_chunks) nxt = cr.draw(chunk_counter);
             }
         }
         __syncwarp();
@@ -254,7 +300,8 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
         // ================================================================= MMA issuer
         if (lane == 0) {
             uint32_t chunk_n = 0;
-            for (uint32_t it = 0; ti.valid(); ti.next(), ++it) {
+            ti.set_chunk(cr.take(false, 0), n_chunks, splits, tps);
+            for (uint32_t it = 0; ti.valid(); ti.next(cr, false, 0), ++it) {
                 const uint32_t s = it % NST, n = it / NST, j = it & 1, u = (it >> 1) & 1;
                 if (ti.first_in_chunk() && it > 0) ++chunk_n;
                 const uint32_t bsel = chunk_n & 1;
@@ -290,6 +337,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             for (int i = 0; i < (K * F) / 128; ++i) sts4(accw + (i * 32 + lane) * 16, make_float4(0.f, 0.f, 0.f, 0.f));
         };
         zero_acc();
+        ti.set_chunk(cr.take(true, lane), n_chunks, splits, tps);
         // this thread's slice of the B operand: part bn, 16-byte chunks [bc0, bc0 + BCH)
         constexpr int BCH = (K * 16) / (NSPL * 32);    // chunks per thread
         const int bn = st / (16 / BCH), bc0 = (st % (16 / BCH)) * BCH;
@@ -339,7 +387,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 }
             }
             // advance the schedule now so that the next tile's m0 (and the next chunk's feat) are in flight
-            ti.next();
+            ti.next(cr, true, lane);
             if (ti.valid()) {
 #pragma unroll
                 for (int p = 0; p < SPASS; ++p)
@@ -451,11 +499,12 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 tl4[p] = ld4_stream(g_inj + r * FK + F + 4 * c);
             }
         };
+        ti.set_chunk(cr.take(true, lane), n_chunks, splits, tps);
         if (ti.valid()) prefetch(ti.row0());
         for (uint32_t it = 0; ti.valid(); ++it) {
             const uint32_t j = it & 1, u = (it >> 1) & 1;
             const long long row0 = ti.row0();
-            ti.next();
+            ti.next(cr, true, lane);
             mbar_wait(bar_tm_full + 8 * j, u);
             tc_fence_after();
             // accumulator row (thread = pixel row warp*32 + lane): dm = D[:, 0:K] + D[:, K:2K]
@@ -539,7 +588,7 @@ size_t decode_bwd_tma_ws_bytes(int B, int P, int K, int F) {
     if (B <= 0 || P <= 0 || P % tma::TILE) return 0;
     const int tps = P / tma::TILE;
     const size_t splits = (size_t)cdiv(tps, tma::CHUNK_TILES);
-    return (size_t)B * splits * K * F * sizeof(float);
+    return (size_t)B * splits * K * F * sizeof(float) + 512;   // + the chunk counter (256-byte aligned)
 }
 
 }  // namespace ups
@@ -578,14 +627,17 @@ extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const
     const int grid = n_chunks < NUM_SMS ? n_chunks : NUM_SMS;
     cudaStream_t s = as_stream(stream);
     float* partial = static_cast<float*>(ws);
+    const size_t counter_off = (((size_t)B * splits * K * F * sizeof(float)) + 255) & ~(size_t)255;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + counter_off);
+    UPS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
     if (K == 16) {
         const size_t sm = tma::Cfg<16>::TOTAL + 1024;
         UPS_CUDA(cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tma::step_decode_bwd_tma_kernel<16><<<grid, tma::Cfg<16>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, n_chunks, splits, tps);
+        tma::step_decode_bwd_tma_kernel<16><<<grid, tma::Cfg<16>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, counter, n_chunks, splits, tps);
     } else {
         const size_t sm = tma::Cfg<32>::TOTAL + 1024;
         UPS_CUDA(cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tma::step_decode_bwd_tma_kernel<32><<<grid, tma::Cfg<32>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, n_chunks, splits, tps);
+        tma::step_decode_bwd_tma_kernel<32><<<grid, tma::Cfg<32>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, counter, n_chunks, splits, tps);
     }
     if (int rc = after_launch("step_decode_bwd_tma_kernel")) return rc;
     const long long n = (long long)B * K * F;

@@ -37,12 +37,12 @@ class PartStep:
         if self.device.type != "cuda":
             raise C.UpsError("PartStep needs a CUDA device: there is no CPU path")
         self.fused = K in (8, 16, 32) and F in (16, 32, 64) and self.P % 32 == 0
-        # K4 variant: "tc" = tcgen05/TMEM + mma.sync tensor-core kernel, "simt" = CUDA-core kernel
+        # K4 variant: "tc" = persistent TMA + tcgen05/TMEM pipeline, "simt" = CUDA-core kernel
         tc_ok = self.fused and K in (16, 32) and F == 64 and self.P % 128 == 0
-        assert decode_bwd in ("auto", "tc", "tc1", "simt")
-        if decode_bwd in ("tc", "tc1") and not tc_ok:
+        assert decode_bwd in ("auto", "tc", "simt")
+        if decode_bwd == "tc" and not tc_ok:
             raise C.UpsError("decode_bwd='tc' needs K in {16,32}, F == 64 and H*W % 128 == 0")
-        self.decode_bwd = (decode_bwd if decode_bwd != "auto" else "tc") if (tc_ok and decode_bwd != "simt") else "simt"
+        self.decode_bwd = "tc" if (tc_ok and decode_bwd != "simt") else "simt"
         f32 = dict(dtype=torch.float32, device=self.device)
         e = torch.empty
         self.T = e(2 * B, 2, 11, **f32)
@@ -121,7 +121,7 @@ class PartStep:
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         want_dimg = self.views_grad
         if self.fused:
-            C.call({"tc": "ups_step_decode_bwd_tc", "tc1": "ups_step_decode_bwd_tc1"}.get(self.decode_bwd, "ups_step_decode_bwd"),
+            C.call("ups_step_decode_bwd_tc" if self.decode_bwd == "tc" else "ups_step_decode_bwd",
                    g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
                    self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
             C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
