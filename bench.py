@@ -185,7 +185,8 @@ def run_gpu(args):
     S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
     P = S * S
     dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev,
-                              decode_bwd=args.decode_bwd)
+                              decode_bwd=args.decode_bwd, n_grad_params=int(args.grad_mb * 1e6 / 4),
+                              bucket_bytes=int(args.bucket_mb) << 20)
     step = dp.step
 
     # ---- synthetic shard, resident in HBM (rank-offset seed)
@@ -392,6 +393,10 @@ def main():
     ap.add_argument("--tps-bwd", action="store_true", help="also back-propagate into the input views (K6)")
     ap.add_argument("--decode-bwd", default="auto", choices=["auto", "tc", "simt"],
                     help="K4 variant: tcgen05 tensor-core kernel or CUDA-core kernel")
+    ap.add_argument("--grad-mb", type=float, default=133.2,
+                    help="size of the stand-in encoder/decoder gradient buffer all-reduced per step when N>1 "
+                         "(33.3 M fp32 parameters of the reference's CNNs, SURVEY.md section 2)")
+    ap.add_argument("--bucket-mb", type=int, default=256, help="all-reduce bucket size; the stand-in buffer is ready at once, so one bucket")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
