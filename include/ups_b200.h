@@ -43,7 +43,9 @@ enum ups_op {
     UPS_OP_POOL = 1,        /* part_pool_fwd / encode_fwd partial sums */
     UPS_OP_INJECT_BWD = 2,  /* part_inject_bwd / decode_bwd dfeat partial sums */
     UPS_OP_POOL_BWD = 3,    /* none */
-    UPS_OP_STEP = 4         /* ups_step_* (max over the four fused calls and their unfused stand-ins) */
+    UPS_OP_STEP = 4,        /* ups_step_* (max over the four fused calls and their unfused stand-ins) */
+    UPS_OP_MOMENTS = 5,     /* ups_mask_moments_fwd partial sums */
+    UPS_OP_KL = 6           /* ups_categorical_kl_fwd partial sums */
 };
 size_t ups_workspace_bytes(int op, int B, int P, int K, int F);
 
@@ -160,6 +162,23 @@ int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const float* g_m
  * dimg1 (optional) = sum_k mh*(g_parts + g_pooled/P).  g_pooled, g_m1, dimg1 may be NULL. */
 int ups_step_encode_bwd(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
                         const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, void* stream);
+
+/* ---- mask statistics on the probabilities (N1, N2) --------------------------
+ * probs_to_mu_sigma(probs, scaling_factor) — cub/code/nn.py:1541-1587 (call sites
+ * cub/code/SB_model48i/model.py:440,458,689).  probs [B,H,W,K]; scaling [B,K];
+ * mu [B,K,2] = (y, x) on the linspace(-1,1) grid; sigma [B,K,2,2]; moments [B,K,5] = the raw sums
+ * (p*y, p*x, p*y*y, p*y*x, p*x*x) kept for the backward.  ws from ups_workspace_bytes(UPS_OP_MOMENTS, B, H*W, K, 0). */
+int ups_mask_moments_fwd(const float* probs, const float* scaling, float* mu, float* sigma, float* moments, int B,
+                         int H, int W, int K, void* ws, size_t ws_bytes, void* stream);
+/* dprobs [B,H,W,K] from g_mu [B,K,2] / g_sigma [B,K,2,2] (either may be NULL); scaling_factor gets no gradient
+ * (the reference always passes a constant). */
+int ups_mask_moments_bwd(const float* g_mu, const float* g_sigma, const float* scaling, const float* moments,
+                         float* dprobs, int B, int H, int W, int K, void* stream);
+/* categorical_kl(probs) — cub/code/SB_model48i/model.py:21-25: mean over pixels of sum_k p*log(K*p + 1e-20).
+ * probs [n_pix,K] -> out[1].  ws from ups_workspace_bytes(UPS_OP_KL, ...). */
+int ups_categorical_kl_fwd(const float* probs, float* out, long long n_pix, int K, void* ws, size_t ws_bytes,
+                           void* stream);
+int ups_categorical_kl_bwd(const float* probs, const float* g_out, float* dprobs, long long n_pix, int K, void* stream);
 
 #ifdef __cplusplus
 }

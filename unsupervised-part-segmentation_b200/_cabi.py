@@ -42,9 +42,13 @@ _SIGS = {
     "ups_step_decode_bwd": [c_f] * 6 + [c_i] * 4 + [c_f, c_sz, c_f],
     "ups_step_decode_bwd_tc": [c_f] * 6 + [c_i] * 4 + [c_f, c_sz, c_f],
     "ups_step_encode_bwd": [c_f] * 7 + [c_i] * 3 + [c_f],
+    "ups_mask_moments_fwd": [c_f] * 5 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_mask_moments_bwd": [c_f] * 5 + [c_i] * 4 + [c_f],
+    "ups_categorical_kl_fwd": [c_f, c_f, c_ll, c_i, c_f, c_sz, c_f],
+    "ups_categorical_kl_bwd": [c_f, c_f, c_f, c_ll, c_i, c_f],
 }
 
-OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP = 0, 1, 2, 3, 4
+OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP, OP_MOMENTS, OP_KL = 0, 1, 2, 3, 4, 5, 6
 
 
 class UpsError(RuntimeError):

@@ -578,6 +578,10 @@ extern "C" size_t ups_workspace_bytes(int op, int B, int P, int K, int F) {
             const size_t m = fused > unfused ? fused : unfused;
             return (m > tc ? m : tc) + 256;
         }
+        case UPS_OP_MOMENTS:
+            return (B <= 0 || P <= 0) ? 256 : moments_ws_bytes(B, P, K);
+        case UPS_OP_KL:
+            return (size_t)NUM_SMS * 8 * sizeof(float) + 256;
         default:
             return 0;
     }

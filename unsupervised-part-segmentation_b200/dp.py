@@ -65,7 +65,10 @@ class GradAllReducer:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 for b in self.buckets:
-                    dist.all_reduce(b, op=dist.ReduceOp.AVG)   # NCCL averages in the collective: no extra pass
+                    # SUM (not AVG): NCCL's in-switch NVLS algorithms exist for sum only, and on NVSwitch they
+                    # need far fewer SM-resident channels than the 32-channel ring AVG falls back to
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+                    b.mul_(1.0 / self.world)
                 self._done = torch.cuda.Event()
                 self._done.record(self.stream)
         else:

@@ -10,6 +10,11 @@ PARTS_DIM = 3      # cub/code/SB_model48i/model.py:12
 FEATURE_DIM = 4    # cub/code/SB_model48i/model.py:13
 
 
+def categorical_kl(probs):
+    """cub/code/SB_model48i/model.py:21-25 — reduce_mean over pixels of sum_k p*log(K*p + 1e-20)."""
+    return ops.categorical_kl(probs)
+
+
 def mask_parts(image, mask):
     """cub/code/SB_model48i/model.py:176-187 — [B,H,W,3],[B,H,W,parts] -> [B,H,W,parts,3]."""
     bs, h, w, n_features = image.shape

@@ -70,3 +70,12 @@ def unpool_features_gathered(feature_vectors, mask):
     assert len(fshape) == 3, fshape
     assert fshape[0] == bs, fshape
     return ops.part_gather(feature_vectors, mask)
+
+
+def probs_to_mu_sigma(probs, scaling_factor):
+    """cub/code/nn.py:1541-1587 — per-part mean (y, x) and 2x2 covariance of the [b,h,w,k] densities on
+    the linspace(-1, 1) grid; scaling_factor [b,k].  Returns (mu [b,k,2], sigma [b,k,2,2])."""
+    bn, h, w, nk = probs.shape
+    sf = scaling_factor.reshape(bn, nk)
+    mu, sigma, _ = ops.mask_moments(probs, sf)
+    return mu, sigma

@@ -422,3 +422,73 @@ def _part_gather(feat: Tensor, labels: Tensor) -> Tensor:
 
 
 part_gather = _op("part_gather", _part_gather, lambda f, l: f.new_empty(*l.shape, f.shape[-1]))
+
+
+# ------------------------------------------------------------------ mask statistics
+def _mask_moments(probs: Tensor, scaling: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    probs, scaling = _f32(probs, "probs"), _f32(scaling, "scaling_factor")
+    B, H, W, K = probs.shape
+    mu = torch.empty(B, K, 2, dtype=torch.float32, device=probs.device)
+    sigma = torch.empty(B, K, 2, 2, dtype=torch.float32, device=probs.device)
+    moments = torch.empty(B, K, 5, dtype=torch.float32, device=probs.device)
+    ws = _ws(C.workspace_bytes(C.OP_MOMENTS, B, H * W, K, 0), probs)
+    C.call("ups_mask_moments_fwd", probs.data_ptr(), scaling.data_ptr(), mu.data_ptr(), sigma.data_ptr(),
+           moments.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream())
+    return mu, sigma, moments
+
+
+def _mask_moments_fake(probs, scaling):
+    B, H, W, K = probs.shape
+    return probs.new_empty(B, K, 2), probs.new_empty(B, K, 2, 2), probs.new_empty(B, K, 5)
+
+
+def _mask_moments_grad(g_mu: Tensor, g_sigma: Tensor, scaling: Tensor, moments: Tensor, shape: list[int]) -> Tensor:
+    g_mu, g_sigma, scaling, moments = _f32(g_mu), _f32(g_sigma), _f32(scaling), _f32(moments)
+    B, H, W, K = shape
+    dprobs = torch.empty(B, H, W, K, dtype=torch.float32, device=moments.device)
+    C.call("ups_mask_moments_bwd", g_mu.data_ptr(), g_sigma.data_ptr(), scaling.data_ptr(), moments.data_ptr(),
+           dprobs.data_ptr(), B, H, W, K, _stream())
+    return dprobs
+
+
+mask_moments_grad = _op("mask_moments_grad", _mask_moments_grad,
+                        lambda gm, gs, s, m, shape: m.new_empty(shape))
+
+
+def _mask_moments_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1], output[2])
+    ctx.shape = list(inputs[0].shape)
+
+
+def _mask_moments_bwd(ctx, g_mu, g_sigma, g_moments):
+    scaling, moments = ctx.saved_tensors
+    g_mu = torch.zeros(moments.shape[0], moments.shape[1], 2, device=moments.device) if g_mu is None else g_mu
+    g_sigma = torch.zeros(moments.shape[0], moments.shape[1], 2, 2, device=moments.device) if g_sigma is None else g_sigma
+    return mask_moments_grad(g_mu, g_sigma, scaling, moments, ctx.shape), None
+
+
+mask_moments = _op("mask_moments", _mask_moments, _mask_moments_fake, _mask_moments_bwd, _mask_moments_setup)
+
+
+def _categorical_kl(probs: Tensor) -> Tensor:
+    probs = _f32(probs, "probs")
+    K = probs.shape[-1]
+    n_pix = probs.numel() // K
+    out = torch.empty((), dtype=torch.float32, device=probs.device)
+    ws = _ws(C.workspace_bytes(C.OP_KL, 0, 0, K, 0), probs)
+    C.call("ups_categorical_kl_fwd", probs.data_ptr(), out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def _categorical_kl_grad(probs: Tensor, g: Tensor) -> Tensor:
+    probs, g = _f32(probs), _f32(g)
+    K = probs.shape[-1]
+    d = torch.empty_like(probs)
+    C.call("ups_categorical_kl_bwd", probs.data_ptr(), g.data_ptr(), d.data_ptr(), probs.numel() // K, K, _stream())
+    return d
+
+
+categorical_kl_grad = _op("categorical_kl_grad", _categorical_kl_grad, lambda p, g: torch.empty_like(p))
+categorical_kl = _op("categorical_kl", _categorical_kl, lambda p: p.new_empty(()),
+                     lambda ctx, g: categorical_kl_grad(ctx.saved_tensors[0], g),
+                     lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
