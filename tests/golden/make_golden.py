@@ -8,8 +8,9 @@ Reference functions executed (file:line of the definitions):
   baselines/unsupervised-disentangling/transformations.py: tf_rotation_mat :5, tps_parameters :17,
       make_input_tps_param :59, ThinPlateSpline :93
   cub/code/nn.py: softmax :58, spatial_softmax :65, apply_partwise :81, hard_max_straight_through :118,
-      hard_max :134, straight_through_estimator :154, mask2hotmask :2086, unpool_features_gathered :2469
-  cub/code/SB_model48i/model.py: mask_parts :176, encode_parts :214, unpool_features :225
+      hard_max :134, straight_through_estimator :154, probs_to_mu_sigma :1541, mask2hotmask :2086,
+      unpool_features_gathered :2469
+  cub/code/SB_model48i/model.py: categorical_kl :21, mask_parts :176, encode_parts :214, unpool_features :225
   deepfashion/code/foo.py: pool_features :287, unpool_features :462, pool_unpool_block :574
   baselines/unsupervised-disentangling/ops.py: get_features :182
 """
@@ -39,7 +40,7 @@ def load_reference():
     tf.load_functions(f"{REF}/cub/code/nn.py",
                       ["softmax", "spatial_softmax", "apply_partwise", "hard_max_straight_through",
                        "hard_max", "straight_through_estimator", "mask2hotmask",
-                       "unpool_features_gathered"], ns_nn)
+                       "unpool_features_gathered", "probs_to_mu_sigma"], ns_nn)
     nn = types.SimpleNamespace(**{k: v for k, v in ns_nn.items() if callable(v)})
     ns_model = dict(tf=tf, np=np, nn=nn, PARTS_DIM=3, FEATURE_DIM=4)
     tf.load_functions(f"{REF}/cub/code/SB_model48i/model.py",
@@ -47,6 +48,7 @@ def load_reference():
     ns_foo = dict(tf=tf, np=np, nn=nn)
     tf.load_functions(f"{REF}/deepfashion/code/foo.py",
                       ["pool_features", "unpool_features", "pool_unpool_block"], ns_foo)
+    tf.load_functions(f"{REF}/cub/code/SB_model48i/model.py", ["categorical_kl"], ns_model)
     ns_ops = dict(tf=tf, np=np, wrappy=lambda f: f)
     tf.load_functions(f"{REF}/baselines/unsupervised-disentangling/ops.py", ["get_features"], ns_ops)
     return ns_tps, nn, ns_model, ns_foo, ns_ops
@@ -159,7 +161,30 @@ def gen_parts(nn, ns_model, ns_foo, ns_ops):
         lt=lt, pt=pt, pt_hard=nn.hard_max(pt, 3), pt_arg=tf.argmax(pt, axis=3))
 
 
+def gen_stats(ns_nn_funcs, ns_model):
+    """probs_to_mu_sigma (cub/code/nn.py:1541) and categorical_kl (model.py:21)
+    on spatial-softmax densities, as at cub/code/SB_model48i/model.py:437-440,659-661,683-689."""
+    g = torch.Generator().manual_seed(777)
+    out = {}
+    for tag, B, H, W, K in (("a", 2, 8, 8, 4), ("b", 1, 6, 10, 25)):
+        logits = T(torch.randn(B, H, W, K, generator=g)).requires_grad_(True)
+        dens = tf.reshape(tf._t(torch.softmax(logits.reshape(B, H * W, K), dim=1)), (B, H, W, K))   # sums to 1 over HW
+        sf = T(torch.rand(B, K, generator=g) * 0.5 + 0.75)
+        mu, sigma = ns_nn_funcs["probs_to_mu_sigma"](dens, sf)
+        p = tf._t(torch.softmax(logits, dim=-1))
+        kl = ns_model["categorical_kl"](p)
+        g_mu = torch.randn(mu.shape, generator=g)
+        g_sigma = torch.randn(sigma.shape, generator=g)
+        (d_dens,) = torch.autograd.grad([mu, sigma], [dens], [g_mu, g_sigma], retain_graph=True)
+        (d_p,) = torch.autograd.grad(kl, p, torch.tensor(1.0))
+        out.update({f"{tag}_dens": dens, f"{tag}_sf": sf, f"{tag}_mu": mu, f"{tag}_sigma": sigma, f"{tag}_p": p,
+                    f"{tag}_kl": kl, f"{tag}_g_mu": g_mu, f"{tag}_g_sigma": g_sigma, f"{tag}_d_dens": d_dens,
+                    f"{tag}_d_p": d_p})
+    npz("stats.npz", **out)
+
+
 if __name__ == "__main__":
     ns_tps, nn, ns_model, ns_foo, ns_ops = load_reference()
     gen_tps(ns_tps)
     gen_parts(nn, ns_model, ns_foo, ns_ops)
+    gen_stats(vars(nn), ns_model)

@@ -39,6 +39,16 @@ class TFTensor(torch.Tensor):
     def get_shape(self):
         return TShape(super().shape)
 
+    # TF tensors are immutable: `x *= y` rebinds the name to a new tensor (cub/code/nn.py:1586)
+    def __imul__(self, other):
+        return self * other
+
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
     def __getitem__(self, idx):
         # TF strided-slice allows x[..., ::-1]; torch does not -> slice, then flip
         if isinstance(idx, tuple) and any(isinstance(i, builtin_slice) and i.step == -1

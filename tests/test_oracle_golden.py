@@ -153,3 +153,22 @@ def test_ties_and_extremes(golden):
     close(p, g["pt"], 1e-5, 1e-30)
     close(P.hard_max(p, 3), g["pt_hard"], 0, 0)
     assert np.array_equal(P.argmax_labels(p).numpy(), g["pt_arg"])
+
+
+def test_mask_statistics(golden):
+    """probs_to_mu_sigma (cub/code/nn.py:1541-1587) and categorical_kl
+    (cub/code/SB_model48i/model.py:21-25), values and autograd gradients."""
+    from oracle import stats as S
+    g = golden("stats.npz")
+    for tag in ("a", "b"):
+        dens = t(g[f"{tag}_dens"]).requires_grad_(True)
+        mu, sigma = S.probs_to_mu_sigma(dens, t(g[f"{tag}_sf"]))
+        close(mu, g[f"{tag}_mu"], 1e-5, 1e-6)
+        close(sigma, g[f"{tag}_sigma"], 1e-5, 1e-6)
+        (d,) = torch.autograd.grad([mu, sigma], [dens], [t(g[f"{tag}_g_mu"]), t(g[f"{tag}_g_sigma"])])
+        close(d, g[f"{tag}_d_dens"], 1e-5, 1e-6)
+        p = t(g[f"{tag}_p"]).requires_grad_(True)
+        kl = S.categorical_kl(p)
+        close(kl, g[f"{tag}_kl"], 1e-6, 1e-7)
+        (dp,) = torch.autograd.grad(kl, p)
+        close(dp, g[f"{tag}_d_p"], 1e-5, 1e-7)
