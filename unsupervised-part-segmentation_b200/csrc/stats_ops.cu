@@ -12,8 +12,8 @@ constexpr int ST_TPB = 256;
 constexpr int NMOM = 5;  // sum p*y, p*x, p*y*y, p*y*x, p*x*x
 
 int moments_splits(int B, int P) {
-    // ~8 CTAs per SM in total, each with at least 512 pixels
-    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);
+    // ~32 CTAs per SM in total (several waves: short tail), each with at least 512 pixels
+    long long want = cdiv(32ll * NUM_SMS, B > 0 ? B : 1);
     const long long maxs = cdiv(P, 512);
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
@@ -50,6 +50,65 @@ __global__ void __launch_bounds__(ST_TPB) mask_moments_partial_kernel(const floa
     for (int e = t; e < K * NMOM; e += ST_TPB) {
         float s = 0.f;
         for (int ph = 0; ph < PP; ++ph) s += red[ph * K * NMOM + e];
+        partial[((size_t)b * gridDim.x + blockIdx.x) * (K * NMOM) + e] = s;
+    }
+}
+
+// Fast path for K = 4*LPP: LPP lanes per pixel, one float4 (4 parts) per lane, 4 pixels per lane in flight.
+// Lane-private accumulators, then a fixed shuffle tree over the warp's pixel groups and a fixed-order sum
+// over the CTA's warps.
+template <int LPP>
+__global__ void __launch_bounds__(ST_TPB) mask_moments_partial_vec_kernel(const float* __restrict__ probs,
+                                                                          float* __restrict__ partial, int P, int H,
+                                                                          int W, int pix_per_cta) {
+    constexpr int K = 4 * LPP, PW = 32 / LPP, NW = ST_TPB / 32, UN = 4;
+    __shared__ float red[NW][K * NMOM];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane & (LPP - 1), q = lane / LPP;
+    const int p_begin = blockIdx.x * pix_per_cta, p_end = min(P, p_begin + pix_per_cta);
+    const float step_h = lin_step(H), step_w = lin_step(W);
+    float a[4][NMOM];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < NMOM; ++m) a[i][m] = 0.f;
+    const float* src = probs + (size_t)b * P * K + 4 * c;
+    for (int p0 = p_begin + warp * PW * UN; p0 < p_end; p0 += NW * PW * UN) {
+        float4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int p = p0 + u * PW + q;
+            v[u] = p < p_end ? ld4_stream(src + (size_t)p * K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int p = min(p0 + u * PW + q, P - 1);
+            const int i = p / W, j = p - i * W;
+            const float y = lin_at(i, step_h), x = lin_at(j, step_w);
+            const float yy = y * y, yx = y * x, xx = x * x;
+            const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a[e][0] = fmaf(vv[e], y, a[e][0]); a[e][1] = fmaf(vv[e], x, a[e][1]);
+                a[e][2] = fmaf(vv[e], yy, a[e][2]); a[e][3] = fmaf(vv[e], yx, a[e][3]);
+                a[e][4] = fmaf(vv[e], xx, a[e][4]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int m = 0; m < NMOM; ++m) {
+            float s = a[e][m];
+#pragma unroll
+            for (int o = LPP; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (q == 0) red[warp][(4 * c + e) * NMOM + m] = s;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * NMOM; e += ST_TPB) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[w][e];
         partial[((size_t)b * gridDim.x + blockIdx.x) * (K * NMOM) + e] = s;
     }
 }
@@ -110,6 +169,42 @@ __global__ void __launch_bounds__(ST_TPB) mask_moments_bwd_kernel(const float* _
     }
 }
 
+template <int LPP>
+__global__ void __launch_bounds__(ST_TPB) mask_moments_bwd_vec_kernel(const float* __restrict__ g_mu,
+                                                                      const float* __restrict__ g_sigma,
+                                                                      const float* __restrict__ scaling,
+                                                                      const float* __restrict__ moments,
+                                                                      float* __restrict__ dprobs, int P, int H, int W,
+                                                                      int pix_per_cta) {
+    constexpr int K = 4 * LPP, PW = 32 / LPP, NW = ST_TPB / 32;
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane & (LPP - 1), q = lane / LPP;
+    float c0[4], c1[4], c2[4], c3[4], c4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const size_t bk = (size_t)b * K + 4 * c + e;
+        const float s1 = scaling[bk], s2 = s1 * s1;
+        const float m0 = moments[bk * NMOM], m1 = moments[bk * NMOM + 1];
+        const float g00 = g_sigma ? g_sigma[bk * 4] : 0.f, g01 = g_sigma ? g_sigma[bk * 4 + 1] + g_sigma[bk * 4 + 2] : 0.f,
+                    g11 = g_sigma ? g_sigma[bk * 4 + 3] : 0.f;
+        const float gm0 = g_mu ? g_mu[bk * 2] : 0.f, gm1 = g_mu ? g_mu[bk * 2 + 1] : 0.f;
+        c2[e] = s2 * g00; c3[e] = s2 * g01; c4[e] = s2 * g11;
+        c0[e] = s1 * gm0 - s2 * (2.f * g00 * m0 + g01 * m1);
+        c1[e] = s1 * gm1 - s2 * (2.f * g11 * m1 + g01 * m0);
+    }
+    const int p_begin = blockIdx.x * pix_per_cta, p_end = min(P, p_begin + pix_per_cta);
+    const float step_h = lin_step(H), step_w = lin_step(W);
+    float* dst = dprobs + (size_t)b * P * K + 4 * c;
+    for (int p = p_begin + warp * PW + q; p < p_end; p += NW * PW) {
+        const int i = p / W, j = p - i * W;
+        const float y = lin_at(i, step_h), x = lin_at(j, step_w);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = fmaf(y, fmaf(c2[e], y, fmaf(c3[e], x, c0[e])), x * fmaf(c4[e], x, c1[e]));
+        st4_stream(dst + (size_t)p * K, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 // ------------------------------------------------------------------ categorical KL
 constexpr int KL_BLOCKS = NUM_SMS * 8;
 
@@ -122,14 +217,15 @@ __global__ void __launch_bounds__(ST_TPB) categorical_kl_partial_kernel(const fl
     const long long stride = (long long)gridDim.x * ST_TPB;
     for (long long i = (long long)blockIdx.x * ST_TPB + threadIdx.x; i < n4; i += stride) {
         const float4 p = ld4_stream(probs + 4 * i);
-        acc += p.x * logf(fmaf(kf, p.x, 1e-20f));
-        acc += p.y * logf(fmaf(kf, p.y, 1e-20f));
-        acc += p.z * logf(fmaf(kf, p.z, 1e-20f));
-        acc += p.w * logf(fmaf(kf, p.w, 1e-20f));
+        // __logf (MUFU.LG2): abs error ~2^-21 on the log, far inside the 1e-4 / 1e-5 tolerance of the mean
+        acc = fmaf(p.x, __logf(fmaf(kf, p.x, 1e-20f)), acc);
+        acc = fmaf(p.y, __logf(fmaf(kf, p.y, 1e-20f)), acc);
+        acc = fmaf(p.z, __logf(fmaf(kf, p.z, 1e-20f)), acc);
+        acc = fmaf(p.w, __logf(fmaf(kf, p.w, 1e-20f)), acc);
     }
     if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {   // tail (n not a multiple of 4)
         const float p = probs[(n4 << 2) + threadIdx.x];
-        acc += p * logf(fmaf(kf, p, 1e-20f));
+        acc = fmaf(p, __logf(fmaf(kf, p, 1e-20f)), acc);
     }
     acc = group_sum<32>(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -159,7 +255,7 @@ __global__ void __launch_bounds__(ST_TPB) categorical_kl_bwd_kernel(const float*
     const long long n4 = n >> 2;
     auto d = [&](float p) {
         const float u = fmaf(kf, p, 1e-20f);
-        return g * (logf(u) + __fdividef(kf * p, u));
+        return g * (__logf(u) + __fdividef(kf * p, u));
     };
     if (i < n4) {
         const float4 p = ld4_stream(probs + 4 * i);
@@ -192,8 +288,16 @@ extern "C" int ups_mask_moments_fwd(const float* probs, const float* scaling, fl
     const int per = (int)cdiv(P, splits);
     cudaStream_t s = as_stream(stream);
     float* partial = static_cast<float*>(ws);
-    const size_t sm = (size_t)(ST_TPB / K) * K * NMOM * sizeof(float);
-    mask_moments_partial_kernel<<<dim3(splits, B), ST_TPB, sm, s>>>(probs, partial, P, H, W, K, per);
+    const dim3 grid(splits, B);
+    if ((K == 4 || K == 8 || K == 16 || K == 32) && aligned16(probs)) {
+        if (K == 4) mask_moments_partial_vec_kernel<1><<<grid, ST_TPB, 0, s>>>(probs, partial, P, H, W, per);
+        else if (K == 8) mask_moments_partial_vec_kernel<2><<<grid, ST_TPB, 0, s>>>(probs, partial, P, H, W, per);
+        else if (K == 16) mask_moments_partial_vec_kernel<4><<<grid, ST_TPB, 0, s>>>(probs, partial, P, H, W, per);
+        else mask_moments_partial_vec_kernel<8><<<grid, ST_TPB, 0, s>>>(probs, partial, P, H, W, per);
+    } else {
+        const size_t sm = (size_t)(ST_TPB / K) * K * NMOM * sizeof(float);
+        mask_moments_partial_kernel<<<grid, ST_TPB, sm, s>>>(probs, partial, P, H, W, K, per);
+    }
     if (int rc = after_launch("mask_moments_partial_kernel")) return rc;
     const long long n = (long long)B * K;
     mask_moments_finalize_kernel<<<(unsigned)cdiv(n, 128), 128, 0, s>>>(partial, scaling, moments, mu, sigma, splits, K, n);
@@ -208,8 +312,16 @@ extern "C" int ups_mask_moments_bwd(const float* g_mu, const float* g_sigma, con
     const int P = H * W;
     const int splits = moments_splits(B, P);
     const int per = (int)cdiv(P, splits);
-    mask_moments_bwd_kernel<<<dim3(splits, B), ST_TPB, 0, as_stream(stream)>>>(g_mu, g_sigma, scaling, moments, dprobs, P,
-                                                                               H, W, K, per);
+    const dim3 grid(splits, B);
+    cudaStream_t s = as_stream(stream);
+    if ((K == 4 || K == 8 || K == 16 || K == 32) && aligned16(dprobs)) {
+        if (K == 4) mask_moments_bwd_vec_kernel<1><<<grid, ST_TPB, 0, s>>>(g_mu, g_sigma, scaling, moments, dprobs, P, H, W, per);
+        else if (K == 8) mask_moments_bwd_vec_kernel<2><<<grid, ST_TPB, 0, s>>>(g_mu, g_sigma, scaling, moments, dprobs, P, H, W, per);
+        else if (K == 16) mask_moments_bwd_vec_kernel<4><<<grid, ST_TPB, 0, s>>>(g_mu, g_sigma, scaling, moments, dprobs, P, H, W, per);
+        else mask_moments_bwd_vec_kernel<8><<<grid, ST_TPB, 0, s>>>(g_mu, g_sigma, scaling, moments, dprobs, P, H, W, per);
+    } else {
+        mask_moments_bwd_kernel<<<grid, ST_TPB, 0, s>>>(g_mu, g_sigma, scaling, moments, dprobs, P, H, W, K, per);
+    }
     return after_launch("mask_moments_bwd_kernel");
 }
 

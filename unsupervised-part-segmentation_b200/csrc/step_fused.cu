@@ -12,6 +12,8 @@
 // Reductions over pixels (pooled, dfeat) are accumulated privately (per lane / per warp) in
 // shared memory, reduced in a fixed order per CTA and summed over splits by a second tiny
 // kernel: bit-reproducible run to run, no atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ups {
@@ -442,9 +444,11 @@ __global__ void split_finalize_kernel(const float* __restrict__ partial, float* 
     out[i] = divide_by > 0 ? s / (float)divide_by : s;
 }
 
-// pixels per CTA: aim at ~16 CTAs per SM-slot so the tail wave is short; multiple of 128
+// pixels per CTA: aim at ~96 CTAs per SM in total (many short waves: measured 16 -> 96 gives 3-7 % on the
+// HBM-bound kernels, profiles/r01_tuning.md); multiple of 128
 int fused_pix_per_cta(int B, int P) {
-    long long want = cdiv(16ll * NUM_SMS, B > 0 ? B : 1);
+    static const int target = []() { const char* e = getenv("UPS_FUSED_CTAS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 96; }();
+    long long want = cdiv((long long)target * NUM_SMS, B > 0 ? B : 1);
     long long maxs = cdiv(P, 128);
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
@@ -478,7 +482,11 @@ extern "C" int ups_step_decode_fwd(const float* l0, const float* feat, float* m0
     if (B == 0) return UPS_OK;
     const int per = fused_pix_per_cta(B, P);
     dim3 grid((unsigned)cdiv(P, per), B);
-    const size_t sm = (size_t)K * F * sizeof(float);
+    size_t sm = (size_t)K * F * sizeof(float);
+    // tuning knob: cap the resident CTAs per SM (by shared-memory footprint) so that a co-running kernel
+    // on another stream (K1, see step.py) keeps a share of every SM's registers
+    static const int cap = []() { const char* e = getenv("UPS_DECODE_FWD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (cap > 0) { const size_t want = (size_t)(200 * 1024) / cap - 1024; if (want > sm) sm = want; }
     cudaStream_t s = as_stream(stream);
 #define UPS_DEC_FWD2(LPP, FT)                                                                           \
     {                                                                                                   \

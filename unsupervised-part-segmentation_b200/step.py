@@ -16,6 +16,8 @@ The CNNs between those pieces are not part of the path: `l0`, `l1` (mask decoder
 to `backward`.  All buffers are allocated once in __init__ (180 GB HBM: the B=256 CUB step
 holds ~3.6 GB); forward/backward only enqueue kernels on the current stream.
 """
+import os
+
 import torch
 
 from . import _cabi as C
@@ -68,6 +70,12 @@ class PartStep:
         self._img1 = None
         self._feat = None
         self._coord = None
+        # K3 (decode side: l0, feat only) does not depend on the warp: it runs on a side stream beside
+        # K1 (issue-bound canonical TPS math, ~12 % DRAM) and K2
+        self.overlap_fwd = self.fused and self.use_tps and os.environ.get("UPS_OVERLAP_FWD", "1") != "0"
+        if self.overlap_fwd:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
 
     # ------------------------------------------------------------------ forward
     def forward(self, views, coord, t_vector, l0, l1, feat):
@@ -79,6 +87,14 @@ class PartStep:
         assert views.is_contiguous() and l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
         assert tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        if self.overlap_fwd:
+            main = torch.cuda.current_stream()
+            self._fork.record(main)
+            self._side.wait_event(self._fork)
+            with torch.cuda.stream(self._side):
+                C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
+                       self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, self._side.cuda_stream)
+                self._join.record(self._side)
         if self.use_tps:
             assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
             C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
@@ -97,8 +113,11 @@ class PartStep:
         if self.fused:
             C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
                    self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
-            C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
-                   self.inj.data_ptr(), B, P, K, F, st)
+            if self.overlap_fwd:
+                torch.cuda.current_stream().wait_event(self._join)
+            else:
+                C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
+                       self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
         else:
             C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
