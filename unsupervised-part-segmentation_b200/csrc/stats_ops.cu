@@ -12,9 +12,9 @@ constexpr int ST_TPB = 256;
 constexpr int NMOM = 5;  // sum p*y, p*x, p*y*y, p*y*x, p*x*x
 
 int moments_splits(int B, int P) {
-    // ~32 CTAs per SM in total (several waves: short tail), each with at least 512 pixels
-    long long want = cdiv(32ll * NUM_SMS, B > 0 ? B : 1);
-    const long long maxs = cdiv(P, 512);
+    // ~16 CTAs per SM in total (several waves: short tail), each with at least 1024 pixels
+    long long want = cdiv(16ll * NUM_SMS, B > 0 ? B : 1);
+    const long long maxs = cdiv(P, 1024);
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     return (int)want;
@@ -73,13 +73,19 @@ __global__ void __launch_bounds__(ST_TPB) mask_moments_partial_vec_kernel(const 
 #pragma unroll
         for (int m = 0; m < NMOM; ++m) a[i][m] = 0.f;
     const float* src = probs + (size_t)b * P * K + 4 * c;
-    for (int p0 = p_begin + warp * PW * UN; p0 < p_end; p0 += NW * PW * UN) {
-        float4 v[UN];
+    // register double buffer: the next 4 pixels per lane are in flight while the current ones are reduced
+    auto load = [&](float4 (&v)[UN], int p0) {
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int p = p0 + u * PW + q;
             v[u] = p < p_end ? ld4_stream(src + (size_t)p * K) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    float4 v[UN], nv[UN];
+    int p0 = p_begin + warp * PW * UN;
+    load(v, p0);
+    for (; p0 < p_end; p0 += NW * PW * UN) {
+        load(nv, p0 + NW * PW * UN);
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int p = min(p0 + u * PW + q, P - 1);
@@ -94,6 +100,8 @@ __global__ void __launch_bounds__(ST_TPB) mask_moments_partial_vec_kernel(const 
                 a[e][4] = fmaf(vv[e], xx, a[e][4]);
             }
         }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) v[u] = nv[u];
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e)
