@@ -25,7 +25,7 @@ if os.path.exists(lp):
     for r in rows[1:]:
         n = r[i_name].split("(")[0].replace("void ", "")
         agg.setdefault(n, []).append(float(r[i_val].replace(",", "")))
-    ours = {n: v for n, v in agg.items() if n.startswith(("ups::", "tc::"))}
+    ours = {n: v for n, v in agg.items() if n.startswith(("ups::", "tc::", "tma::"))}
     tot = sum(sum(v) for v in ours.values())
     out.append(f"## Launch list ({tag}_launches.csv: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
                "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e`)\n")

@@ -6,6 +6,7 @@
 
 #include "../../include/ups_b200.h"
 #include "canon_math.cuh"
+#include "pk_math.cuh"
 
 namespace ups {
 
@@ -88,19 +89,23 @@ template <int LPP>
 __device__ __forceinline__ float4 softmax4(float4 v, int c, float& pmax, int& arg, int& nmax) {
     float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
     m = group_max<LPP>(m);
+    // packed fp32x2 evaluation (pk_math.cuh): lanes bit-identical to exp_canon(__fsub_rn(v, m)) etc.
+    const pk::Ops o;
+    const pk::f2 m2 = pk::splat(m);
+    const pk::f2 d[2] = {o.sub(pk::pack(v.x, v.y), m2), o.sub(pk::pack(v.z, v.w), m2)};
+    pk::f2 ee[2];
+    pk::exp_canon2n<2>(o, d, ee);
+    const pk::f2 e01 = ee[0], e23 = ee[1];
     float4 e;
-    e.x = exp_canon(__fsub_rn(v.x, m));
-    e.y = exp_canon(__fsub_rn(v.y, m));
-    e.z = exp_canon(__fsub_rn(v.z, m));
-    e.w = exp_canon(__fsub_rn(v.w, m));
+    pk::unpack(e01, e.x, e.y);
+    pk::unpack(e23, e.z, e.w);
     float s = __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w));
     s = group_sum_canon<LPP>(s);
     const float rs = __frcp_rn(s);
+    const pk::f2 rs2 = pk::splat(rs);
     float4 p;
-    p.x = __fmul_rn(e.x, rs);
-    p.y = __fmul_rn(e.y, rs);
-    p.z = __fmul_rn(e.z, rs);
-    p.w = __fmul_rn(e.w, rs);
+    pk::unpack(o.mul(e01, rs2), p.x, p.y);
+    pk::unpack(o.mul(e23, rs2), p.z, p.w);
     pmax = group_max<LPP>(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w)));
     int a = 1 << 30;
     a = (p.w == pmax) ? 4 * c + 3 : a;
@@ -115,11 +120,14 @@ __device__ __forceinline__ float4 softmax4(float4 v, int c, float& pmax, int& ar
 
 // straight_through_estimator(hard_max(p), p) for the lane's 4 parts
 __device__ __forceinline__ float4 hard_st4(float4 p, float pmax) {
+    // fl(fl(h - p) + p), two parts per FFMA2
+    const pk::Ops o;
+    const pk::f2 p01 = pk::pack(p.x, p.y), p23 = pk::pack(p.z, p.w);
+    const pk::f2 h01 = pk::pack(p.x == pmax ? 1.0f : 0.0f, p.y == pmax ? 1.0f : 0.0f);
+    const pk::f2 h23 = pk::pack(p.z == pmax ? 1.0f : 0.0f, p.w == pmax ? 1.0f : 0.0f);
     float4 h;
-    h.x = st_value(p.x == pmax ? 1.0f : 0.0f, p.x);
-    h.y = st_value(p.y == pmax ? 1.0f : 0.0f, p.y);
-    h.z = st_value(p.z == pmax ? 1.0f : 0.0f, p.z);
-    h.w = st_value(p.w == pmax ? 1.0f : 0.0f, p.w);
+    pk::unpack(o.add(o.sub(h01, p01), p01), h.x, h.y);
+    pk::unpack(o.add(o.sub(h23, p23), p23), h.z, h.w);
     return h;
 }
 #endif

@@ -126,8 +126,9 @@ struct EncFwdSmem {
     static constexpr int WREG = MW + IW + MON + LAB + ACC;
 };
 
-template <int LPP>
-__global__ void __launch_bounds__(FTPB) step_encode_fwd_kernel(const float* __restrict__ l1,
+// MINB: resident CTAs per SM asked of ptxas (an explicit value also keeps the exp chains interleaved)
+template <int LPP, int MINB>
+__global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float* __restrict__ l1,
                                                                const float* __restrict__ img1,
                                                                float* __restrict__ m1, float* __restrict__ parts,
                                                                float* __restrict__ partial, int B, int P,
@@ -514,13 +515,17 @@ extern "C" int ups_step_encode_fwd(const float* l1, const float* img1, float* m1
     dim3 grid(splits, B);
     cudaStream_t s = as_stream(stream);
     float* partial = static_cast<float*>(ws);
-#define UPS_ENC_FWD(LPP)                                                                                   \
-    {                                                                                                      \
-        const size_t sm = (size_t)FW * EncFwdSmem<LPP>::WREG * sizeof(float);                              \
-        if (int rc = set_smem(step_encode_fwd_kernel<LPP>, sm)) return rc;                                 \
-        step_encode_fwd_kernel<LPP><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per);    \
+    static const int minb = []() { const char* e = getenv("UPS_ENC_FWD_MINB"); return e ? atoi(e) : 6; }();
+#define UPS_ENC_FWD2(LPP, MB)                                                                                 \
+    {                                                                                                         \
+        const size_t sm = (size_t)FW * EncFwdSmem<LPP>::WREG * sizeof(float);                                 \
+        if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB>, sm)) return rc;                                \
+        step_encode_fwd_kernel<LPP, MB><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per);   \
     }
+#define UPS_ENC_FWD(LPP) \
+    { if (minb == 4) UPS_ENC_FWD2(LPP, 4) else if (minb == 5) UPS_ENC_FWD2(LPP, 5) else UPS_ENC_FWD2(LPP, 6) }
     if (K == 4) UPS_ENC_FWD(1) else if (K == 8) UPS_ENC_FWD(2) else if (K == 16) UPS_ENC_FWD(4) else UPS_ENC_FWD(8)
+#undef UPS_ENC_FWD2
 #undef UPS_ENC_FWD
     if (int rc = after_launch("step_encode_fwd_kernel")) return rc;
     const long long n = (long long)B * K * 3;
