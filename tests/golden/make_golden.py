@@ -183,8 +183,73 @@ def gen_stats(ns_nn_funcs, ns_model):
     npz("stats.npz", **out)
 
 
+def gen_priors():
+    """mask priors and sampling on the part logits / probabilities.
+    Reference functions executed: cub/code/nn.py fd_kernel :1357, tf_grad :1366, tf_squared_grad :1374,
+    mumford_shah :1381, edge_set :1389, MeanFieldDistribution :1395 (sample :1421, kl_improper_gmrf :1444,
+    kl_tv :1453), mask2hotmask :2086, mask2rgb :2067; call sites cub/code/SB_model48i/model.py:420-421 (sample),
+    :667-681 (weak cross entropy), :744-769 (Mumford-Shah sums, area cost), :1071 (GMRF prior)."""
+    colors_holder = [None]
+    ns = dict(tf=tf, np=np, make_mask_colors=lambda n_parts: colors_holder[0])
+    tf.load_functions(f"{REF}/cub/code/nn.py",
+                      ["difference1d", "fd_kernel", "tf_grad", "tf_squared_grad", "mumford_shah", "edge_set",
+                       "MeanFieldDistribution", "mask2hotmask", "mask2rgb", "softmax", "spatial_softmax", "hard_max",
+                       "straight_through_estimator"], ns)
+    g = torch.Generator().manual_seed(2024)
+    tf.set_generator(g)
+    out = {}
+    for tag, B, H, W, K in (("a", 2, 8, 8, 4), ("b", 1, 6, 10, 16)):
+        logits = T(torch.randn(B, H, W, K, generator=g)).requires_grad_(True)
+        p = tf._t(torch.softmax(logits, dim=-1)).detach().requires_grad_(True)
+        # --- Mumford-Shah on the probabilities (model.py:744-746); lambda chosen so that both branches occur
+        alpha, lam = 1.0, 2.0e-3
+        r, smooth, contour = ns["mumford_shah"](p, alpha, lam)
+        assert 0.1 < float((smooth > 0).float().mean()) < 0.9
+        sums = [tf.reduce_sum(v, axis=(1, 2)) for v in (r, smooth, contour, p)]         # [B,K] each
+        cots = [torch.randn(v.shape, generator=g) for v in (r, smooth, contour)]
+        gsums = [torch.randn(v.shape, generator=g) for v in sums]
+        (d_p_elem,) = torch.autograd.grad([r, smooth, contour], [p], cots, retain_graph=True)
+        (d_p_sums,) = torch.autograd.grad(sums, [p], gsums, retain_graph=True)
+        edges = ns["edge_set"](p, alpha, lam)
+        # --- MeanFieldDistribution on the logits
+        dist = ns["MeanFieldDistribution"](logits, K)
+        tf.set_generator(torch.Generator().manual_seed(99))
+        sample = dist.sample(noise_level=0.7)
+        eps = torch.randn(B, H, W, K, generator=torch.Generator().manual_seed(99))      # the same draw
+        gmrf = dist.kl_improper_gmrf()
+        tv = dist.kl_tv()
+        kl0 = dist.kl()
+        (d_gmrf,) = torch.autograd.grad(gmrf, logits, torch.tensor(1.0), retain_graph=True)
+        (d_kl0,) = torch.autograd.grad(kl0, logits, torch.tensor(1.0), retain_graph=True)
+        tf.set_generator(g)
+        # --- weak cross entropy (model.py:667-681), both entropy_func settings
+        p_labels = ns["softmax"](logits, spatial=False)
+        labels = ns["straight_through_estimator"](ns["hard_max"](p_labels, 3), p_labels)
+        ce = tf.reduce_mean(tf.nn.softmax_cross_entropy_with_logits_v2(labels, logits, dim=3))
+        ent = tf.reduce_mean(tf.nn.softmax_cross_entropy_with_logits_v2(p_labels, logits, dim=3))
+        (d_ce,) = torch.autograd.grad(ce, logits, torch.tensor(1.0), retain_graph=True)
+        (d_ent,) = torch.autograd.grad(ent, logits, torch.tensor(1.0), retain_graph=True)
+        # --- mask2rgb with an explicit colour table (the reference's make_mask_colors is matplotlib's inferno
+        #     LUT, not available here and not on the path: the table is an input)
+        colors = torch.rand(K, 3, generator=g)
+        colors_holder[0] = colors.numpy().astype(np.float64)
+        rgb_hot = ns["mask2rgb"](p.detach(), True)
+        rgb_soft = ns["mask2rgb"](p.detach(), False)
+        out.update({f"{tag}_logits": logits, f"{tag}_p": p, f"{tag}_alpha": np.float32(alpha), f"{tag}_lam": np.float32(lam),
+                    f"{tag}_r": r, f"{tag}_smooth": smooth, f"{tag}_contour": contour, f"{tag}_edges": edges,
+                    f"{tag}_sum_r": sums[0], f"{tag}_sum_smooth": sums[1], f"{tag}_sum_contour": sums[2], f"{tag}_sum_p": sums[3],
+                    f"{tag}_g_r": cots[0], f"{tag}_g_smooth": cots[1], f"{tag}_g_contour": cots[2],
+                    f"{tag}_g_sum_r": gsums[0], f"{tag}_g_sum_smooth": gsums[1], f"{tag}_g_sum_contour": gsums[2],
+                    f"{tag}_g_sum_p": gsums[3], f"{tag}_d_p_elem": d_p_elem, f"{tag}_d_p_sums": d_p_sums,
+                    f"{tag}_eps": eps, f"{tag}_sample": sample, f"{tag}_gmrf": gmrf, f"{tag}_tv": tv, f"{tag}_kl0": kl0,
+                    f"{tag}_d_gmrf": d_gmrf, f"{tag}_d_kl0": d_kl0, f"{tag}_ce": ce, f"{tag}_ent": ent, f"{tag}_d_ce": d_ce,
+                    f"{tag}_d_ent": d_ent, f"{tag}_colors": colors, f"{tag}_rgb_hot": rgb_hot, f"{tag}_rgb_soft": rgb_soft})
+    npz("priors.npz", **out)
+
+
 if __name__ == "__main__":
     ns_tps, nn, ns_model, ns_foo, ns_ops = load_reference()
     gen_tps(ns_tps)
     gen_parts(nn, ns_model, ns_foo, ns_ops)
     gen_stats(vars(nn), ns_model)
+    gen_priors()

@@ -104,8 +104,8 @@ def ones_like(x):
     return _t(torch.ones_like(x))
 
 
-def zeros_like(x):
-    return _t(torch.zeros_like(x))
+def zeros_like(x, dtype=None):
+    return _t(torch.zeros_like(x, dtype=_DT.get(dtype, dtype)))
 
 
 def range(n):  # noqa: A001  (tf.range)
@@ -272,7 +272,73 @@ def map_fn(fn, elems, dtype=None):
     return _t(torch.stack(outs))
 
 
-nn = types.SimpleNamespace(softmax=lambda x, axis=-1: _t(torch.softmax(x, dim=axis)))
+def minimum(a, b):
+    # TF MinimumGrad routes the gradient to `a` where a <= b, else to `b`
+    a, b = _t(a), torch.as_tensor(b, dtype=a.dtype) * torch.ones_like(a)
+    return _t(torch.where(a <= b, a, b))
+
+
+def where(cond, x, y):
+    return _t(torch.where(cond, _t(x), _t(y)))
+
+
+def random_normal(shape, mean=0.0, stddev=1.0, dtype=float32):
+    return _t(torch.randn(_shape_arg(shape), generator=_GEN[0], dtype=float32) * stddev + mean)
+
+
+def _conv2d(input, filter, strides, padding):  # noqa: A002
+    # tf.nn.conv2d, NHWC input, HWIO filter, stride 1, SAME (odd kernels: symmetric zero padding);
+    # a numpy filter is converted to the input's dtype (convert_to_tensor with preferred dtype)
+    assert padding == "SAME" and list(strides) == [1, 1, 1, 1]
+    w = torch.as_tensor(np.asarray(filter), dtype=input.dtype) if not isinstance(filter, torch.Tensor) else filter
+    kh, kw = w.shape[0], w.shape[1]
+    assert kh % 2 == 1 and kw % 2 == 1
+    y = torch.nn.functional.conv2d(_t(input).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=(kh // 2, kw // 2))
+    return _t(y.permute(0, 2, 3, 1).contiguous())
+
+
+def _image_gradients(image):
+    # tf.image.image_gradients: forward differences, zero in the last row (dy) / last column (dx)
+    image = _t(image)
+    dy = torch.cat([image[:, 1:] - image[:, :-1], torch.zeros_like(image[:, :1])], dim=1)
+    dx = torch.cat([image[:, :, 1:] - image[:, :, :-1], torch.zeros_like(image[:, :, :1])], dim=2)
+    return _t(dy), _t(dx)
+
+
+def _total_variation(images):
+    # tf.image.total_variation for a 4-D batch: sum |dy| + sum |dx| over (1,2,3) -> [batch]
+    images = _t(images)
+    dy = images[:, 1:] - images[:, :-1]
+    dx = images[:, :, 1:] - images[:, :, :-1]
+    return _t(dy.abs().sum(dim=(1, 2, 3)) + dx.abs().sum(dim=(1, 2, 3)))
+
+
+class _XentV2(torch.autograd.Function):
+    """tf.nn.softmax_cross_entropy_with_logits_v2 (dim = last axis): loss = sum_k labels*(lse - (x - max));
+    registered gradient (nn_grad._SoftmaxCrossEntropyWithLogitsGrad, first order): d/dlogits = g*(softmax - labels)
+    -- the fused kernel's `backprop` output, NOT multiplied by sum(labels) -- and d/dlabels = -g*log_softmax."""
+
+    @staticmethod
+    def forward(ctx, labels, logits):
+        lsm = torch.log_softmax(logits, dim=-1)
+        ctx.save_for_backward(labels, lsm)
+        return -(labels * lsm).sum(dim=-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        labels, lsm = ctx.saved_tensors
+        g = g.unsqueeze(-1)
+        return -g * lsm, g * (torch.exp(lsm) - labels)
+
+
+def _xent_v2(labels, logits, dim=-1):
+    assert dim in (-1, logits.dim() - 1)
+    return _t(_XentV2.apply(_t(labels).as_subclass(torch.Tensor), _t(logits).as_subclass(torch.Tensor)))
+
+
+nn = types.SimpleNamespace(softmax=lambda x, axis=-1: _t(torch.softmax(x, dim=axis)), conv2d=_conv2d,
+                           softmax_cross_entropy_with_logits_v2=_xent_v2)
+image = types.SimpleNamespace(image_gradients=_image_gradients, total_variation=_total_variation)
 
 import builtins as _b  # noqa: E402
 builtin_range = _b.range
@@ -285,8 +351,14 @@ def load_functions(path, names, namespace):
     inside `namespace` (decorators kept).  The source text never leaves this process."""
     src = open(path).read()
     tree = ast.parse(src)
-    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
-    found = {n.name for n in wanted}
+    def _name(n):
+        if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+            return n.name
+        if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name):
+            return n.targets[0].id      # module-level constants such as nn.py's `difference1d`
+        return None
+    wanted = [n for n in tree.body if _name(n) in names]
+    found = {_name(n) for n in wanted}
     missing = set(names) - found
     assert not missing, (path, missing)
     mod = ast.Module(body=wanted, type_ignores=[])
