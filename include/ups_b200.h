@@ -45,7 +45,10 @@ enum ups_op {
     UPS_OP_POOL_BWD = 3,    /* none */
     UPS_OP_STEP = 4,        /* ups_step_* (max over the four fused calls and their unfused stand-ins) */
     UPS_OP_MOMENTS = 5,     /* ups_mask_moments_fwd partial sums */
-    UPS_OP_KL = 6           /* ups_categorical_kl_fwd partial sums */
+    UPS_OP_KL = 6,          /* ups_categorical_kl_fwd partial sums */
+    UPS_OP_MUMFORD_SHAH = 7, /* ups_mumford_shah_fwd partial sums (only when `sums` is requested) */
+    UPS_OP_LOGIT_PRIORS = 8, /* ups_logit_priors_fwd partial sums */
+    UPS_OP_WEAK_XENT = 9    /* ups_weak_xent_fwd partial sums (P = pixels per sample, B*P pixels in total) */
 };
 size_t ups_workspace_bytes(int op, int B, int P, int K, int F);
 
@@ -179,6 +182,49 @@ int ups_mask_moments_bwd(const float* g_mu, const float* g_sigma, const float* s
 int ups_categorical_kl_fwd(const float* probs, float* out, long long n_pix, int K, void* ws, size_t ws_bytes,
                            void* stream);
 int ups_categorical_kl_bwd(const float* probs, const float* g_out, float* dprobs, long long n_pix, int K, void* stream);
+
+/* ---- mask priors and mean-field sampling around the softmax ------------------ */
+/* mumford_shah(x, alpha, lambda_) / edge_set(x, alpha, lambda_) — cub/code/nn.py:1357-1392 (finite differences
+ * fd_kernel/tf_grad/tf_squared_grad :1357-1378), call site cub/code/SB_model48i/model.py:744-769.
+ * x [B,H,W,K] -> r, smooth, contour, edges [B,H,W,K] (each may be NULL) and sums [B,4,K] = sum over (h,w) of
+ * (r, smooth, contour, x) (may be NULL; these are what the training step squares).  Elementwise outputs are
+ * bit-identical to the reference expression.  ws from ups_workspace_bytes(UPS_OP_MUMFORD_SHAH, B, H*W, K, 0),
+ * needed only with `sums`. */
+int ups_mumford_shah_fwd(const float* x, float alpha, float lambda, float* r, float* smooth, float* contour,
+                         float* edges, float* sums, int B, int H, int W, int K, void* ws, size_t ws_bytes, void* stream);
+/* dx [B,H,W,K] from elementwise cotangents g_r / g_smooth / g_contour [B,H,W,K] and/or g_sums [B,4,K] (each may be
+ * NULL); tf.minimum routes the gradient to alpha*g where alpha*g <= lambda, tf.where to the selected branch. */
+int ups_mumford_shah_bwd(const float* x, float alpha, float lambda, const float* g_r, const float* g_smooth,
+                         const float* g_contour, const float* g_sums, float* dx, int B, int H, int W, int K, void* stream);
+/* MeanFieldDistribution.kl / kl_improper_gmrf / kl_tv — cub/code/nn.py:1429-1451 (call site model.py:1071):
+ * mean [B,H,W,K] -> out[3] = (0.5*sum mean^2, 0.5*sum (dy^2+dx^2), sum |dy|+|dx|), each averaged over the batch;
+ * dy/dx = tf.image.image_gradients (forward differences, zero in the last row / column).
+ * ws from ups_workspace_bytes(UPS_OP_LOGIT_PRIORS, ...). */
+int ups_logit_priors_fwd(const float* mean, float* out, int B, int H, int W, int K, void* ws, size_t ws_bytes, void* stream);
+/* dmean [B,H,W,K] = sum_i g_out[i] * d out[i] / d mean, g_out[3] on the device. */
+int ups_logit_priors_bwd(const float* mean, const float* g_out, float* dmean, int B, int H, int W, int K, void* stream);
+/* MeanFieldDistribution.sample(noise_level) — cub/code/nn.py:1421-1427 (call site model.py:420-421):
+ * out = mean + noise_level*eps, n elements; the N(0,1) draw `eps` is an input.  ups_part_softmax_sampled_fwd fuses
+ * this in front of the softmax. */
+int ups_mean_field_sample_fwd(const float* mean, const float* eps, float noise_level, float* out, long long n, void* stream);
+/* softmax(MeanFieldDistribution.sample()) in one pass: like ups_part_softmax_fwd on logits = mean + noise_level*eps;
+ * logits_out (may be NULL) receives the sampled logits (model.py:423-424 keeps them as m0_logits / m1_logits). */
+int ups_part_softmax_sampled_fwd(const float* mean, const float* eps, float noise_level, float* logits_out, float* probs,
+                                 int64_t* labels, float* hard, long long n_pix, int K, void* stream);
+/* weak cross entropy — cub/code/SB_model48i/model.py:667-681: mean over pixels of
+ * softmax_cross_entropy_with_logits_v2(labels, logits) with labels = ST(hard_max(softmax(logits))) (mode 0,
+ * entropy_func "cross_entropy") or softmax(logits) (mode 1, "entropy").  logits [n_pix,K] -> out[1].
+ * ws from ups_workspace_bytes(UPS_OP_WEAK_XENT, B, P, K, 0) with B*P = n_pix. */
+int ups_weak_xent_fwd(const float* logits, int mode, float* out, long long n_pix, int K, void* ws, size_t ws_bytes,
+                      void* stream);
+/* dlogits with TF's registered gradient of the v2 op (into logits and into labels, the latter chained through the
+ * straight-through estimator and the softmax). */
+int ups_weak_xent_bwd(const float* logits, int mode, const float* g_out, float* dlogits, long long n_pix, int K,
+                      void* stream);
+/* mask2rgb(mask, make_hot) — cub/code/nn.py:2067-2083 (mask2hotmask :2086-2089; eval_01.py:276-281):
+ * mask [n_pix,K], table [K,3] = (colors - 0.5)*2 (prepared by the caller as the reference does in numpy) ->
+ * out [n_pix,3]; make_hot: colour of the first maximum, else sum_k mask_k*table_k. */
+int ups_mask2rgb_fwd(const float* mask, const float* table, int make_hot, float* out, long long n_pix, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Roofline numbers for the mask-statistics kernels at the CUB bench shape:
+"""Roofline numbers for the mask-statistics / prior / sampling kernels at the CUB bench shape:
 probs [256,128,128,16].  CUDA-event timing per C-ABI call, algorithmic bytes / time vs the measured HBM peak."""
 import json
 import os
@@ -25,9 +25,20 @@ def main():
     g_mu, g_sigma = torch.randn(B, K, 2, device=dev), torch.randn(B, K, 2, 2, device=dev)
     d = torch.empty_like(probs)
     out, gout = torch.empty((), device=dev), torch.ones((), device=dev)
-    ws = torch.empty(max(C.workspace_bytes(C.OP_MOMENTS, B, H * W, K, 0), C.workspace_bytes(C.OP_KL, 0, 0, K, 0)),
+    ws = torch.empty(max(C.workspace_bytes(op, B, H * W, K, 0) for op in
+                         (C.OP_MOMENTS, C.OP_KL, C.OP_MUMFORD_SHAH, C.OP_LOGIT_PRIORS, C.OP_WEAK_XENT)),
                      dtype=torch.uint8, device=dev)
     nbytes = probs.numel() * 4
+    n_pix = B * H * W
+    logits = torch.randn(B, H, W, K, device=dev, generator=g)
+    eps = torch.randn(B, H, W, K, device=dev, generator=g)
+    d2, d3 = torch.empty_like(probs), torch.empty_like(probs)
+    labels = torch.empty(B, H, W, dtype=torch.int64, device=dev)
+    sums, g_sums = torch.empty(B, 4, K, device=dev), torch.randn(B, 4, K, device=dev)
+    pri, g_pri = torch.empty(3, device=dev), torch.ones(3, device=dev)
+    table, rgb = torch.rand(K, 3, device=dev) * 2 - 1, torch.empty(B, H, W, 3, device=dev)
+    lam = float(1.0 * (0.25 * (probs[:, :, :-1] - probs[:, :, 1:])).square().median() * 2)
+    P = lambda t: t.data_ptr()  # noqa: E731
     calls = {
         "ups_mask_moments_fwd": (lambda: C.call("ups_mask_moments_fwd", probs.data_ptr(), sf.data_ptr(), mu.data_ptr(),
                                                 sigma.data_ptr(), mom.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), st), nbytes),
@@ -37,6 +48,24 @@ def main():
                                                   ws.data_ptr(), ws.numel(), st), nbytes),
         "ups_categorical_kl_bwd": (lambda: C.call("ups_categorical_kl_bwd", probs.data_ptr(), gout.data_ptr(), d.data_ptr(),
                                                   B * H * W, K, st), 2 * nbytes),
+        "ups_mumford_shah_fwd(sums)": (lambda: C.call("ups_mumford_shah_fwd", P(probs), 1.0, lam, None, None, None, None, P(sums),
+                                                      B, H, W, K, P(ws), ws.numel(), st), nbytes),
+        "ups_mumford_shah_fwd(maps)": (lambda: C.call("ups_mumford_shah_fwd", P(probs), 1.0, lam, P(d), P(d2), P(d3), None, None,
+                                                      B, H, W, K, None, 0, st), 4 * nbytes),
+        "ups_mumford_shah_bwd(sums)": (lambda: C.call("ups_mumford_shah_bwd", P(probs), 1.0, lam, None, None, None, P(g_sums), P(d),
+                                                      B, H, W, K, st), 2 * nbytes),
+        "ups_logit_priors_fwd": (lambda: C.call("ups_logit_priors_fwd", P(logits), P(pri), B, H, W, K, P(ws), ws.numel(), st), nbytes),
+        "ups_logit_priors_bwd": (lambda: C.call("ups_logit_priors_bwd", P(logits), P(g_pri), P(d), B, H, W, K, st), 2 * nbytes),
+        "ups_mean_field_sample_fwd": (lambda: C.call("ups_mean_field_sample_fwd", P(logits), P(eps), 0.7, P(d), logits.numel(), st),
+                                      3 * nbytes),
+        "ups_part_softmax_sampled_fwd": (lambda: C.call("ups_part_softmax_sampled_fwd", P(logits), P(eps), 0.7, P(d), P(d2),
+                                                        P(labels), P(d3), n_pix, K, st), 5 * nbytes + 8 * n_pix),
+        "ups_part_softmax_fwd": (lambda: C.call("ups_part_softmax_fwd", P(logits), P(d2), P(labels), P(d3), n_pix, K, st),
+                                 3 * nbytes + 8 * n_pix),
+        "ups_weak_xent_fwd": (lambda: C.call("ups_weak_xent_fwd", P(logits), 0, P(out), n_pix, K, P(ws), ws.numel(), st), nbytes),
+        "ups_weak_xent_bwd": (lambda: C.call("ups_weak_xent_bwd", P(logits), 0, P(gout), P(d), n_pix, K, st), 2 * nbytes),
+        "ups_mask2rgb_fwd(hot)": (lambda: C.call("ups_mask2rgb_fwd", P(probs), P(table), 1, P(rgb), n_pix, K, st),
+                                  nbytes + 12 * n_pix),
     }
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2; READ to flush (clean lines)
     res = {}

@@ -73,6 +73,10 @@ REF_SIGNATURES = {
     "get_features": "(features, part_map, slim)",                     # baselines/unsupervised-disentangling/ops.py:182
     "make_input_tps_param": "(tps_param, move_point=None, scal_point=None)",       # transformations.py:59
     "ThinPlateSpline": "(U, coord, vector, out_size, n_c, move=None, scal=None)",  # transformations.py:93
+    "probs_to_mu_sigma": "(probs, scaling_factor)",                   # cub/code/nn.py:1541
+    "categorical_kl": "(probs)",                                      # cub/code/SB_model48i/model.py:21
+    "mumford_shah": "(x, alpha, lambda_)",                            # cub/code/nn.py:1381
+    "edge_set": "(x, alpha, lambda_)",                                # cub/code/nn.py:1389
 }
 
 
@@ -83,6 +87,13 @@ def test_reference_signatures(ups):
     assert list(p)[:7] == ["batch_size", "scal", "tps_scal", "rot_scal", "off_scal", "scal_var", "rescal"]
     assert p["rescal"].default == 1 and "augm_scal" in p
     assert list(inspect.signature(ups.make_tps).parameters)[:2] == ["views", "tps_parameters"]  # model.py:282
+    p = inspect.signature(ups.mask2rgb).parameters           # cub/code/nn.py:2067 (+ the colour table as an input)
+    assert list(p)[:2] == ["mask", "make_hot"] and p["make_hot"].default is True
+    mf = ups.MeanFieldDistribution                            # cub/code/nn.py:1395-1457
+    assert str(inspect.signature(mf.__init__)) == "(self, parameters, dim, stochastic=True)"
+    assert list(inspect.signature(mf.sample).parameters)[:2] == ["self", "noise_level"]
+    for m in ("kl", "kl_improper_gmrf", "kl_tv", "kl_mumford_sha", "n_parameters"):
+        assert hasattr(mf, m), m
 
 
 def test_tps_parameters_ranges_and_structure(ups):

@@ -172,3 +172,43 @@ def test_mask_statistics(golden):
         close(kl, g[f"{tag}_kl"], 1e-6, 1e-7)
         (dp,) = torch.autograd.grad(kl, p)
         close(dp, g[f"{tag}_d_p"], 1e-5, 1e-7)
+
+
+def test_mask_priors(golden):
+    """Mumford-Shah costs and edge set (cub/code/nn.py:1357-1392), the mean-field sample and its
+    KL / GMRF / TV priors (:1395-1451), the weak cross entropy (cub/code/SB_model48i/model.py:667-681) and mask2rgb
+    (cub/code/nn.py:2067-2083): values bit-exact where the chain is elementwise, gradients by autograd."""
+    from oracle import priors as R
+    g = golden("priors.npz")
+    for tag in ("a", "b"):
+        alpha, lam = float(g[f"{tag}_alpha"]), float(g[f"{tag}_lam"])
+        p = t(g[f"{tag}_p"]).requires_grad_(True)
+        r, smooth, contour = R.mumford_shah(p, alpha, lam)
+        for got, k in ((r, "r"), (smooth, "smooth"), (contour, "contour"), (R.edge_set(p, alpha, lam), "edges")):
+            close(got, g[f"{tag}_{k}"], 0, 0)
+        sums = R.mumford_shah_sums(p, alpha, lam)
+        for i, k in enumerate(("sum_r", "sum_smooth", "sum_contour", "sum_p")):
+            close(sums[:, i], g[f"{tag}_{k}"], 1e-5, 1e-7)
+        (d,) = torch.autograd.grad([r, smooth, contour], [p], [t(g[f"{tag}_g_{k}"]) for k in ("r", "smooth", "contour")],
+                                   retain_graph=True)
+        close(d, g[f"{tag}_d_p_elem"], 1e-5, 1e-7)
+        gs = torch.stack([t(g[f"{tag}_g_{k}"]) for k in ("sum_r", "sum_smooth", "sum_contour", "sum_p")], dim=1)
+        (d,) = torch.autograd.grad(sums, p, gs)
+        close(d, g[f"{tag}_d_p_sums"], 1e-5, 1e-7)
+
+        logits = t(g[f"{tag}_logits"]).requires_grad_(True)
+        close(R.mean_field_sample(logits, t(g[f"{tag}_eps"]), 0.7), g[f"{tag}_sample"], 0, 0)
+        pri = R.logit_priors(logits)
+        for i, k in enumerate(("kl0", "gmrf", "tv")):
+            close(pri[i], g[f"{tag}_{k}"], 1e-5, 1e-7)
+        for i, k in ((0, "d_kl0"), (1, "d_gmrf")):
+            (d,) = torch.autograd.grad(pri[i], logits, retain_graph=True)
+            close(d, g[f"{tag}_{k}"], 1e-5, 1e-7)
+        for mode, k in (("cross_entropy", "ce"), ("entropy", "ent")):
+            v = R.weak_cross_entropy(logits, mode)
+            close(v, g[f"{tag}_{k}"], 1e-5, 1e-7)
+            (d,) = torch.autograd.grad(v, logits)
+            close(d, g[f"{tag}_d_{k}"], 1e-4, 1e-7)
+        colors = t(g[f"{tag}_colors"])
+        close(R.mask2rgb(p.detach(), colors, True), g[f"{tag}_rgb_hot"], 0, 0)
+        close(R.mask2rgb(p.detach(), colors, False), g[f"{tag}_rgb_soft"], 1e-5, 1e-7)

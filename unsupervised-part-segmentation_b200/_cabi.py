@@ -46,9 +46,19 @@ _SIGS = {
     "ups_mask_moments_bwd": [c_f] * 5 + [c_i] * 4 + [c_f],
     "ups_categorical_kl_fwd": [c_f, c_f, c_ll, c_i, c_f, c_sz, c_f],
     "ups_categorical_kl_bwd": [c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_mumford_shah_fwd": [c_f, c_fl, c_fl] + [c_f] * 5 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_mumford_shah_bwd": [c_f, c_fl, c_fl] + [c_f] * 5 + [c_i] * 4 + [c_f],
+    "ups_logit_priors_fwd": [c_f, c_f] + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_logit_priors_bwd": [c_f, c_f, c_f] + [c_i] * 4 + [c_f],
+    "ups_mean_field_sample_fwd": [c_f, c_f, c_fl, c_f, c_ll, c_f],
+    "ups_part_softmax_sampled_fwd": [c_f, c_f, c_fl, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_weak_xent_fwd": [c_f, c_i, c_f, c_ll, c_i, c_f, c_sz, c_f],
+    "ups_weak_xent_bwd": [c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
+    "ups_mask2rgb_fwd": [c_f, c_f, c_i, c_f, c_ll, c_i, c_f],
 }
 
 OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP, OP_MOMENTS, OP_KL = 0, 1, 2, 3, 4, 5, 6
+OP_MUMFORD_SHAH, OP_LOGIT_PRIORS, OP_WEAK_XENT = 7, 8, 9
 
 
 class UpsError(RuntimeError):

@@ -20,6 +20,8 @@ int fused_pix_per_cta(int B, int P);  // step_fused.cu
 size_t pool_ws_bytes(int B, int P, int KF);  // parts_ops.cu
 size_t decode_bwd_tma_ws_bytes(int B, int P, int K, int F);  // step_decode_bwd_tma.cu
 size_t moments_ws_bytes(int B, int P, int K);  // stats_ops.cu
+size_t mumford_shah_ws_bytes(int B, int P, int K);  // priors_ops.cu
+size_t priors_scalar_ws_bytes();                    // priors_ops.cu
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -9,8 +9,11 @@ constexpr int TPB = 256;
 
 // =================================================================== softmax over parts
 // Fast path: K = 4*LPP, LPP lanes per pixel, one float4 per lane, fully coalesced.
-template <int LPP, int UNROLL>
+// SAMPLED: logits = mean + noise*eps first (MeanFieldDistribution.sample, cub/code/nn.py:1421-1427), one rounding per step.
+template <int LPP, int UNROLL, bool SAMPLED>
 __global__ void __launch_bounds__(TPB) part_softmax_fwd_kernel(const float* __restrict__ logits,
+                                                               const float* __restrict__ eps, float noise,
+                                                               float* __restrict__ logits_out,
                                                                float* __restrict__ probs,
                                                                long long* __restrict__ labels,
                                                                float* __restrict__ hard, long long n4) {
@@ -20,7 +23,14 @@ __global__ void __launch_bounds__(TPB) part_softmax_fwd_kernel(const float* __re
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const long long i = base + (long long)u * TPB;
-        v[u] = ld4_stream(logits + 4 * (i < n4 ? i : n4 - 1));
+        const long long ii = i < n4 ? i : n4 - 1;
+        v[u] = ld4_stream(logits + 4 * ii);
+        if (SAMPLED) {
+            const float4 e = ld4_stream(eps + 4 * ii);
+            v[u] = make_float4(__fadd_rn(v[u].x, __fmul_rn(noise, e.x)), __fadd_rn(v[u].y, __fmul_rn(noise, e.y)),
+                               __fadd_rn(v[u].z, __fmul_rn(noise, e.z)), __fadd_rn(v[u].w, __fmul_rn(noise, e.w)));
+            if (logits_out && i < n4) st4(logits_out + 4 * i, v[u]);
+        }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -38,6 +48,8 @@ __global__ void __launch_bounds__(TPB) part_softmax_fwd_kernel(const float* __re
 
 // Generic K (e.g. the reference's shipped n_parts = 25): one thread per pixel.
 __global__ void __launch_bounds__(128) part_softmax_fwd_generic_kernel(const float* __restrict__ logits,
+                                                                       const float* __restrict__ eps, float noise,
+                                                                       float* __restrict__ logits_out,
                                                                        float* __restrict__ probs,
                                                                        long long* __restrict__ labels,
                                                                        float* __restrict__ hard, long long n_pix,
@@ -46,6 +58,12 @@ __global__ void __launch_bounds__(128) part_softmax_fwd_generic_kernel(const flo
     if (i >= n_pix) return;
     float x[KMAX], p[KMAX], e[KMAX];
     for (int k = 0; k < K; ++k) x[k] = logits[i * K + k];
+    if (eps) {
+        for (int k = 0; k < K; ++k) {
+            x[k] = __fadd_rn(x[k], __fmul_rn(noise, eps[i * K + k]));
+            if (logits_out) logits_out[i * K + k] = x[k];
+        }
+    }
     const float pmax = softmax_row_canon(x, p, e, K);
     int arg = -1;
     for (int k = 0; k < K; ++k) {
@@ -358,19 +376,26 @@ using namespace ups;
 static inline unsigned nblk(long long n, int tpb) { return (unsigned)cdiv(n, tpb); }
 #define UPS_GRID_OK(n, tpb) UPS_REQUIRE(cdiv((n), (tpb)) < (1ll << 31), "problem too large for one launch")
 
-extern "C" int ups_part_softmax_fwd(const float* logits, float* probs, long long* labels, float* hard_st,
-                                    long long n_pix, int K, void* stream) {
-    UPS_REQUIRE(logits && probs, "part_softmax_fwd: null pointer");
-    UPS_REQUIRE(n_pix >= 0 && K >= 1 && K <= KMAX, "part_softmax_fwd: n_pix=%lld K=%d (1..%d)", n_pix, K, KMAX);
+static int part_softmax_fwd_impl(const char* what, const float* logits, const float* eps, float noise,
+                                 float* logits_out, float* probs, long long* labels, float* hard_st, long long n_pix,
+                                 int K, void* stream) {
+    UPS_REQUIRE(logits && probs, "%s: null pointer", what);
+    UPS_REQUIRE(n_pix >= 0 && K >= 1 && K <= KMAX, "%s: n_pix=%lld K=%d (1..%d)", what, n_pix, K, KMAX);
     if (n_pix == 0) return UPS_OK;
     cudaStream_t s = as_stream(stream);
-    const bool vec = aligned16(logits) && aligned16(probs) && (!hard_st || aligned16(hard_st));
+    const bool vec = aligned16(logits) && aligned16(probs) && (!hard_st || aligned16(hard_st)) && aligned16(eps) &&
+                     aligned16(logits_out);
     constexpr int U = 4;
 #define UPS_SM_FWD(LPP)                                                                                              \
     {                                                                                                                \
         const long long n4 = n_pix * LPP;                                                                            \
         UPS_GRID_OK(n4, TPB * U);                                                                                    \
-        part_softmax_fwd_kernel<LPP, U><<<nblk(n4, TPB * U), TPB, 0, s>>>(logits, probs, labels, hard_st, n4);       \
+        if (eps)                                                                                                     \
+            part_softmax_fwd_kernel<LPP, U, true><<<nblk(n4, TPB * U), TPB, 0, s>>>(logits, eps, noise, logits_out,  \
+                                                                                    probs, labels, hard_st, n4);     \
+        else                                                                                                         \
+            part_softmax_fwd_kernel<LPP, U, false><<<nblk(n4, TPB * U), TPB, 0, s>>>(logits, nullptr, 0.f, nullptr,  \
+                                                                                     probs, labels, hard_st, n4);    \
         return after_launch("part_softmax_fwd_kernel");                                                              \
     }
     if (vec && K == 4) UPS_SM_FWD(1)
@@ -379,8 +404,23 @@ extern "C" int ups_part_softmax_fwd(const float* logits, float* probs, long long
     if (vec && K == 32) UPS_SM_FWD(8)
 #undef UPS_SM_FWD
     UPS_GRID_OK(n_pix, 128);
-    part_softmax_fwd_generic_kernel<<<nblk(n_pix, 128), 128, 0, s>>>(logits, probs, labels, hard_st, n_pix, K);
+    part_softmax_fwd_generic_kernel<<<nblk(n_pix, 128), 128, 0, s>>>(logits, eps, noise, logits_out, probs, labels,
+                                                                     hard_st, n_pix, K);
     return after_launch("part_softmax_fwd_generic_kernel");
+}
+
+extern "C" int ups_part_softmax_fwd(const float* logits, float* probs, long long* labels, float* hard_st,
+                                    long long n_pix, int K, void* stream) {
+    return part_softmax_fwd_impl("part_softmax_fwd", logits, nullptr, 0.f, nullptr, probs, labels, hard_st, n_pix, K,
+                                 stream);
+}
+
+extern "C" int ups_part_softmax_sampled_fwd(const float* mean, const float* eps, float noise_level, float* logits_out,
+                                            float* probs, int64_t* labels, float* hard_st, long long n_pix, int K,
+                                            void* stream) {
+    UPS_REQUIRE(eps, "part_softmax_sampled_fwd: null pointer");
+    return part_softmax_fwd_impl("part_softmax_sampled_fwd", mean, eps, noise_level, logits_out, probs,
+                                 reinterpret_cast<long long*>(labels), hard_st, n_pix, K, stream);
 }
 
 extern "C" int ups_part_softmax_bwd(const float* probs, const float* g, float* dlogits, long long n_pix, int K,
@@ -582,6 +622,15 @@ extern "C" size_t ups_workspace_bytes(int op, int B, int P, int K, int F) {
             return (B <= 0 || P <= 0) ? 256 : moments_ws_bytes(B, P, K);
         case UPS_OP_KL:
             return (size_t)NUM_SMS * 8 * sizeof(float) + 256;
+        case UPS_OP_MUMFORD_SHAH:
+            return (B <= 0 || P <= 0) ? 256 : mumford_shah_ws_bytes(B, P, K);
+        case UPS_OP_LOGIT_PRIORS:
+            return priors_scalar_ws_bytes();
+        case UPS_OP_WEAK_XENT: {
+            const size_t generic = (B <= 0 || P <= 0) ? 0 : (size_t)cdiv((long long)B * P, 128) * sizeof(float);
+            const size_t fast = priors_scalar_ws_bytes();
+            return (generic > fast ? generic : fast) + 256;
+        }
         default:
             return 0;
     }

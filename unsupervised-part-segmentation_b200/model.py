@@ -15,6 +15,16 @@ def categorical_kl(probs):
     return ops.categorical_kl(probs)
 
 
+def weak_cross_entropy(log_probs, entropy_func="cross_entropy"):
+    """cub/code/SB_model48i/model.py:667-681 — reduce_mean of softmax_cross_entropy_with_logits_v2 between the part
+    logits and their own straight-through hard assignment ("cross_entropy") or their softmax ("entropy")."""
+    if entropy_func == "cross_entropy":
+        return ops.weak_xent(log_probs, 0)
+    elif entropy_func == "entropy":
+        return ops.weak_xent(log_probs, 1)
+    raise ValueError("unkown entropy_func")
+
+
 def mask_parts(image, mask):
     """cub/code/SB_model48i/model.py:176-187 — [B,H,W,3],[B,H,W,parts] -> [B,H,W,parts,3]."""
     bs, h, w, n_features = image.shape

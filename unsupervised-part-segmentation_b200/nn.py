@@ -79,3 +79,92 @@ def probs_to_mu_sigma(probs, scaling_factor):
     sf = scaling_factor.reshape(bn, nk)
     mu, sigma, _ = ops.mask_moments(probs, sf)
     return mu, sigma
+
+
+# ------------------------------------------------------------------ mask priors and sampling
+def mumford_shah(x, alpha, lambda_):
+    """cub/code/nn.py:1381-1386 — (r, smoothness_cost, contour_cost) of the finite-difference energy
+    g = |tf_grad(x)|^2 (nn.py:1357-1378), each [b,h,w,k]."""
+    assert x.dim() == 4, list(x.shape)
+    return ops.mumford_shah(x, float(alpha), float(lambda_))
+
+
+def mumford_shah_sums(x, alpha, lambda_):
+    """The four spatial sums cub/code/SB_model48i/model.py:744-769 squares: [b,4,k] = sum over (h,w) of
+    (r, smoothness_cost, contour_cost, x), in one pass over x and without the three [b,h,w,k] maps."""
+    assert x.dim() == 4, list(x.shape)
+    return ops.mumford_shah_sums(x, float(alpha), float(lambda_))
+
+
+def edge_set(x, alpha, lambda_):
+    """cub/code/nn.py:1389-1392."""
+    assert x.dim() == 4, list(x.shape)
+    return ops.edge_set(x.detach(), float(alpha), float(lambda_))
+
+
+class MeanFieldDistribution(object):
+    """cub/code/nn.py:1395-1457 — the distribution object on the part logits (model.py:413-421).  `sample` takes the
+    N(0,1) draw as an optional argument (a seeded torch.Generator otherwise): TF's RNG stream is not reproducible."""
+
+    def __init__(self, parameters, dim, stochastic=True):
+        self.parameters = parameters
+        self.dim = dim
+        self.stochastic = stochastic
+        ps = list(self.parameters.shape)
+        assert len(ps) == 4
+        self.batch_size = ps[0]
+        self.event_axes = [1, 2, 3]
+        self.mean = self.parameters
+        self.shape = ps
+        self._priors = None
+
+    @staticmethod
+    def n_parameters(dim):
+        return dim
+
+    def sample(self, noise_level=1.0, eps=None, generator=None):
+        if not self.stochastic:
+            return self.mean
+        if eps is None:
+            eps = torch.randn(self.shape, generator=generator, device=self.mean.device, dtype=torch.float32)
+        return ops.mean_field_sample(self.mean, eps, float(noise_level))
+
+    def sample_softmax(self, noise_level=1.0, eps=None, generator=None):
+        """softmax(sample()) in one pass (cub/code/SB_model48i/model.py:420-430): -> (logits, probs, labels, hard)
+        with hard = straight_through_estimator(hard_max(probs, 3), probs)."""
+        if not self.stochastic:
+            probs, labels, hard = ops.part_softmax_full(self.mean)
+            return self.mean, probs, labels, hard
+        if eps is None:
+            eps = torch.randn(self.shape, generator=generator, device=self.mean.device, dtype=torch.float32)
+        return ops.part_softmax_sampled(self.mean, eps, float(noise_level))
+
+    def _all(self):
+        if self._priors is None:
+            self._priors = ops.logit_priors(self.mean)      # one pass yields the three energies
+        return self._priors
+
+    def kl(self, other=None):
+        if other is not None:
+            raise NotImplementedError("Only KL to standard normal is implemented.")
+        return self._all()[0]
+
+    def kl_improper_gmrf(self):
+        return self._all()[1]
+
+    def kl_tv(self):
+        return self._all()[2]
+
+    def kl_mumford_sha(self, alpha, lambda_):
+        r, _, _ = mumford_shah(self.mean, alpha, lambda_)
+        return r.sum(dim=self.event_axes).mean()
+
+
+def mask2rgb(mask, make_hot=True, colors=None):
+    """cub/code/nn.py:2067-2083 — [b,h,w,k] -> [b,h,w,3] in [-1,1].  `colors` [k,3] in [0,1] replaces the reference's
+    make_mask_colors (matplotlib's inferno LUT, not available here): default = an evenly spaced grey ramp."""
+    n_parts = mask.shape[3]
+    if colors is None:
+        colors = torch.linspace(0, 1, n_parts, dtype=torch.float64)[:, None].repeat(1, 3)
+    table = ((torch.as_tensor(colors).to(torch.float64).cpu() - 0.5) * 2).to(torch.float32).to(mask.device)
+    return ops.mask2rgb(mask.detach(), table, bool(make_hot))

@@ -492,3 +492,172 @@ categorical_kl_grad = _op("categorical_kl_grad", _categorical_kl_grad, lambda p,
 categorical_kl = _op("categorical_kl", _categorical_kl, lambda p: p.new_empty(()),
                      lambda ctx, g: categorical_kl_grad(ctx.saved_tensors[0], g),
                      lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
+# ------------------------------------------------------------------ mask priors / sampling
+def _mumford_shah(x: Tensor, alpha: float, lambda_: float) -> Tuple[Tensor, Tensor, Tensor]:
+    x = _f32(x, "x")
+    B, H, W, K = x.shape
+    r, s, c = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, r.data_ptr(), s.data_ptr(), c.data_ptr(), None, None,
+           B, H, W, K, None, 0, _stream())
+    return r, s, c
+
+
+def _mumford_shah_grad(x: Tensor, alpha: float, lambda_: float, g_r: Optional[Tensor], g_s: Optional[Tensor],
+                       g_c: Optional[Tensor], g_sums: Optional[Tensor]) -> Tensor:
+    x = _f32(x, "x")
+    B, H, W, K = x.shape
+    gs = [None if g is None else _f32(g) for g in (g_r, g_s, g_c, g_sums)]
+    dx = torch.empty_like(x)
+    C.call("ups_mumford_shah_bwd", x.data_ptr(), alpha, lambda_, *[_ptr(g) for g in gs], dx.data_ptr(), B, H, W, K,
+           _stream())
+    return dx
+
+
+mumford_shah_grad = _op("mumford_shah_grad", _mumford_shah_grad, lambda x, a, l, gr, gs, gc, gq: torch.empty_like(x))
+
+
+def _ms_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.alpha, ctx.lam = inputs[1], inputs[2]
+
+
+mumford_shah = _op("mumford_shah", _mumford_shah,
+                   lambda x, a, l: (torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)),
+                   lambda ctx, g_r, g_s, g_c: (mumford_shah_grad(ctx.saved_tensors[0], ctx.alpha, ctx.lam, g_r, g_s, g_c,
+                                                                 None), None, None),
+                   _ms_setup)
+
+
+def _mumford_shah_sums(x: Tensor, alpha: float, lambda_: float) -> Tensor:
+    x = _f32(x, "x")
+    B, H, W, K = x.shape
+    sums = torch.empty(B, 4, K, dtype=torch.float32, device=x.device)
+    ws = _ws(C.workspace_bytes(C.OP_MUMFORD_SHAH, B, H * W, K, 0), x)
+    C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, None, None, None, None, sums.data_ptr(), B, H, W, K,
+           ws.data_ptr(), ws.numel(), _stream())
+    return sums
+
+
+mumford_shah_sums = _op("mumford_shah_sums", _mumford_shah_sums,
+                        lambda x, a, l: x.new_empty(x.shape[0], 4, x.shape[3]),
+                        lambda ctx, g: (mumford_shah_grad(ctx.saved_tensors[0], ctx.alpha, ctx.lam, None, None, None, g),
+                                        None, None),
+                        _ms_setup)
+
+
+def _edge_set(x: Tensor, alpha: float, lambda_: float) -> Tensor:
+    x = _f32(x, "x")
+    B, H, W, K = x.shape
+    e = torch.empty_like(x)
+    C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, None, None, None, e.data_ptr(), None, B, H, W, K,
+           None, 0, _stream())
+    return e
+
+
+edge_set = _op("edge_set", _edge_set, lambda x, a, l: torch.empty_like(x))
+
+
+def _logit_priors(mean: Tensor) -> Tensor:
+    mean = _f32(mean, "mean")
+    B, H, W, K = mean.shape
+    out = torch.empty(3, dtype=torch.float32, device=mean.device)
+    ws = _ws(C.workspace_bytes(C.OP_LOGIT_PRIORS, B, H * W, K, 0), mean)
+    C.call("ups_logit_priors_fwd", mean.data_ptr(), out.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def _logit_priors_grad(mean: Tensor, g: Tensor) -> Tensor:
+    mean, g = _f32(mean), _f32(g)
+    B, H, W, K = mean.shape
+    d = torch.empty_like(mean)
+    C.call("ups_logit_priors_bwd", mean.data_ptr(), g.data_ptr(), d.data_ptr(), B, H, W, K, _stream())
+    return d
+
+
+logit_priors_grad = _op("logit_priors_grad", _logit_priors_grad, lambda m, g: torch.empty_like(m))
+logit_priors = _op("logit_priors", _logit_priors, lambda m: m.new_empty(3),
+                   lambda ctx, g: logit_priors_grad(ctx.saved_tensors[0], g),
+                   lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
+def _mean_field_sample(mean: Tensor, eps: Tensor, noise_level: float) -> Tensor:
+    mean, eps = _f32(mean, "mean"), _f32(eps, "eps")
+    assert mean.shape == eps.shape, (list(mean.shape), list(eps.shape))
+    out = torch.empty_like(mean)
+    C.call("ups_mean_field_sample_fwd", mean.data_ptr(), eps.data_ptr(), noise_level, out.data_ptr(), mean.numel(),
+           _stream())
+    return out
+
+
+mean_field_sample = _op("mean_field_sample", _mean_field_sample, lambda m, e, n: torch.empty_like(m),
+                        lambda ctx, g: (g, None, None), lambda ctx, inputs, output: None)
+
+
+def _part_softmax_sampled(mean: Tensor, eps: Tensor, noise_level: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    mean, eps = _f32(mean, "mean"), _f32(eps, "eps")
+    assert mean.shape == eps.shape, (list(mean.shape), list(eps.shape))
+    K = mean.shape[-1]
+    logits, probs, hard = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+    labels = torch.empty(mean.shape[:-1], dtype=torch.int64, device=mean.device)
+    C.call("ups_part_softmax_sampled_fwd", mean.data_ptr(), eps.data_ptr(), noise_level, logits.data_ptr(),
+           probs.data_ptr(), labels.data_ptr(), hard.data_ptr(), mean.numel() // K, K, _stream())
+    return logits, probs, labels, hard
+
+
+def _pss_bwd(ctx, g_logits, g_probs, g_labels, g_hard):
+    (p,) = ctx.saved_tensors
+    g = g_probs if g_hard is None else (g_hard if g_probs is None else g_probs + g_hard)
+    d = None if g is None else part_softmax_grad(p, g)
+    if g_logits is not None:
+        d = g_logits if d is None else d + g_logits
+    return d, None, None
+
+
+part_softmax_sampled = _op(
+    "part_softmax_sampled", _part_softmax_sampled,
+    lambda m, e, n: (torch.empty_like(m), torch.empty_like(m), m.new_empty(m.shape[:-1], dtype=torch.int64),
+                     torch.empty_like(m)),
+    _pss_bwd, lambda ctx, inputs, output: ctx.save_for_backward(output[1]))
+
+
+def _weak_xent(logits: Tensor, mode: int) -> Tensor:
+    x = _f32(logits, "logits")
+    K = x.shape[-1]
+    n_pix = x.numel() // K
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    ws = _ws(C.workspace_bytes(C.OP_WEAK_XENT, 1, n_pix, K, 0), x)
+    C.call("ups_weak_xent_fwd", x.data_ptr(), mode, out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def _weak_xent_grad(logits: Tensor, mode: int, g: Tensor) -> Tensor:
+    x, g = _f32(logits), _f32(g)
+    K = x.shape[-1]
+    d = torch.empty_like(x)
+    C.call("ups_weak_xent_bwd", x.data_ptr(), mode, g.data_ptr(), d.data_ptr(), x.numel() // K, K, _stream())
+    return d
+
+
+def _wx_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.mode = inputs[1]
+
+
+weak_xent_grad = _op("weak_xent_grad", _weak_xent_grad, lambda x, m, g: torch.empty_like(x))
+weak_xent = _op("weak_xent", _weak_xent, lambda x, m: x.new_empty(()),
+                lambda ctx, g: (weak_xent_grad(ctx.saved_tensors[0], ctx.mode, g), None), _wx_setup)
+
+
+def _mask2rgb(mask: Tensor, table: Tensor, make_hot: bool) -> Tensor:
+    mask, table = _f32(mask, "mask"), _f32(table, "colors")
+    K = mask.shape[-1]
+    assert list(table.shape) == [K, 3], list(table.shape)
+    out = torch.empty(*mask.shape[:-1], 3, dtype=torch.float32, device=mask.device)
+    C.call("ups_mask2rgb_fwd", mask.data_ptr(), table.data_ptr(), int(make_hot), out.data_ptr(), mask.numel() // K, K,
+           _stream())
+    return out
+
+
+mask2rgb = _op("mask2rgb", _mask2rgb, lambda m, t, h: m.new_empty(*m.shape[:-1], 3))
