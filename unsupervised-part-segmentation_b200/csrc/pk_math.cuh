@@ -42,10 +42,34 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     return r;
 }
 
-// the three neutral operands, loaded once per kernel into registers
+// A constant-bank value lives in a UNIFORM register, and an FFMA2 takes at most one uniform-or-
+// immediate operand: fma(y, one, imm) or fma(T_uniform, r, nzero) then costs two MOVs to copy the
+// neutral operand into a vector register pair -- at every add of the Horner chains.  ptxas proves
+// uniformity through loads from uniform addresses too, so the three values are made formally
+// lane-dependent: OR-ed with (%laneid + %smid) >> 16, which is 0 everywhere but not to the compiler
+// (ptxas folds %laneid >> 5 by itself).
+__device__ __forceinline__ unsigned lane_zero() {
+    unsigned l, sm;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    return (l + sm) >> 16;
+}
+__device__ __forceinline__ f2 vector_resident(unsigned bits, unsigned z) {
+    f2 r;
+    const unsigned b = bits | z;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(b));
+    return r;
+}
+
+// the three neutral operands, built once per kernel in vector registers
 struct Ops {
     f2 one, nzero, none;
-    __device__ __forceinline__ Ops() : one(NEUTRAL.one), nzero(NEUTRAL.nzero), none(NEUTRAL.none) {}
+    __device__ __forceinline__ Ops() {
+        const unsigned z = lane_zero();
+        one = vector_resident(0x3f800000u, z);
+        nzero = vector_resident(0x80000000u, z);
+        none = vector_resident(0xbf800000u, z);
+    }
     __device__ __forceinline__ f2 mul(f2 a, f2 b) const { return fma2(a, b, nzero); }
     __device__ __forceinline__ f2 add(f2 a, f2 b) const { return fma2(a, one, b); }
     __device__ __forceinline__ f2 sub(f2 a, f2 b) const { return fma2(b, none, a); }
@@ -69,14 +93,13 @@ __device__ __forceinline__ void log_canon2n(const Ops& o, const f2 (&x)[NP], f2 
         float x0, x1;
         unpack(x[n], x0, x1);
         const int b0 = __float_as_int(x0), b1 = __float_as_int(x1);
-        // mantissa in [0.5, 1); if < sqrt(1/2): m <- 2m (exact) and e <- e - 1; then m - 1
-        const float m0 = __int_as_float((b0 & 0x007FFFFF) | 0x3F000000);
-        const float m1 = __int_as_float((b1 & 0x007FFFFF) | 0x3F000000);
-        const bool lt0 = m0 < 0.707106781186547524f, lt1 = m1 < 0.707106781186547524f;
-        const float t0 = __int_as_float(__float_as_int(m0) + (lt0 ? 0x00800000 : 0));
-        const float t1 = __int_as_float(__float_as_int(m1) + (lt1 ? 0x00800000 : 0));
-        const int e0 = ((b0 >> 23) & 0xFF) - 126 - (lt0 ? 1 : 0);
-        const int e1 = ((b1 >> 23) & 0xFF) - 126 - (lt1 ? 1 : 0);
+        // canonical split: mantissa m in [0.5, 1), e = E - 126; if m < sqrt(1/2): m <- 2m, e <- e - 1.
+        // For a positive normal x that is one subtraction and one shift: with S = bits(sqrt(1/2)f) =
+        // (126 << 23) + 0x3504F3, (b - S) >> 23 = E - 126 - (mantissa bits < 0x3504F3), and removing
+        // that exponent from b leaves bits(m) or bits(2m).  Same e and t as the compare-and-select form.
+        const int e0 = (b0 - 0x3F3504F3) >> 23, e1 = (b1 - 0x3F3504F3) >> 23;
+        const float t0 = __int_as_float(b0 - (e0 << 23));
+        const float t1 = __int_as_float(b1 - (e1 << 23));
         m[n] = o.sub(pack(t0, t1), o.one);
         ef[n] = o.sub(pack(small_int_as_magic(e0), small_int_as_magic(e1)), splat(MAGIC));  // exact
     }

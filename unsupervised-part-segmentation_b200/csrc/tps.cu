@@ -245,9 +245,12 @@ __global__ void __launch_bounds__(WARP_TPB, MINB) tps_warp_fwd_kernel(const floa
                                                                 float* __restrict__ mesh, int N2, int H, int W,
                                                                 int Crt, int oh, int ow) {
     __shared__ float sm_const[42];
-    extern __shared__ float sm_out[];  // 2 * WARP_TPB * C floats
+    extern __shared__ __align__(16) float sm_out[];  // 2 * WARP_TPB * C floats
     const int Cc = (C > 0) ? C : Crt;
     const int b = blockIdx.y;
+    // float4 tile stores: C == 3 (a tile is 96 float4, tiles start at multiples of 128 pixels = 1536 B)
+    const bool vec_store = (C == 3) && ((oh * ow) % 4 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out2)) & 15u) == 0;
     const pk::Ops o;
     SampleConstPk k;
     load_sample_const_pk(k, sm_const, coord, T, move, scal, b);
@@ -322,10 +325,18 @@ __global__ void __launch_bounds__(WARP_TPB, MINB) tps_warp_fwd_kernel(const floa
         // coalesced write of the tile: WARP_TPB*C contiguous floats
         const int n_live = min(WARP_TPB, OP - base) * Cc;
         float* ob_ = out + ((size_t)b * OP + base) * Cc;
-        for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob_ + e, sm_out[e]);
-        if (second) {
-            float* ob2 = out2 + ((size_t)b * OP + base) * Cc;
-            for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob2 + e, sm_out2[e]);
+        float* ob2 = second ? out2 + ((size_t)b * OP + base) * Cc : nullptr;
+        if (vec_store && n_live == WARP_TPB * Cc) {
+            // full tile of 16-byte aligned rows: one LDS.128 + STG.128 per thread and image
+            constexpr int NV = (C > 0) ? WARP_TPB * C / 4 : 0;
+            if ((int)threadIdx.x < NV) {
+                st4_stream(ob_ + 4 * threadIdx.x, reinterpret_cast<const float4*>(sm_out)[threadIdx.x]);
+                if (second) st4_stream(ob2 + 4 * threadIdx.x, reinterpret_cast<const float4*>(sm_out2)[threadIdx.x]);
+            }
+        } else {
+            for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob_ + e, sm_out[e]);
+            if (second)
+                for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob2 + e, sm_out2[e]);
         }
         __syncthreads();
     }
