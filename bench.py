@@ -304,6 +304,10 @@ def run_gpu(args):
                                                               g_inj=g_inj, g_parts=g_parts, g_pooled=g_pooled, g_m0=g_m0,
                                                               g_m1=g_m1, g_warped=g_warped), B)
         line["e2e"] = e2e
+        # same step with the views crossing PCIe as the dataset's uint8 pixels (reported beside, not instead of, e2e)
+        targs = dict(views=views, coord=coord_h, tv=tv_h, l0=l0, l1=l1, feat=feat, g_inj=g_inj, g_parts=g_parts,
+                     g_pooled=g_pooled, g_m0=g_m0, g_m1=g_m1, g_warped=g_warped)
+        line["e2e_uint8_views"] = run_e2e(args, torch, dist, dp, dev, world, targs, B, u8=True)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -316,27 +320,40 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, dist, dp, dev, world, t, B):
+def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
     """Host-resident per-step inputs (what the reference feeds through feed_dict each step: the
     image views, cub/code/SB_model48i/model.py:316-327, plus the TPS parameters drawn on the host)
     are copied host->device every step from pinned memory; the step's host-visible results (the
     int64 part labels that evaluation consumes, the pooled part appearances and dfeat) are read
     back every step.  Logits, part features and cotangents are produced ON the device by the
     CNNs that surround the path in the real model, so they stay device-resident here too.
-    Copies run on a side stream, double-buffered, so that they overlap the previous step."""
-    views_h = t["views"].cpu().pin_memory()
+    Copies run on a side stream, double-buffered, so that they overlap the previous step.
+
+    u8=True: the views cross PCIe as the dataset's uint8 pixels and the data pipeline's
+    `astype(float32) * 2 / 255 - 1` (cub/code/data/data.py:134) runs on the device inside
+    PartStep.forward (ups_views_u8_to_f32) -- same step, a quarter of the H2D bytes."""
+    if u8:
+        g = torch.Generator().manual_seed(args.seed)
+        views_h = torch.randint(0, 256, tuple(t["views"].shape), dtype=torch.uint8, generator=g).pin_memory()
+    else:
+        views_h = t["views"].cpu().pin_memory()
     coord_h, tv_h = t["coord"].pin_memory(), t["tv"].pin_memory()
     step = dp.step
     lab_h = torch.empty(step.labels0.shape, dtype=torch.int64).pin_memory()
     pooled_h = torch.empty(step.pooled.shape).pin_memory()
     dfeat_h = torch.empty(step.dfeat.shape).pin_memory()
-    bufs = [dict(views=torch.empty_like(t["views"]), coord=torch.empty(coord_h.shape, device=dev),
+    lab_d, pooled_d, dfeat_d = (torch.empty_like(x) for x in (step.labels0, step.pooled, step.dfeat))
+    bufs = [dict(views=torch.empty(views_h.shape, dtype=views_h.dtype, device=dev),
+                 coord=torch.empty(coord_h.shape, device=dev),
                  tv=torch.empty(tv_h.shape, device=dev)) for _ in range(2)]
     copy_s = torch.cuda.Stream(device=dev)
+    out_s = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
-    h2d = views_h.numel() * 4 + coord_h.numel() * 4 + tv_h.numel() * 4
+    done = torch.cuda.Event()
+    drained = torch.cuda.Event()
+    h2d = views_h.numel() * views_h.element_size() + coord_h.numel() * 4 + tv_h.numel() * 4
     d2h = lab_h.numel() * 8 + pooled_h.numel() * 4 + dfeat_h.numel() * 4
 
     def stage(i):
@@ -351,6 +368,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B):
     def run(n):
         for ev in freed:
             ev.record(main_s)
+        drained.record(main_s)
         stage(0)
         for i in range(n):
             if i + 1 < n:
@@ -360,9 +378,20 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B):
             dp.forward(b["views"], b["coord"], b["tv"], t["l0"], t["l1"], t["feat"])
             dp.backward(t["g_inj"], t["g_parts"], t["g_pooled"], t["g_m0"], t["g_m1"], t["g_warped"])
             freed[i % 2].record(main_s)
-            lab_h.copy_(step.labels0, non_blocking=True)
-            pooled_h.copy_(step.pooled, non_blocking=True)
-            dfeat_h.copy_(step.dfeat, non_blocking=True)
+            # results -> a device staging copy (35 MB device-to-device, ~12 us), read back from there on
+            # its own stream: the D2H of step i overlaps the kernels of step i+1
+            main_s.wait_event(drained)          # the previous read-back has left the staging buffers
+            lab_d.copy_(step.labels0, non_blocking=True)
+            pooled_d.copy_(step.pooled, non_blocking=True)
+            dfeat_d.copy_(step.dfeat, non_blocking=True)
+            done.record(main_s)
+            with torch.cuda.stream(out_s):
+                out_s.wait_event(done)
+                lab_h.copy_(lab_d, non_blocking=True)
+                pooled_h.copy_(pooled_d, non_blocking=True)
+                dfeat_h.copy_(dfeat_d, non_blocking=True)
+                drained.record(out_s)
+        main_s.wait_event(drained)
 
     def barrier():
         if world > 1:
@@ -385,8 +414,10 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B):
     assert int(lab_h.max()) < dp.step.K
     return {"value": world * B * n / (ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": n, "ms_per_step": ms / n,
-            "boundary": "host: views + TPS params in, int64 labels + pooled + dfeat out; "
-                        "logits/features/cotangents device-resident (CNN outputs in the real model)"}
+            "boundary": ("host: %s views + TPS params in, int64 labels + pooled + dfeat out; "
+                         "logits/features/cotangents device-resident (CNN outputs in the real model)")
+                        % ("uint8 (normalised on the device as cub/code/data/data.py:134 does on the host)" if u8
+                           else "fp32")}
 
 
 def main():

@@ -52,6 +52,14 @@ enum ups_op {
 };
 size_t ups_workspace_bytes(int op, int B, int P, int K, int F);
 
+/* ---- image ingest ------------------------------------------------------------------- */
+/* The normalisation the reference's data pipeline applies on the host right before the views are fed
+ * (cub/code/data/data.py:134,152; pennaction/code/data/data.py:134,152):
+ *     o.astype(np.float32) * 2.0 / 255.0 - 1.0
+ * src: n uint8 values (any NHWC image batch), dst: n fp32 values; both 16-byte aligned device pointers.
+ * Bit-identical to the numpy expression (fp32 multiply, correctly rounded divide, subtract). */
+int ups_views_u8_to_f32(const unsigned char* src, float* dst, long long n, void* stream);
+
 /* ---- thin-plate-spline warp -------------------------------------------------------- */
 /* make_input_tps_param(tps_param) — baselines/unsupervised-disentangling/transformations.py:59-77
  * coord,vector [N,8,2]; offset,offset_2 [N,1,2]; t_scal [N,2]; rot_mat [N,2,2] -> t_vector [N,8,2]

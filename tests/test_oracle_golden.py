@@ -212,3 +212,16 @@ def test_mask_priors(golden):
         colors = t(g[f"{tag}_colors"])
         close(R.mask2rgb(p.detach(), colors, True), g[f"{tag}_rgb_hot"], 0, 0)
         close(R.mask2rgb(p.detach(), colors, False), g[f"{tag}_rgb_soft"], 1e-5, 1e-7)
+
+
+def test_image_ingest_normalisation():
+    """oracle.ingest vs the reference's own expression (cub/code/data/data.py:134), all 256 bytes."""
+    import os
+    from oracle import ingest
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ingest.npz"))
+    assert str(d["expression"]) == "o.astype(np.float32) * 2.0 / 255.0 - 1.0"
+    for src, want in ((d["all_bytes"], d["out_bytes"]), (d["img"], d["out_img"])):
+        got = ingest.images_from_uint8(src).numpy()
+        assert got.dtype == np.float32 and got.shape == want.shape
+        assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    assert d["out_bytes"][0] == -1.0 and d["out_bytes"][255] == 1.0

@@ -321,24 +321,27 @@ __global__ void __launch_bounds__(WARP_TPB, MINB) tps_warp_fwd_kernel(const floa
                 }
             }
         }
-        __syncthreads();
         // coalesced write of the tile: WARP_TPB*C contiguous floats
         const int n_live = min(WARP_TPB, OP - base) * Cc;
         float* ob_ = out + ((size_t)b * OP + base) * Cc;
         float* ob2 = second ? out2 + ((size_t)b * OP + base) * Cc : nullptr;
         if (vec_store && n_live == WARP_TPB * Cc) {
-            // full tile of 16-byte aligned rows: one LDS.128 + STG.128 per thread and image
-            constexpr int NV = (C > 0) ? WARP_TPB * C / 4 : 0;
-            if ((int)threadIdx.x < NV) {
-                st4_stream(ob_ + 4 * threadIdx.x, reinterpret_cast<const float4*>(sm_out)[threadIdx.x]);
-                if (second) st4_stream(ob2 + 4 * threadIdx.x, reinterpret_cast<const float4*>(sm_out2)[threadIdx.x]);
+            // full tile of 16-byte aligned rows.  Each warp staged its own 32 pixels (96 floats = 24 float4,
+            // 384 contiguous bytes of the output): a warp-level sync is enough, no CTA barrier.
+            __syncwarp();
+            const int lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) * 24;   // float4 index of the warp's slice
+            if (lane < 24) {
+                st4_stream(ob_ + 4 * (w4 + lane), reinterpret_cast<const float4*>(sm_out)[w4 + lane]);
+                if (second) st4_stream(ob2 + 4 * (w4 + lane), reinterpret_cast<const float4*>(sm_out2)[w4 + lane]);
             }
+            __syncwarp();
         } else {
+            __syncthreads();
             for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob_ + e, sm_out[e]);
             if (second)
                 for (int e = threadIdx.x; e < n_live; e += WARP_TPB) __stcs(ob2 + e, sm_out2[e]);
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

@@ -76,6 +76,14 @@ def inject_features(feature_vectors, mask):
     return ops.part_inject(feature_vectors, mask)
 
 
+def images_from_uint8(images):
+    """The host-side normalisation of the reference's data pipeline, moved onto the device:
+    `o.astype(np.float32) * 2.0 / 255.0 - 1.0` (cub/code/data/data.py:134,152;
+    pennaction/code/data/data.py:134,152).  uint8 CUDA tensor of any shape -> fp32, bit-identical
+    to the numpy expression.  Lets a step's views cross PCIe as bytes."""
+    return ops.views_u8_to_f32(images)
+
+
 def make_tps(views, tps_parameters, generator=None):
     """TrainModel.make_tps — cub/code/SB_model48i/model.py:282-311 (3 views; the target view
     re-uses the first-half parameters) / pennaction/code/SB_model48i/model.py:281-303 (2 views)."""

@@ -40,6 +40,22 @@ def _op(name, schema_fn, fake_fn, backward=None, setup=None):
     return op
 
 
+# ------------------------------------------------------------------ image ingest
+def _views_u8_to_f32(images: Tensor) -> Tensor:
+    if not images.is_cuda:
+        raise C.UpsError("ups_b200: images must be a CUDA tensor (no CPU fallback exists)")
+    if images.dtype != torch.uint8:
+        raise C.UpsError(f"ups_b200: images must be uint8, got {images.dtype}")
+    images = images.contiguous()
+    out = torch.empty(images.shape, dtype=torch.float32, device=images.device)
+    C.call("ups_views_u8_to_f32", images.data_ptr(), out.data_ptr(), images.numel(), _stream())
+    return out
+
+
+views_u8_to_f32 = _op("views_u8_to_f32", _views_u8_to_f32,
+                      lambda images: torch.empty(images.shape, dtype=torch.float32, device=images.device))
+
+
 # ------------------------------------------------------------------ TPS
 def _tps_input_param(coord: Tensor, vector: Tensor, offset: Tensor, offset_2: Tensor, t_scal: Tensor,
                      rot_mat: Tensor) -> Tensor:

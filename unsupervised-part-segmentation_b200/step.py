@@ -67,6 +67,7 @@ class PartStep:
             self.dm = e(B, S, S, K, **f32)
             self.dm2 = e(B, S, S, K, **f32)
             self.dfm = e(B, S, S, 3, **f32)
+        self._views_f32 = None   # allocated on first use: fp32 copy of uint8 views (data.py:134 on the device)
         self._img1 = None
         self._feat = None
         self._coord = None
@@ -79,11 +80,18 @@ class PartStep:
 
     # ------------------------------------------------------------------ forward
     def forward(self, views, coord, t_vector, l0, l1, feat):
-        """views [V,B,S,S,3] (view0, view1[, view0_target]); coord, t_vector [2B,8,2] from
-        make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict of views into
-        the step's persistent output buffers."""
+        """views [V,B,S,S,3] (view0, view1[, view0_target]), fp32 in [-1, 1] or the dataset's uint8
+        (normalised on the device exactly as cub/code/data/data.py:134 does on the host); coord,
+        t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
+        of views into the step's persistent output buffers."""
         B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
         st = _cur_stream()
+        if views.dtype == torch.uint8:
+            assert views.is_contiguous() and tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
+            if self._views_f32 is None:
+                self._views_f32 = torch.empty(V, B, S, S, 3, dtype=torch.float32, device=self.device)
+            C.call("ups_views_u8_to_f32", views.data_ptr(), self._views_f32.data_ptr(), views.numel(), st)
+            views = self._views_f32
         assert views.is_contiguous() and l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
         assert tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
