@@ -10,4 +10,4 @@ this package against them.  TF's kernel-level rounding (Eigen exp/log, cuBLAS ma
 fp32 matrix_inverse) is emulated by torch CPU ops in those fixtures, so the pin is on the
 algorithm, not on TF's last ulp.
 """
-from . import canon, parts, tps, step, stats, priors, ingest  # noqa: F401
+from . import canon, parts, tps, step, stats, priors, ingest, inject_conv  # noqa: F401

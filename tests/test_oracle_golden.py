@@ -225,3 +225,27 @@ def test_image_ingest_normalisation():
         assert got.dtype == np.float32 and got.shape == want.shape
         assert np.array_equal(got.view(np.int32), want.view(np.int32))
     assert d["out_bytes"][0] == -1.0 and d["out_bytes"][255] == 1.0
+
+
+def test_inject_conv_first_layer(golden):
+    """oracle.inject_conv vs the reference's unpool_features + reduce_sum + concat (model.py:225-249,482-484)
+    followed by its own _conv2d (nn.py:617-664), values and all four gradients; also the per-sample filter
+    table the CUDA path uses is the same sum re-associated."""
+    from oracle import inject_conv as IC
+    g = golden("inject_conv.npz")
+    for tag in ("a", "b", "c"):
+        mask, feat, V, b = (t(g[f"{tag}_{n}"]).requires_grad_(True) for n in ("mask", "feat", "V", "b"))
+        y = IC.inject_conv2d(feat, mask, V, b)
+        close(y, g[f"{tag}_out"], 1e-5, 1e-6)
+        grads = torch.autograd.grad(y, [mask, feat, V, b], t(g[f"{tag}_g_out"]))
+        for got, name in zip(grads, ("dmask", "dfeat", "dV", "db")):
+            close(got, g[f"{tag}_{name}"], 1e-4, 1e-5)
+        # the table form: out[p] = b + sum_tap sum_k mask[p+tap,k] * G[tap,k,:]
+        G = IC.inject_conv_table(feat, V)                                    # [B,9,K,Co]
+        B, H, W, K = mask.shape
+        mp = torch.nn.functional.pad(mask, (0, 0, 1, 1, 1, 1))
+        y2 = b.reshape(1, 1, 1, -1).expand(B, H, W, -1).clone()
+        for i in range(3):
+            for j in range(3):
+                y2 = y2 + torch.einsum("bhwk,bko->bhwo", mp[:, i:i + H, j:j + W], G[:, 3 * i + j])
+        close(y2, g[f"{tag}_out"], 1e-4, 1e-5)
