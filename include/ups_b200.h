@@ -234,6 +234,41 @@ int ups_weak_xent_bwd(const float* logits, int mode, const float* g_out, float* 
  * out [n_pix,3]; make_hot: colour of the first maximum, else sum_k mask_k*table_k. */
 int ups_mask2rgb_fwd(const float* mask, const float* table, int make_hot, float* out, long long n_pix, int K, void* stream);
 
+/* ---- the decoder's first convolution on the part assignment ----------------------
+ * Replaces   injected = tf.concat([tf.reduce_sum(unpool_features(feat, mask), 3), mask], 3)   cub/code/SB_model48i/model.py:482-484
+ *            h = nn.conv2d(injected, config[0])  (3x3, stride 1, SAME, + bias)               model.py:96 (`dd`, :485), cub/code/nn.py:617-664
+ * without materialising `injected` [B,h,w,F+K]:  h = b + conv3x3(mask, G[b])  with the per-sample filter table
+ *   G[b,t,k,o] = sum_f feat[b,k,f] V[t,f,o] + V[t,F+k,o],   t = 3*i + j,  V = TensorFlow HWIO [3,3,F+K,Co].
+ * K <= 32, Co a multiple of 4 in [4,128]. */
+/* feat [B,K,F], V [9,F+K,Co] -> G [B,9,K,Co] */
+int ups_inject_conv_table_fwd(const float* feat, const float* V, float* G, int B, int K, int F, int Co, void* stream);
+/* dG [B,9,K,Co] -> dfeat [B,K,F] (may be NULL), dV [9,F+K,Co] (may be NULL; summed over the batch) */
+int ups_inject_conv_table_bwd(const float* dG, const float* feat, const float* V, float* dfeat, float* dV, int B, int K,
+                              int F, int Co, void* stream);
+/* mask [B,H,W,K] (any values; the straight-through hard mask of model.py:473 takes the one-non-zero fast path),
+ * G [B,9,K,Co], bias [Co] -> out [B,H,W,Co] */
+int ups_inject_conv_fwd(const float* mask, const float* G, const float* bias, float* out, int B, int H, int W, int K,
+                        int Co, void* stream);
+/* g_out [B,H,W,Co] -> dmask [B,H,W,K], dG [B,9,K,Co], db [Co] (may be NULL).
+ * probs != NULL: the mask is ST(hard_max(probs)) of probs = softmax(logits) (nn.py:117-168); dmask (+ g_extra, the
+ * cotangent reaching the probabilities from elsewhere, may be NULL) is passed through the straight-through estimator
+ * and the softmax backward, and `dmask` receives dlogits instead.
+ * ws from ups_inject_conv_workspace_bytes (per-split partial sums, reduced in a fixed order: deterministic). */
+int ups_inject_conv_bwd(const float* g_out, const float* mask, const float* G, const float* probs, const float* g_extra,
+                        float* dmask, float* dG, float* db, int B, int H, int W, int K, int Co, void* ws, size_t ws_bytes,
+                        void* stream);
+size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co);
+
+/* ---- the appearance encoder's first convolution on the masked part images (encoder side) ----
+ * Replaces   view1_parts = mask_parts(view1, encoding_mask)                      cub/code/SB_model48i/model.py:176-187, :478
+ *            nn.apply_partwise(view1_parts, e_alpha) -> fold to [K*B,h,w,3]       cub/code/nn.py:81-113
+ *            e_alpha's first layer nn.conv2d(x, config[0]) (3x3, SAME, + bias)    model.py:40, cub/code/nn.py:617-664
+ * without materialising the part images: img [B,H,W,3], mask [B,H,W,K], V [9,3,Co] (HWIO flattened), bias [Co]
+ * -> out_pm [K*B,H,W,Co] part-major (row k*B+b, the batch layout apply_partwise hands the encoder).
+ * Forward only: the encoder's own backward produces g_parts, which ups_step_encode_bwd consumes. */
+int ups_parts_conv_fwd(const float* img, const float* mask, const float* V, const float* bias, float* out_pm, int B,
+                       int H, int W, int K, int C, int Co, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

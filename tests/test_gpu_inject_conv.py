@@ -1,0 +1,178 @@
+"""-m gpu: SURVEY.md 8f N4 — the decoder's first convolution on the part assignment
+(cub/code/SB_model48i/model.py:482-485 + cub/code/nn.py:617-664) against the oracle and the committed
+reference fixture, forward and all gradients, through the reference-named helper."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inject_conv as IC
+from oracle import parts as OP
+from util import assert_bitexact, assert_close, reduce_atol
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inject_conv.npz")
+
+
+@pytest.fixture(scope="module")
+def ups():
+    import ups_b200
+    return ups_b200
+
+
+def _case(B, H, W, K, F, Co, kind, seed):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, H, W, K, generator=g)
+    if kind == "ties":          # exact ties (several ones per pixel) and empty pixels among the hard ones
+        logits[:, 0] = torch.round(logits[:, 0])
+    p = OP.softmax(logits)
+    mask = p if kind == "soft" else OP.hard_max_straight_through(p, 3)
+    if kind == "ties":
+        mask = mask.clone()
+        mask[:, -1, ::2] = 0.0
+    feat = torch.randn(B, K, F, generator=g)
+    stdv = math.sqrt(1.0 / ((F + K) * 9))
+    V = (torch.rand(3, 3, F + K, Co, generator=g) * 2 - 1) * stdv
+    b = (torch.rand(Co, generator=g) * 2 - 1) * stdv
+    gy = torch.randn(B, H, W, Co, generator=g)
+    return logits, mask.detach(), feat, V, b, gy
+
+
+def _check_grads(got, want, H, W, B):
+    names = ("dmask", "dfeat", "dV", "db")
+    n_terms = (9, H * W * 9, B * H * W, B * H * W)
+    for a, o, name, n in zip(got, want, names, n_terms):
+        assert_close(a, o, name, atol=reduce_atol(n))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_reference_fixture(ups, tag):
+    """Values and gradients produced by the reference's own unpool_features / _conv2d bodies (tests/golden/
+    make_golden_inject_conv.py): hard mask with a tie and an empty pixel (a), the CUB sizes K=16 F=64 Co=32 (b),
+    a soft mask with K=5 (c)."""
+    g = np.load(GOLDEN)
+    mask, feat, V, b = (torch.from_numpy(g[f"{tag}_{n}"]).cuda().requires_grad_(True) for n in ("mask", "feat", "V", "b"))
+    y = ups.model.inject_conv2d(feat, mask, V, b)
+    assert_close(y, torch.from_numpy(g[f"{tag}_out"]), "out")
+    grads = torch.autograd.grad(y, [mask, feat, V, b], torch.from_numpy(g[f"{tag}_g_out"]).cuda())
+    B, H, W, _ = mask.shape
+    _check_grads(grads, [torch.from_numpy(g[f"{tag}_{n}"]) for n in ("dmask", "dfeat", "dV", "db")], H, W, B)
+
+
+SHAPES = [(2, 64, 64, 16, 64, 32, "hard"), (1, 128, 128, 16, 64, 32, "hard"), (3, 40, 50, 25, 16, 32, "ties"),
+          (2, 33, 31, 8, 8, 64, "hard"), (1, 16, 48, 32, 64, 128, "ties"), (2, 20, 70, 4, 4, 4, "soft"),
+          (1, 1, 1, 16, 64, 32, "hard"), (1, 3, 37, 5, 6, 8, "soft"), (5, 17, 16, 12, 32, 16, "ties"),
+          (2, 64, 64, 16, 64, 32, "soft")]
+
+
+@pytest.mark.parametrize("B,H,W,K,F,Co,kind", SHAPES)
+def test_inject_conv2d_vs_oracle(ups, B, H, W, K, F, Co, kind):
+    _, mask, feat, V, b, gy = _case(B, H, W, K, F, Co, kind, seed=B * 100 + K + Co)
+    lo = [t.clone().requires_grad_(True) for t in (mask, feat, V, b)]
+    y_o = IC.inject_conv2d(lo[1], lo[0], lo[2], lo[3])
+    g_o = torch.autograd.grad(y_o, lo, gy)
+    lc = [t.cuda().requires_grad_(True) for t in (mask, feat, V, b)]
+    y = ups.model.inject_conv2d(lc[1], lc[0], lc[2], lc[3])
+    assert y.shape == (B, H, W, Co)
+    assert_close(y, y_o.detach(), "out")
+    # equals the un-fused path of this library too: conv over the materialised injected map
+    inj = ups.model.inject_features(lc[1].detach(), lc[0].detach())
+    assert_close(IC.conv2d_same(inj.cpu(), V, b), y_o.detach(), "conv(inject_features)")
+    got = torch.autograd.grad(y, lc, gy.cuda())
+    _check_grads(got, g_o, H, W, B)
+
+
+def test_table(ups):
+    B, K, F, Co = 3, 16, 64, 32
+    g = torch.Generator().manual_seed(5)
+    feat, V = torch.randn(B, K, F, generator=g), torch.randn(3, 3, F + K, Co, generator=g)
+    G = ups.ops.inject_conv_table(feat.cuda(), V.reshape(9, F + K, Co).cuda())
+    assert_close(G, IC.inject_conv_table(feat, V), "G", atol=reduce_atol(F) * 8)
+
+
+@pytest.mark.parametrize("B,H,W,K,F,Co", [(2, 64, 64, 16, 64, 32), (1, 48, 40, 8, 16, 32), (2, 32, 32, 25, 8, 16)])
+def test_decode_conv2d_vs_oracle(ups, B, H, W, K, F, Co):
+    """softmax -> argmax -> ST(hard_max) -> inject -> conv, and its backward with cotangents on both the conv output
+    and the probabilities (model.py:426,434-436,447,470-473,482-485)."""
+    logits, _, feat, V, b, gy = _case(B, H, W, K, F, Co, "ties", seed=K + Co)
+    g = torch.Generator().manual_seed(3)
+    gm = torch.randn(B, H, W, K, generator=g)
+    lo = [t.clone().requires_grad_(True) for t in (logits, feat, V, b)]
+    m0_o = OP.softmax(lo[0])
+    mh_o = OP.hard_max_straight_through(m0_o, 3)
+    y_o = IC.inject_conv2d(lo[1], mh_o, lo[2], lo[3])
+    g_o = torch.autograd.grad([y_o, m0_o], lo, [gy, gm])
+    lc = [t.cuda().requires_grad_(True) for t in (logits, feat, V, b)]
+    m0, labels, mh, y = ups.model.decode_conv2d(*lc)
+    assert_bitexact(m0, m0_o.detach(), "m0")
+    assert_bitexact(mh, mh_o.detach(), "mask")
+    assert torch.equal(labels.cpu(), OP.argmax_labels(m0_o.detach()))
+    assert_close(y, y_o.detach(), "out")
+    got = torch.autograd.grad([y, m0], lc, [gy.cuda(), gm.cuda()])
+    for a, o, name, n in zip(got, g_o, ("dlogits", "dfeat", "dV", "db"), (9 * Co, H * W * 9, B * H * W, B * H * W)):
+        assert_close(a, o, name, atol=reduce_atol(n))
+
+
+def test_run_to_run_determinism(ups):
+    _, mask, feat, V, b, gy = _case(4, 64, 64, 16, 64, 32, "ties", seed=11)
+    outs = []
+    for _ in range(2):
+        lc = [t.cuda().requires_grad_(True) for t in (mask, feat, V, b)]
+        y = ups.model.inject_conv2d(lc[1], lc[0], lc[2], lc[3])
+        outs.append([y] + list(torch.autograd.grad(y, lc, gy.cuda())))
+    for a, c in zip(*outs):
+        assert_bitexact(a, c.cpu(), "run-to-run")
+
+
+def test_full_size_linearity(ups):
+    """CUB B=64 slice of BASELINE configs[1] (the oracle would take minutes): out(feat_a + feat_b) - bias terms is
+    additive in the features, and the hard-mask conv equals a gather of table rows."""
+    B, H, W, K, F, Co = 64, 128, 128, 16, 64, 32
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logits = torch.randn(B, H, W, K, device="cuda", generator=g)
+    mh = ups.nn.hard_max_straight_through(ups.nn.softmax(logits), 3)
+    fa, fb = torch.randn(B, K, F, device="cuda", generator=g), torch.randn(B, K, F, device="cuda", generator=g)
+    V = torch.randn(3, 3, F + K, Co, device="cuda", generator=g) * 0.05
+    b = torch.randn(Co, device="cuda", generator=g)
+    zero_b = torch.zeros_like(b)
+    ya = ups.model.inject_conv2d(fa, mh, V, b)
+    yb = ups.model.inject_conv2d(fb, mh, V, zero_b)
+    Vm = V.clone()
+    Vm[:, :, F:] = 0                                    # drop the mask channels so that they are not counted twice
+    y0 = ups.model.inject_conv2d(fb * 0, mh, V - Vm, zero_b)
+    yab = ups.model.inject_conv2d(fa + fb, mh, V, b)
+    assert_close(yab, (ya + yb - y0).cpu(), "additivity in feat", rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------- encoder side: conv on the masked part images
+PC_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "parts_conv.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_parts_conv_reference_fixture(ups, tag):
+    g = np.load(PC_GOLDEN)
+    mask, image, V, b = (torch.from_numpy(g[f"{tag}_{n}"]).cuda() for n in ("mask", "image", "V", "b"))
+    y = ups.model.parts_conv2d(image, mask, V, b)
+    assert_close(y, torch.from_numpy(g[f"{tag}_out"]), "out")
+
+
+@pytest.mark.parametrize("B,H,W,K,Co,kind", [(2, 64, 64, 16, 32, "hard"), (1, 128, 128, 16, 32, "ties"),
+                                             (3, 40, 50, 25, 32, "ties"), (2, 33, 31, 8, 64, "soft"),
+                                             (1, 16, 48, 32, 128, "hard"), (2, 9, 70, 4, 5, "soft"),
+                                             (1, 1, 1, 16, 32, "hard")])
+def test_parts_conv2d_vs_oracle(ups, B, H, W, K, Co, kind):
+    from oracle import parts_conv as PC
+    _, mask, _, _, _, _ = _case(B, H, W, K, 4, Co, kind, seed=B * 10 + K)
+    g = torch.Generator().manual_seed(Co)
+    image = torch.rand(B, H, W, 3, generator=g) * 2 - 1
+    V = (torch.rand(3, 3, 3, Co, generator=g) * 2 - 1) * math.sqrt(1.0 / 27)
+    b = (torch.rand(Co, generator=g) * 2 - 1) * math.sqrt(1.0 / 27)
+    y_o = PC.parts_conv2d(image, mask, V, b)
+    y = ups.model.parts_conv2d(image.cuda(), mask.cuda(), V.cuda(), b.cuda())
+    assert y.shape == (K * B, H, W, Co)
+    assert_close(y, y_o, "out")
+    # equals this library's own un-fused path: conv over the materialised part-major part images
+    parts_pm = ups.model.mask_parts_partmajor(image.cuda(), mask.cuda())
+    assert_close(IC.conv2d_same(parts_pm.cpu(), V, b), y_o, "conv(mask_parts_partmajor)")

@@ -249,3 +249,17 @@ def test_inject_conv_first_layer(golden):
             for j in range(3):
                 y2 = y2 + torch.einsum("bhwk,bko->bhwo", mp[:, i:i + H, j:j + W], G[:, 3 * i + j])
         close(y2, g[f"{tag}_out"], 1e-4, 1e-5)
+
+
+def test_parts_conv_first_layer(golden):
+    """oracle.parts_conv vs the reference's mask_parts (model.py:176-187) + apply_partwise (nn.py:81-113) + _conv2d
+    (nn.py:617-664) executed under the shim: value in the part-major layout and all four gradients."""
+    from oracle import parts_conv as PC
+    g = golden("parts_conv.npz")
+    for tag in ("a", "b", "c"):
+        mask, image, V, b = (t(g[f"{tag}_{n}"]).requires_grad_(True) for n in ("mask", "image", "V", "b"))
+        y = PC.parts_conv2d(image, mask, V, b)
+        close(y, g[f"{tag}_out"], 1e-5, 1e-6)
+        grads = torch.autograd.grad(y, [mask, image, V, b], t(g[f"{tag}_g_out"]))
+        for got, name in zip(grads, ("dmask", "dimage", "dV", "db")):
+            close(got, g[f"{tag}_{name}"], 1e-4, 1e-5)

@@ -56,6 +56,11 @@ _SIGS = {
     "ups_weak_xent_fwd": [c_f, c_i, c_f, c_ll, c_i, c_f, c_sz, c_f],
     "ups_weak_xent_bwd": [c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
     "ups_mask2rgb_fwd": [c_f, c_f, c_i, c_f, c_ll, c_i, c_f],
+    "ups_inject_conv_table_fwd": [c_f, c_f, c_f] + [c_i] * 4 + [c_f],
+    "ups_inject_conv_table_bwd": [c_f] * 5 + [c_i] * 4 + [c_f],
+    "ups_inject_conv_fwd": [c_f] * 4 + [c_i] * 5 + [c_f],
+    "ups_parts_conv_fwd": [c_f] * 5 + [c_i] * 6 + [c_f],
+    "ups_inject_conv_bwd": [c_f] * 8 + [c_i] * 5 + [c_f, c_sz, c_f],
 }
 
 OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP, OP_MOMENTS, OP_KL = 0, 1, 2, 3, 4, 5, 6
@@ -83,6 +88,8 @@ def _load():
     lib.ups_launch_count_reset.restype = None
     lib.ups_workspace_bytes.argtypes = [c_i] * 5
     lib.ups_workspace_bytes.restype = c_sz
+    lib.ups_inject_conv_workspace_bytes.argtypes = [c_i] * 5
+    lib.ups_inject_conv_workspace_bytes.restype = c_sz
     return lib, path
 
 
@@ -105,6 +112,10 @@ def launch_count():
 
 def launch_count_reset():
     lib.ups_launch_count_reset()
+
+
+def inject_conv_workspace_bytes(B, H, W, K, Co):
+    return int(lib.ups_inject_conv_workspace_bytes(B, H, W, K, Co))
 
 
 def workspace_bytes(op, B, P, K, F):

@@ -5,7 +5,8 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libups_b200.so")
 HOST_LIB = os.path.join(CSRC, "libups_canon_host.so")
-CU_SOURCES = ["cabi.cu", "tps.cu", "parts_ops.cu", "step_fused.cu", "step_decode_bwd_tma.cu", "stats_ops.cu", "priors_ops.cu", "ingest.cu"]
+CU_SOURCES = ["cabi.cu", "tps.cu", "parts_ops.cu", "step_fused.cu", "step_decode_bwd_tma.cu", "stats_ops.cu", "priors_ops.cu", "ingest.cu",
+              "inject_conv.cu", "parts_conv.cu"]
 HEADERS = ["common.cuh", "canon_math.cuh", "pk_math.cuh", os.path.join("..", "..", "include", "ups_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

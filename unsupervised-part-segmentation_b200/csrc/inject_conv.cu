@@ -1,0 +1,591 @@
+// SURVEY.md 8f N4 (decoder side): the hourglass decoder's first convolution consuming the part
+// assignment directly, so that the injected map [B,h,w,F+K] (1.34 GB at CUB B=256) never exists.
+//
+//   injected = concat(sum_k unpool_features(feat, mask), mask)       cub/code/SB_model48i/model.py:482-484
+//   h        = conv2d(injected, V[3,3,F+K,Co]) + b                   model.py:96 (dd, :485), cub/code/nn.py:617-664
+//
+// Re-association: with the per-sample table  G[b,t,k,o] = sum_f feat[b,k,f] V[t,f,o] + V[t,F+k,o]  (t = 3i+j)
+//   h[b,y,x,o] = b[o] + sum_t sum_k mask[b,y+i-1,x+j-1,k] G[b,t,k,o]
+// and the decoding mask is straight-through hard (one non-zero per pixel, model.py:434-436,473), so the
+// forward is 9 table-row gathers per pixel (exact for any mask: pixels with several non-zeros take a dense
+// loop).  Backward: dmask is a dense (P x 9Co).(9Co x K) contraction on the g_out tile in shared memory,
+// dG a label-sorted segmented sum (deterministic, no atomics), db a column sum.
+#include "common.cuh"
+
+namespace ups {
+namespace {
+
+constexpr int IC_FWD_THREADS = 256;  // 8 warps = 8 rows of a strip
+constexpr int IC_FWD_ROWS = 8;
+constexpr int IC_BWD_THREADS = 288;  // 9 warps: one per filter tap in the dG phase
+constexpr int IC_TW = 32;            // backward tile width (pixels); thread = pixels (x, x+16)
+constexpr int IC_SMEM_BUDGET = 200 * 1024;
+
+// (label, value) of a mask pixel: label >= 0 one non-zero; -1 several non-zeros; -2 none
+__device__ __forceinline__ int2 compact_pixel(const float* __restrict__ m, int K) {
+    int lab = -2, nz = 0;
+    float val = 0.f;
+    if ((K & 3) == 0) {
+        for (int k = 0; k < K; k += 4) {
+            const float4 v = ld4(m + k);
+            const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (a[j] != 0.f) {
+                    if (nz == 0) { lab = k + j; val = a[j]; }
+                    ++nz;
+                }
+        }
+    } else {
+        for (int k = 0; k < K; ++k) {
+            const float v = __ldg(m + k);
+            if (v != 0.f) {
+                if (nz == 0) { lab = k; val = v; }
+                ++nz;
+            }
+        }
+    }
+    if (nz > 1) lab = -1;
+    return make_int2(lab, __float_as_int(val));
+}
+
+// ------------------------------------------------------------------ table G = feat.V[:F] + V[F:]
+__global__ void __launch_bounds__(256) inject_conv_table_fwd_kernel(const float* __restrict__ feat,
+                                                                    const float* __restrict__ V, float* __restrict__ G,
+                                                                    int K, int F, int Co) {
+    extern __shared__ float sf[];  // feat[b] : K*F
+    const int t = blockIdx.x, b = blockIdx.y;
+    for (int i = threadIdx.x; i < K * F; i += blockDim.x) sf[i] = __ldg(feat + (size_t)b * K * F + i);
+    __syncthreads();
+    const float* Vt = V + (size_t)t * (F + K) * Co;
+    for (int idx = threadIdx.x; idx < K * Co; idx += blockDim.x) {
+        const int k = idx / Co, o = idx - k * Co;
+        float acc = 0.f;
+        for (int f = 0; f < F; ++f) acc = fmaf(sf[k * F + f], __ldg(Vt + (size_t)f * Co + o), acc);
+        acc += __ldg(Vt + (size_t)(F + k) * Co + o);
+        G[(((size_t)b * 9 + t) * K + k) * Co + o] = acc;
+    }
+}
+
+// dfeat[b,k,f] = sum_{t,o} dG[b,t,k,o] V[t,f,o]
+__global__ void __launch_bounds__(256) inject_conv_table_bwd_feat_kernel(const float* __restrict__ dG,
+                                                                         const float* __restrict__ V,
+                                                                         float* __restrict__ dfeat, int K, int F, int Co) {
+    extern __shared__ float sd[];  // dG[b] : 9*K*Co
+    const int b = blockIdx.x;
+    const int n = 9 * K * Co;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sd[i] = __ldg(dG + (size_t)b * n + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int idx = warp; idx < K * F; idx += nw) {  // one warp per (k,f): lanes stride o
+        const int k = idx / F, f = idx - k * F;
+        float acc = 0.f;
+        for (int t = 0; t < 9; ++t) {
+            const float* Vr = V + ((size_t)t * (F + K) + f) * Co;
+            const float* dr = sd + (t * K + k) * Co;
+            for (int o = lane; o < Co; o += 32) acc = fmaf(dr[o], __ldg(Vr + o), acc);
+        }
+        acc = group_sum<32>(acc);
+        if (lane == 0) dfeat[((size_t)b * K + k) * F + f] = acc;
+    }
+}
+
+// dV[t,c,o] = sum_{b,k} feat[b,k,c] dG[b,t,k,o]  (c < F);   dV[t,F+k,o] = sum_b dG[b,t,k,o]
+__global__ void __launch_bounds__(128) inject_conv_table_bwd_filter_kernel(const float* __restrict__ dG,
+                                                                           const float* __restrict__ feat,
+                                                                           float* __restrict__ dV, int B, int K, int F,
+                                                                           int Co) {
+    const int t = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (F+K)*Co
+    if (idx >= (F + K) * Co) return;
+    const int c = idx / Co, o = idx - c * Co;
+    float acc = 0.f;
+    if (c < F) {
+        for (int b = 0; b < B; ++b) {
+            const float* d = dG + (((size_t)b * 9 + t) * K) * Co + o;
+            const float* fr = feat + (size_t)b * K * F + c;
+            for (int k = 0; k < K; ++k) acc = fmaf(__ldg(fr + (size_t)k * F), __ldg(d + (size_t)k * Co), acc);
+        }
+    } else {
+        const int k = c - F;
+        for (int b = 0; b < B; ++b) acc += __ldg(dG + (((size_t)b * 9 + t) * K + k) * Co + o);
+    }
+    dV[((size_t)t * (F + K) + c) * Co + o] = acc;
+}
+
+// ------------------------------------------------------------------ forward
+// grid (splits, B); a CTA walks `strips_per_cta` strips of 8 rows x W of one sample; warp = row, lane = o.
+template <int CCH>
+__global__ void __launch_bounds__(IC_FWD_THREADS) inject_conv_fwd_kernel(const float* __restrict__ mask,
+                                                                         const float* __restrict__ G,
+                                                                         const float* __restrict__ bias,
+                                                                         float* __restrict__ out, int H, int W, int K,
+                                                                         int Co, int strips_per_cta) {
+    extern __shared__ float4 smem4[];
+    float* sG = reinterpret_cast<float*>(smem4);          // [9][K][Co]
+    int2* sM = reinterpret_cast<int2*>(sG + 9 * K * Co);  // [(8+2)][W+2]  (9*K*Co % 4 == 0 -> 8-byte aligned)
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nG = 9 * K * Co;
+    const float* Gb = G + (size_t)b * nG;
+    for (int i = 4 * tid; i < nG; i += 4 * IC_FWD_THREADS) st4(sG + i, ld4(Gb + i));
+    float bo[CCH];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) bo[c] = (lane + 32 * c < Co) ? __ldg(bias + lane + 32 * c) : 0.f;
+
+    const int n_strips = (H + IC_FWD_ROWS - 1) / IC_FWD_ROWS;
+    const int s_beg = blockIdx.x * strips_per_cta;
+    const int s_end = min(n_strips, s_beg + strips_per_cta);
+    const int Wp = W + 2;
+    const float* mb = mask + (size_t)b * H * W * K;
+    for (int s = s_beg; s < s_end; ++s) {
+        const int y0 = s * IC_FWD_ROWS;
+        __syncthreads();  // sG visible / previous strip's readers done
+        for (int i = tid; i < (IC_FWD_ROWS + 2) * Wp; i += IC_FWD_THREADS) {
+            const int r = i / Wp, c = i - r * Wp;
+            const int y = y0 - 1 + r, x = c - 1;
+            int2 e = make_int2(-2, 0);
+            if (y >= 0 && y < H && x >= 0 && x < W) e = compact_pixel(mb + ((size_t)y * W + x) * K, K);
+            sM[i] = e;
+        }
+        __syncthreads();
+        const int y = y0 + warp;
+        if (y >= H) continue;  // whole warp; it still reaches the barriers of the next iteration
+        float* orow = out + (((size_t)b * H + y) * W) * Co;
+        for (int x = 0; x < W; ++x) {
+            float acc[CCH];
+#pragma unroll
+            for (int c = 0; c < CCH; ++c) acc[c] = bo[c];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t - 3 * dy;
+                const int2 e = sM[(warp + dy) * Wp + x + dx];
+                if (e.x >= 0) {
+                    const float v = __int_as_float(e.y);
+                    const float* g = sG + (t * K + e.x) * Co;
+#pragma unroll
+                    for (int c = 0; c < CCH; ++c)
+                        if (lane + 32 * c < Co) acc[c] = fmaf(v, g[lane + 32 * c], acc[c]);
+                } else if (e.x == -1) {  // several non-zeros: dense over k
+                    const float* m = mb + ((size_t)(y + dy - 1) * W + (x + dx - 1)) * K;
+                    for (int k = 0; k < K; ++k) {
+                        const float v = __ldg(m + k);
+                        if (v != 0.f) {
+                            const float* g = sG + (t * K + k) * Co;
+#pragma unroll
+                            for (int c = 0; c < CCH; ++c)
+                                if (lane + 32 * c < Co) acc[c] = fmaf(v, g[lane + 32 * c], acc[c]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CCH; ++c)
+                if (lane + 32 * c < Co) __stcs(orow + (size_t)x * Co + lane + 32 * c, acc[c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward
+struct BwdSmem {
+    int off_G, off_dG, off_db, off_g, off_list, off_tmp, off_dense, off_cnt, off_base, total;  // bytes
+};
+__host__ __device__ inline BwdSmem bwd_smem_layout(int KP, int K, int Co, int TH) {
+    BwdSmem s;
+    const int npx = TH * IC_TW, nch = npx / 32;
+    int o = 0;
+    s.off_G = o;     o += 4 * 9 * KP * Co;
+    s.off_dG = o;    o += 4 * 9 * K * Co;
+    s.off_db = o;    o += 4 * 9 * Co;
+    s.off_g = o;     o += 4 * (TH + 2) * (IC_TW + 2) * (Co + 4);
+    o = (o + 7) & ~7;
+    s.off_list = o;  o += 8 * npx;
+    s.off_tmp = o;   o += 8 * npx;
+    s.off_dense = o; o += 4 * npx;
+    s.off_cnt = o;   o += 4 * nch * (K + 1);   // per chunk: K label counts + 1 dense count
+    s.off_base = o;  o += 4 * (2 * K + 2);     // bucket starts [K+1] + sizes [K+1]
+    s.total = (o + 15) & ~15;
+    return s;
+}
+
+// grid (splits, B).  Tile = TH x 32 mask pixels q of one sample; the g_out tile carries a 1-pixel halo.
+//   dmask[q,k] = sum_t sum_o g_out[q - off_t, o] G[t,k,o]          (off_t = (i-1, j-1))
+//   dG[t,k,o] += sum_q mask[q,k] g_out[q - off_t, o]
+// If probs != NULL the dmask (+ g_extra) goes through the straight-through estimator (identity, nn.py:154-168)
+// and the softmax backward, and dlogits is written instead.
+template <int KP>
+__global__ void __launch_bounds__(IC_BWD_THREADS, 1) inject_conv_bwd_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ mask, const float* __restrict__ G,
+    const float* __restrict__ probs, const float* __restrict__ g_extra, float* __restrict__ dmask,
+    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co, int TH, int tiles_x, int n_tiles,
+    int tiles_per_cta) {
+    extern __shared__ float4 smem4[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>(smem4);
+    const BwdSmem L = bwd_smem_layout(KP, K, Co, TH);
+    float* sG = reinterpret_cast<float*>(sm + L.off_G);      // [9][KP][Co], rows k >= K zero
+    float* sdG = reinterpret_cast<float*>(sm + L.off_dG);    // [9][K][Co]
+    float* sdb = reinterpret_cast<float*>(sm + L.off_db);    // [9 warps][Co]
+    float* sg = reinterpret_cast<float*>(sm + L.off_g);      // [(TH+2)][34][Co+4]
+    int2* sList = reinterpret_cast<int2*>(sm + L.off_list);  // label-sorted (q, value)
+    int2* sTmp = reinterpret_cast<int2*>(sm + L.off_tmp);    // per pixel (label | rank<<8, value)
+    int* sDense = reinterpret_cast<int*>(sm + L.off_dense);  // pixels with several non-zeros
+    int* sCnt = reinterpret_cast<int*>(sm + L.off_cnt);      // [nch][K+1]
+    int* sBase = reinterpret_cast<int*>(sm + L.off_base);    // [K+1] bucket starts
+    int* sTot = sBase + K + 1;                               // [K+1] bucket sizes, [K] = #dense
+
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int CoP = Co + 4, Co4 = Co >> 2, TWp = IC_TW + 2;
+    const int npx = TH * IC_TW, nch = npx >> 5;
+    const size_t img = (size_t)b * H * W;
+
+    for (int i = tid; i < 9 * KP * Co; i += IC_BWD_THREADS) {
+        const int o = i % Co, k = (i / Co) % KP, t = i / (Co * KP);
+        sG[i] = k < K ? __ldg(G + (((size_t)b * 9 + t) * K + k) * Co + o) : 0.f;
+    }
+    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) sdG[i] = 0.f;
+    for (int i = tid; i < 9 * Co; i += IC_BWD_THREADS) sdb[i] = 0.f;
+
+    const int t_beg = blockIdx.x * tiles_per_cta;
+    const int t_end = min(n_tiles, t_beg + tiles_per_cta);
+    for (int tile = t_beg; tile < t_end; ++tile) {
+        const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * IC_TW;
+        __syncthreads();  // previous tile fully consumed; initialisation visible
+        // (1) g_out tile with halo, zero outside the image
+        for (int i = tid; i < (TH + 2) * TWp * Co4; i += IC_BWD_THREADS) {
+            const int px = i / Co4, o4 = i - px * Co4;
+            const int r = px / TWp, c = px - r * TWp;
+            const int y = y0 - 1 + r, x = x0 - 1 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = ld4_stream(g_out + ((img + (size_t)y * W + x) * Co + 4 * o4));
+            st4(sg + px * CoP + 4 * o4, v);
+        }
+        // (2a) compact the tile's mask pixels, count labels per 32-pixel chunk
+        for (int i = tid; i < nch * (K + 1); i += IC_BWD_THREADS) sCnt[i] = 0;
+        __syncthreads();
+        for (int ch = warp; ch < nch; ch += IC_BWD_THREADS / 32) {
+            const int i = ch * 32 + lane;
+            const int y = y0 + (i >> 5), x = x0 + (i & 31);
+            int2 e = make_int2(-2, 0);
+            if (y < H && x < W) e = compact_pixel(mask + (img + (size_t)y * W + x) * K, K);
+            const unsigned peers = __match_any_sync(0xffffffffu, e.x);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0 && e.x >= -1) sCnt[ch * (K + 1) + (e.x >= 0 ? e.x : K)] = __popc(peers);
+            sTmp[i] = make_int2((e.x & 0xff) | (rank << 8), e.y);
+        }
+        __syncthreads();
+        // (2b) exclusive prefix of the counts: over chunks per label, then over labels
+        if (tid <= K) {
+            int run = 0;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int c = sCnt[ch * (K + 1) + tid];
+                sCnt[ch * (K + 1) + tid] = run;
+                run += c;
+            }
+            sTot[tid] = run;  // [0..K) label totals, [K] pixels with several non-zeros
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int k = 0; k < K; ++k) {
+                sBase[k] = run;
+                run += sTot[k];
+            }
+            sBase[K] = run;
+        }
+        __syncthreads();
+        // (2c) scatter into label-sorted order (stable: chunk order, then lane order)
+        for (int i = tid; i < npx; i += IC_BWD_THREADS) {
+            const int2 e = sTmp[i];
+            const int lab = (int)(signed char)(e.x & 0xff), rank = e.x >> 8, ch = i >> 5;
+            if (lab >= 0)
+                sList[sBase[lab] + sCnt[ch * (K + 1) + lab] + rank] = make_int2(i, e.y);
+            else if (lab == -1)
+                sDense[sCnt[ch * (K + 1) + K] + rank] = i;
+        }
+        __syncthreads();
+
+        // (3) dmask for two pixels (x, x+16) of one tile row per thread
+        if (tid < TH * 16) {
+            const int r = tid >> 4, xa = tid & 15;
+            float acc[2][KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[0][k] = acc[1][k] = 0.f;
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t - 3 * dy;
+                const float* ga = sg + ((r + 2 - dy) * TWp + xa + 2 - dx) * CoP;
+                const float* gb = ga + 16 * CoP;
+                const float* Gt = sG + t * KP * Co;
+#pragma unroll 2
+                for (int o4 = 0; o4 < Co4; ++o4) {
+                    const float4 va = *reinterpret_cast<const float4*>(ga + 4 * o4);
+                    const float4 vb = *reinterpret_cast<const float4*>(gb + 4 * o4);
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const float4 w = *reinterpret_cast<const float4*>(Gt + k * Co + 4 * o4);
+                        acc[0][k] = fmaf(va.x, w.x, fmaf(va.y, w.y, fmaf(va.z, w.z, fmaf(va.w, w.w, acc[0][k]))));
+                        acc[1][k] = fmaf(vb.x, w.x, fmaf(vb.y, w.y, fmaf(vb.z, w.z, fmaf(vb.w, w.w, acc[1][k]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = y0 + r, x = x0 + xa + 16 * h;
+                if (y < H && x < W) {
+                    const size_t base = (img + (size_t)y * W + x) * K;
+                    if (g_extra != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < KP; ++k)
+                            if (k < K) acc[h][k] += __ldg(g_extra + base + k);
+                    }
+                    if (probs != nullptr) {
+                        float p[KP];
+                        float dot = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) {
+                            p[k] = k < K ? __ldg(probs + base + k) : 0.f;
+                            dot = fmaf(acc[h][k], p[k], dot);
+                        }
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) acc[h][k] = p[k] * (acc[h][k] - dot);
+                    }
+                    if ((K & 3) == 0) {
+#pragma unroll
+                        for (int k = 0; k < KP; k += 4)
+                            if (k < K)
+                                st4_stream(dmask + base + k,
+                                           make_float4(acc[h][k], acc[h][k + 1], acc[h][k + 2], acc[h][k + 3]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < KP; ++k)
+                            if (k < K) dmask[base + k] = acc[h][k];
+                    }
+                }
+            }
+        }
+
+        // (4) dG: warp = tap, lane = o; per label a segmented sum over the sorted list (4 independent chains)
+        {
+            const int t = warp, dy = t / 3, dx = t - 3 * dy;
+            const float* gt = sg + ((2 - dy) * TWp + 2 - dx) * CoP;  // + (ty*TWp + tx)*CoP + o
+            for (int oc = 0; oc < Co; oc += 32) {
+                const int o = oc + lane;
+                if (o < Co) {
+                    for (int k = 0; k < K; ++k) {
+                        const int beg = sBase[k], end = sBase[k + 1];
+                        if (beg == end) continue;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        int j = beg;
+                        for (; j + 4 <= end; j += 4) {
+                            const int2 e0 = sList[j], e1 = sList[j + 1], e2 = sList[j + 2], e3 = sList[j + 3];
+                            a0 = fmaf(__int_as_float(e0.y), gt[((e0.x >> 5) * TWp + (e0.x & 31)) * CoP + o], a0);
+                            a1 = fmaf(__int_as_float(e1.y), gt[((e1.x >> 5) * TWp + (e1.x & 31)) * CoP + o], a1);
+                            a2 = fmaf(__int_as_float(e2.y), gt[((e2.x >> 5) * TWp + (e2.x & 31)) * CoP + o], a2);
+                            a3 = fmaf(__int_as_float(e3.y), gt[((e3.x >> 5) * TWp + (e3.x & 31)) * CoP + o], a3);
+                        }
+                        for (; j < end; ++j) {
+                            const int2 e0 = sList[j];
+                            a0 = fmaf(__int_as_float(e0.y), gt[((e0.x >> 5) * TWp + (e0.x & 31)) * CoP + o], a0);
+                        }
+                        sdG[(t * K + k) * Co + o] += (a0 + a1) + (a2 + a3);
+                    }
+                    const int nd = sTot[K];
+                    for (int j = 0; j < nd; ++j) {  // pixels with several non-zeros (exact ties, soft masks)
+                        const int i = sDense[j];
+                        const float gv = gt[((i >> 5) * TWp + (i & 31)) * CoP + o];
+                        const float* m = mask + (img + (size_t)(y0 + (i >> 5)) * W + (x0 + (i & 31))) * K;
+                        for (int k = 0; k < K; ++k) {
+                            const float v = __ldg(m + k);
+                            if (v != 0.f) sdG[(t * K + k) * Co + o] = fmaf(v, gv, sdG[(t * K + k) * Co + o]);
+                        }
+                    }
+                    // db: column sums of the tile interior (zero-filled outside the image), rows warp, warp+9, ...
+                    float s = 0.f;
+                    for (int ty = warp; ty < TH; ty += IC_BWD_THREADS / 32) {
+                        const float* row = sg + ((ty + 1) * TWp + 1) * CoP + o;
+                        for (int tx = 0; tx < IC_TW; ++tx) s += row[tx * CoP];
+                    }
+                    sdb[warp * Co + o] += s;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const size_t slot = (size_t)b * gridDim.x + blockIdx.x;
+    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) ws_dG[slot * 9 * K * Co + i] = sdG[i];
+    for (int o = tid; o < Co; o += IC_BWD_THREADS) {
+        float s = 0.f;
+        for (int w = 0; w < IC_BWD_THREADS / 32; ++w) s += sdb[w * Co + o];
+        ws_db[slot * Co + o] = s;
+    }
+}
+
+// dG[b,i] = sum over the sample's splits (ascending); db[o] = sum over all (b, split) slots (ascending)
+__global__ void inject_conv_bwd_finalize_kernel(const float* __restrict__ ws_dG, const float* __restrict__ ws_db,
+                                                float* __restrict__ dG, float* __restrict__ db, int B, int splits,
+                                                int n_per, int Co) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * n_per;
+    if (i < total) {
+        const size_t b = i / n_per, r = i - b * n_per;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += ws_dG[(b * splits + sp) * n_per + r];
+        dG[i] = s;
+    }
+    if (db != nullptr && blockIdx.x == 0) {
+        for (int o = threadIdx.x; o < Co; o += blockDim.x) {
+            float s = 0.f;
+            for (int sl = 0; sl < B * splits; ++sl) s += ws_db[(size_t)sl * Co + o];
+            db[o] = s;
+        }
+    }
+}
+
+int check_dims(const char* what, int B, int H, int W, int K, int Co) {
+    UPS_REQUIRE(B >= 0 && H > 0 && W > 0, "%s: bad sizes B=%d H=%d W=%d", what, B, H, W);
+    UPS_REQUIRE(K >= 1 && K <= 32, "%s: K=%d outside [1,32]", what, K);
+    UPS_REQUIRE(Co >= 4 && Co <= 128 && Co % 4 == 0, "%s: Co=%d must be a multiple of 4 in [4,128]", what, Co);
+    UPS_REQUIRE((long long)B * H * W < (1ll << 31), "%s: B*H*W >= 2^31", what);
+    return UPS_OK;
+}
+
+int fwd_splits(int B, int H) {  // ~8 CTAs of 256 threads per SM
+    const int n_strips = (int)cdiv(H, IC_FWD_ROWS);
+    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);
+    if (want < 1) want = 1;
+    if (want > n_strips) want = n_strips;
+    return (int)want;
+}
+
+int bwd_tile_rows(int KP, int K, int Co) {
+    for (int th = 16; th >= 4; th >>= 1)
+        if (bwd_smem_layout(KP, K, Co, th).total <= IC_SMEM_BUDGET) return th;
+    return 0;
+}
+int bwd_kp(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : 32; }
+
+struct BwdPlan {
+    int KP, TH, tiles_x, tiles_y, n_tiles, splits, tiles_per_cta;
+};
+BwdPlan bwd_plan(int B, int H, int W, int K, int Co) {
+    BwdPlan p;
+    p.KP = bwd_kp(K);
+    p.TH = bwd_tile_rows(p.KP, K, Co);
+    if (p.TH == 0) { p.splits = 0; return p; }
+    p.tiles_x = (int)cdiv(W, IC_TW);
+    p.tiles_y = (int)cdiv(H, p.TH);
+    p.n_tiles = p.tiles_x * p.tiles_y;
+    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);  // one CTA per SM resident; several waves for balance
+    if (want < 1) want = 1;
+    if (want > p.n_tiles) want = p.n_tiles;
+    p.tiles_per_cta = (int)cdiv(p.n_tiles, want);
+    p.splits = (int)cdiv(p.n_tiles, p.tiles_per_cta);
+    return p;
+}
+
+template <int KP>
+int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const float* G, const float* probs,
+               const float* g_extra, float* dmask, float* ws_dG, float* ws_db, int B, int H, int W, int K, int Co,
+               cudaStream_t st) {
+    const int smem = bwd_smem_layout(KP, K, Co, p.TH).total;
+    UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    inject_conv_bwd_kernel<KP><<<dim3(p.splits, B), IC_BWD_THREADS, smem, st>>>(
+        g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.TH, p.tiles_x, p.n_tiles, p.tiles_per_cta);
+    return after_launch("inject_conv_bwd_kernel");
+}
+
+}  // namespace
+}  // namespace ups
+
+using namespace ups;
+
+extern "C" size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co) {
+    if (B <= 0 || H <= 0 || W <= 0 || K < 1 || K > 32 || Co < 4 || Co > 128 || (Co & 3)) return 256;
+    const BwdPlan p = bwd_plan(B, H, W, K, Co);
+    if (p.splits == 0) return 256;
+    return (size_t)B * p.splits * (9 * K * Co + Co) * sizeof(float) + 256;
+}
+
+extern "C" int ups_inject_conv_table_fwd(const float* feat, const float* V, float* G, int B, int K, int F, int Co,
+                                         void* stream) {
+    UPS_REQUIRE(feat && V && G, "inject_conv_table_fwd: null pointer");
+    UPS_REQUIRE(B >= 0 && K >= 1 && K <= 32 && F >= 1 && Co >= 1, "inject_conv_table_fwd: bad sizes");
+    UPS_REQUIRE((size_t)K * F * sizeof(float) <= 48 * 1024, "inject_conv_table_fwd: K*F=%d too large", K * F);
+    if (B == 0) return UPS_OK;
+    inject_conv_table_fwd_kernel<<<dim3(9, B), 256, K * F * sizeof(float), as_stream(stream)>>>(feat, V, G, K, F, Co);
+    return after_launch("inject_conv_table_fwd_kernel");
+}
+
+extern "C" int ups_inject_conv_table_bwd(const float* dG, const float* feat, const float* V, float* dfeat, float* dV,
+                                         int B, int K, int F, int Co, void* stream) {
+    UPS_REQUIRE(dG && feat && V, "inject_conv_table_bwd: null pointer");
+    UPS_REQUIRE(B >= 0 && K >= 1 && K <= 32 && F >= 1 && Co >= 1, "inject_conv_table_bwd: bad sizes");
+    const size_t smem = (size_t)9 * K * Co * sizeof(float);
+    UPS_REQUIRE(smem <= 200 * 1024, "inject_conv_table_bwd: 9*K*Co=%d too large", 9 * K * Co);
+    cudaStream_t st = as_stream(stream);
+    if (dfeat != nullptr && B > 0) {
+        UPS_CUDA(cudaFuncSetAttribute(inject_conv_table_bwd_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        inject_conv_table_bwd_feat_kernel<<<B, 256, smem, st>>>(dG, V, dfeat, K, F, Co);
+        if (int rc = after_launch("inject_conv_table_bwd_feat_kernel")) return rc;
+    }
+    if (dV != nullptr) {
+        inject_conv_table_bwd_filter_kernel<<<dim3((unsigned)cdiv((long long)(F + K) * Co, 128), 9), 128, 0, st>>>(
+            dG, feat, dV, B, K, F, Co);
+        if (int rc = after_launch("inject_conv_table_bwd_filter_kernel")) return rc;
+    }
+    return UPS_OK;
+}
+
+extern "C" int ups_inject_conv_fwd(const float* mask, const float* G, const float* bias, float* out, int B, int H, int W,
+                                   int K, int Co, void* stream) {
+    UPS_REQUIRE(mask && G && bias && out, "inject_conv_fwd: null pointer");
+    if (int rc = check_dims("inject_conv_fwd", B, H, W, K, Co)) return rc;
+    UPS_REQUIRE(aligned16(mask) && aligned16(G), "inject_conv_fwd: mask and G must be 16-byte aligned");
+    if (B == 0) return UPS_OK;
+    const size_t smem = (size_t)9 * K * Co * sizeof(float) + (size_t)(IC_FWD_ROWS + 2) * (W + 2) * sizeof(int2);
+    UPS_REQUIRE(smem <= (size_t)IC_SMEM_BUDGET, "inject_conv_fwd: K=%d Co=%d W=%d needs %zu bytes of shared memory", K, Co,
+                W, smem);
+    const int splits = fwd_splits(B, H);
+    const int n_strips = (int)cdiv(H, IC_FWD_ROWS);
+    const int spc = (int)cdiv(n_strips, splits);
+    const dim3 grid((unsigned)cdiv(n_strips, spc), B);
+    cudaStream_t st = as_stream(stream);
+#define UPS_IC_FWD(CCH)                                                                                               \
+    do {                                                                                                              \
+        UPS_CUDA(cudaFuncSetAttribute(inject_conv_fwd_kernel<CCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)smem));                                                                    \
+        inject_conv_fwd_kernel<CCH><<<grid, IC_FWD_THREADS, smem, st>>>(mask, G, bias, out, H, W, K, Co, spc);        \
+    } while (0)
+    if (Co <= 32) UPS_IC_FWD(1);
+    else if (Co <= 64) UPS_IC_FWD(2);
+    else UPS_IC_FWD(4);
+#undef UPS_IC_FWD
+    return after_launch("inject_conv_fwd_kernel");
+}
+
+extern "C" int ups_inject_conv_bwd(const float* g_out, const float* mask, const float* G, const float* probs,
+                                   const float* g_extra, float* dmask, float* dG, float* db, int B, int H, int W, int K,
+                                   int Co, void* ws, size_t ws_bytes, void* stream) {
+    UPS_REQUIRE(g_out && mask && G && dmask && dG, "inject_conv_bwd: null pointer");
+    if (int rc = check_dims("inject_conv_bwd", B, H, W, K, Co)) return rc;
+    UPS_REQUIRE(aligned16(g_out) && aligned16(mask) && aligned16(dmask), "inject_conv_bwd: buffers must be 16-byte aligned");
+    if (B == 0) return UPS_OK;
+    const BwdPlan p = bwd_plan(B, H, W, K, Co);
+    UPS_REQUIRE(p.splits > 0, "inject_conv_bwd: K=%d Co=%d does not fit shared memory", K, Co);
+    const size_t need = ups_inject_conv_workspace_bytes(B, H, W, K, Co);
+    UPS_REQUIRE(ws != nullptr && ws_bytes >= need, "inject_conv_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    float* ws_dG = reinterpret_cast<float*>(ws);
+    float* ws_db = ws_dG + (size_t)B * p.splits * 9 * K * Co;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    switch (p.KP) {
+        case 8: rc = launch_bwd<8>(p, g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, B, H, W, K, Co, st); break;
+        case 16: rc = launch_bwd<16>(p, g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, B, H, W, K, Co, st); break;
+        case 24: rc = launch_bwd<24>(p, g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, B, H, W, K, Co, st); break;
+        default: rc = launch_bwd<32>(p, g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, B, H, W, K, Co, st); break;
+    }
+    if (rc) return rc;
+    const int n_per = 9 * K * Co;
+    inject_conv_bwd_finalize_kernel<<<(unsigned)cdiv((long long)B * n_per, 256), 256, 0, st>>>(ws_dG, ws_db, dG, db, B,
+                                                                                                 p.splits, n_per, Co);
+    return after_launch("inject_conv_bwd_finalize_kernel");
+}

@@ -76,6 +76,54 @@ def inject_features(feature_vectors, mask):
     return ops.part_inject(feature_vectors, mask)
 
 
+def inject_conv2d(feature_vectors, mask, V, b):
+    """The decoder's first layer on the injected part map, without the map: the three lines at
+    cub/code/SB_model48i/model.py:482-484 followed by hourglass_model's `nn.conv2d(x, config[0])`
+    (model.py:96; `dd`, :485; cub/code/nn.py:617-664 — 3x3, stride 1, SAME, + bias).
+    feature_vectors [B,parts,F], mask [B,h,w,parts], V [3,3,F+parts,Co] (TensorFlow HWIO), b [Co] -> [B,h,w,Co].
+    Equals nn.conv2d(inject_features(feature_vectors, mask)); differentiable in all four arguments."""
+    bs, h, w, n_parts = mask.shape
+    fshape = list(feature_vectors.shape)
+    assert len(fshape) == 3, fshape
+    assert fshape[0] == bs and fshape[1] == n_parts, fshape
+    vshape = list(V.shape)
+    assert vshape[:3] == [3, 3, fshape[2] + n_parts], vshape
+    assert list(b.shape) == [vshape[3]], b.shape
+    G = ops.inject_conv_table(feature_vectors, V.reshape(9, vshape[2], vshape[3]))
+    return ops.inject_conv_apply(mask, G, b)
+
+
+def decode_conv2d(logits, feature_vectors, V, b):
+    """The decode side of the step with the first decoder layer folded in (model.py:426,434-436,447,470-473,482-485):
+    m0 = softmax(logits); labels = argmax(m0); mask = ST(hard_max(m0)); h = inject_conv2d(feature_vectors, mask, V, b).
+    Returns (m0, labels int64, mask, h); the backward runs the conv backward, the straight-through estimator and the
+    softmax backward in one kernel."""
+    bs, h, w, n_parts = logits.shape
+    fshape = list(feature_vectors.shape)
+    assert len(fshape) == 3, fshape
+    assert fshape[0] == bs and fshape[1] == n_parts, fshape
+    vshape = list(V.shape)
+    assert vshape[:3] == [3, 3, fshape[2] + n_parts], vshape
+    assert list(b.shape) == [vshape[3]], b.shape
+    G = ops.inject_conv_table(feature_vectors, V.reshape(9, vshape[2], vshape[3]))
+    return ops.decode_conv(logits, G, b)
+
+
+def parts_conv2d(image, mask, V, b):
+    """The appearance encoder's first layer on the masked part images, without the part images:
+    `mask_parts(image, mask)` (cub/code/SB_model48i/model.py:176-187, :478) folded part-major by
+    `nn.apply_partwise` (cub/code/nn.py:100-103) and fed to encoder_model's `nn.conv2d(x, config[0])`
+    (model.py:40; cub/code/nn.py:617-664).  image [B,h,w,3], mask [B,h,w,parts], V [3,3,3,Co], b [Co]
+    -> [parts*B,h,w,Co] (row k*B+b), what the rest of `e_alpha` consumes inside apply_partwise.  Forward only."""
+    bs, h, w, n_features = image.shape
+    mshape = list(mask.shape)
+    assert mshape[0] == bs and mshape[1] == h and mshape[2] == w, mshape
+    vshape = list(V.shape)
+    assert vshape[:3] == [3, 3, n_features], vshape
+    assert list(b.shape) == [vshape[3]], b.shape
+    return ops.parts_conv(image, mask, V.reshape(9, n_features, vshape[3]), b)
+
+
 def images_from_uint8(images):
     """The host-side normalisation of the reference's data pipeline, moved onto the device:
     `o.astype(np.float32) * 2.0 / 255.0 - 1.0` (cub/code/data/data.py:134,152;

@@ -677,3 +677,102 @@ def _mask2rgb(mask: Tensor, table: Tensor, make_hot: bool) -> Tensor:
 
 
 mask2rgb = _op("mask2rgb", _mask2rgb, lambda m, t, h: m.new_empty(*m.shape[:-1], 3))
+
+
+# ------------------------------------------------------------------ decoder first conv on the part assignment (N4)
+def _inject_conv_table(feat: Tensor, V: Tensor) -> Tensor:
+    feat, V = _f32(feat, "feature_vectors"), _f32(V, "V")
+    B, K, F = feat.shape
+    Co = V.shape[-1]
+    G = torch.empty(B, 9, K, Co, dtype=torch.float32, device=feat.device)
+    C.call("ups_inject_conv_table_fwd", feat.data_ptr(), V.data_ptr(), G.data_ptr(), B, K, F, Co, _stream())
+    return G
+
+
+def _inject_conv_table_grad(dG: Tensor, feat: Tensor, V: Tensor) -> Tuple[Tensor, Tensor]:
+    dG, feat, V = _f32(dG), _f32(feat), _f32(V)
+    B, K, F = feat.shape
+    Co = V.shape[-1]
+    dfeat, dV = torch.empty_like(feat), torch.empty_like(V)
+    C.call("ups_inject_conv_table_bwd", dG.data_ptr(), feat.data_ptr(), V.data_ptr(), dfeat.data_ptr(), dV.data_ptr(),
+           B, K, F, Co, _stream())
+    return dfeat, dV
+
+
+inject_conv_table_grad = _op("inject_conv_table_grad", _inject_conv_table_grad,
+                             lambda g, f, v: (torch.empty_like(f), torch.empty_like(v)))
+inject_conv_table = _op("inject_conv_table", _inject_conv_table,
+                        lambda f, v: f.new_empty(f.shape[0], 9, f.shape[1], v.shape[-1]),
+                        lambda ctx, g: inject_conv_table_grad(g, *ctx.saved_tensors),
+                        lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+def _inject_conv_apply(mask: Tensor, G: Tensor, bias: Tensor) -> Tensor:
+    mask, G, bias = _f32(mask, "mask"), _f32(G, "G"), _f32(bias, "b")
+    B, H, W, K = mask.shape
+    Co = G.shape[-1]
+    out = torch.empty(B, H, W, Co, dtype=torch.float32, device=mask.device)
+    C.call("ups_inject_conv_fwd", mask.data_ptr(), G.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, K, Co,
+           _stream())
+    return out
+
+
+def _inject_conv_apply_grad(g_out: Tensor, mask: Tensor, G: Tensor, probs: Optional[Tensor],
+                            g_extra: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    g_out, mask, G = _f32(g_out), _f32(mask), _f32(G)
+    probs = None if probs is None else _f32(probs)
+    g_extra = None if g_extra is None else _f32(g_extra)
+    B, H, W, K = mask.shape
+    Co = G.shape[-1]
+    dmask, dG = torch.empty_like(mask), torch.empty_like(G)
+    db = torch.empty(Co, dtype=torch.float32, device=mask.device)
+    ws = _ws(C.inject_conv_workspace_bytes(B, H, W, K, Co), mask)
+    C.call("ups_inject_conv_bwd", g_out.data_ptr(), mask.data_ptr(), G.data_ptr(), _ptr(probs), _ptr(g_extra),
+           dmask.data_ptr(), dG.data_ptr(), db.data_ptr(), B, H, W, K, Co, ws.data_ptr(), ws.numel(), _stream())
+    return dmask, dG, db
+
+
+inject_conv_apply_grad = _op(
+    "inject_conv_apply_grad", _inject_conv_apply_grad,
+    lambda g, m, G, p, e: (torch.empty_like(m), torch.empty_like(G), G.new_empty(G.shape[-1])))
+inject_conv_apply = _op("inject_conv_apply", _inject_conv_apply,
+                        lambda m, G, b: m.new_empty(*m.shape[:-1], G.shape[-1]),
+                        lambda ctx, g: inject_conv_apply_grad(g, *ctx.saved_tensors, None, None),
+                        lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1]))
+
+
+def _decode_conv(logits: Tensor, G: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """softmax -> labels -> ST(hard_max) -> first decoder conv, the decode side of the step with the conv folded in."""
+    probs, labels, hard = _part_softmax_full(logits)
+    return probs, labels, hard, _inject_conv_apply(hard, G, bias)
+
+
+def _decode_conv_bwd(ctx, g_probs, g_labels, g_hard, g_out):
+    probs, hard, G = ctx.saved_tensors
+    g_extra = g_probs if g_hard is None else (g_hard if g_probs is None else g_probs + g_hard)
+    if g_out is None:
+        return (None if g_extra is None else part_softmax_grad(probs, g_extra)), None, None
+    dlogits, dG, db = inject_conv_apply_grad(g_out, hard, G, probs, g_extra)
+    return dlogits, dG, db
+
+
+decode_conv = _op(
+    "decode_conv", _decode_conv,
+    lambda x, G, b: (torch.empty_like(x), x.new_empty(x.shape[:-1], dtype=torch.int64), torch.empty_like(x),
+                     x.new_empty(*x.shape[:-1], G.shape[-1])),
+    _decode_conv_bwd, lambda ctx, inputs, output: ctx.save_for_backward(output[0], output[2], inputs[1]))
+
+
+# ------------------------------------------------------------------ encoder first conv on the masked part images (N4)
+def _parts_conv(image: Tensor, mask: Tensor, V: Tensor, bias: Tensor) -> Tensor:
+    image, mask, V, bias = _f32(image, "image"), _f32(mask, "mask"), _f32(V, "V"), _f32(bias, "b")
+    B, H, W, K = mask.shape
+    Cin, Co = image.shape[-1], V.shape[-1]
+    out = torch.empty(K * B, H, W, Co, dtype=torch.float32, device=image.device)
+    C.call("ups_parts_conv_fwd", image.data_ptr(), mask.data_ptr(), V.data_ptr(), bias.data_ptr(), out.data_ptr(),
+           B, H, W, K, Cin, Co, _stream())
+    return out
+
+
+parts_conv = _op("parts_conv", _parts_conv,
+                 lambda i, m, v, b: i.new_empty(m.shape[-1] * m.shape[0], m.shape[1], m.shape[2], v.shape[-1]))
