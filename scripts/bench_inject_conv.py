@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--parts", type=int, default=16)
     ap.add_argument("--no-library", action="store_true", help="skip the cuDNN comparison legs")
+    ap.add_argument("--once", action="store_true", help="call every entry once and exit (for ncu)")
     a = ap.parse_args()
     import torch
     import ups_b200  # noqa: F401
@@ -92,6 +93,11 @@ def main():
             n_pix * 4 * (2 * (F + K) + Co))
         calls["library: cuDNN conv2d fwd on part images [K*B,P,3] (fp32)"] = (
             lambda: TF.conv2d(x_parts, we_nchw, be, padding=1), n_pix * 4 * K * (3 + Co))
+    if a.once:
+        for name, (fn, by) in calls.items():
+            fn()
+        torch.cuda.synchronize()
+        return
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     res = {}
     for name, (fn, by) in calls.items():

@@ -19,7 +19,8 @@ constexpr int IC_FWD_THREADS = 256;  // 8 warps = 8 rows of a strip
 constexpr int IC_FWD_ROWS = 8;
 constexpr int IC_BWD_THREADS = 288;  // 9 warps: one per filter tap in the dG phase
 constexpr int IC_TW = 32;            // backward tile width (pixels); thread = pixels (x, x+16)
-constexpr int IC_SMEM_BUDGET = 200 * 1024;
+constexpr int IC_SMEM_BUDGET = 224 * 1024;   // per CTA (227 KB is the hardware limit)
+constexpr int IC_SMEM_HALF = 112 * 1024;     // two CTAs per SM
 
 // (label, value) of a mask pixel: label >= 0 one non-zero; -1 several non-zeros; -2 none
 __device__ __forceinline__ int2 compact_pixel(const float* __restrict__ m, int K) {
@@ -28,13 +29,13 @@ __device__ __forceinline__ int2 compact_pixel(const float* __restrict__ m, int K
     if ((K & 3) == 0) {
         for (int k = 0; k < K; k += 4) {
             const float4 v = ld4(m + k);
-            const float a[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (a[j] != 0.f) {
-                    if (nz == 0) { lab = k + j; val = a[j]; }
-                    ++nz;
-                }
+#define UPS_IC_SEE(val_, j_)                             \
+    if ((val_) != 0.f) {                                 \
+        if (nz == 0) { lab = k + (j_); val = (val_); }   \
+        ++nz;                                            \
+    }
+            UPS_IC_SEE(v.x, 0) UPS_IC_SEE(v.y, 1) UPS_IC_SEE(v.z, 2) UPS_IC_SEE(v.w, 3)
+#undef UPS_IC_SEE
         }
     } else {
         for (int k = 0; k < K; ++k) {
@@ -67,55 +68,116 @@ __global__ void __launch_bounds__(256) inject_conv_table_fwd_kernel(const float*
     }
 }
 
-// dfeat[b,k,f] = sum_{t,o} dG[b,t,k,o] V[t,f,o]
+// dfeat[b,k,f] = sum_{t,o} dG[b,t,k,o] V[t,f,o]: one CTA per sample, one thread per (k,f), dG[b] in shared memory
 __global__ void __launch_bounds__(256) inject_conv_table_bwd_feat_kernel(const float* __restrict__ dG,
                                                                          const float* __restrict__ V,
                                                                          float* __restrict__ dfeat, int K, int F, int Co) {
-    extern __shared__ float sd[];  // dG[b] : 9*K*Co
+    extern __shared__ float4 sd4[];  // dG[b] : 9*K*Co
+    float* sd = reinterpret_cast<float*>(sd4);
     const int b = blockIdx.x;
     const int n = 9 * K * Co;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sd[i] = __ldg(dG + (size_t)b * n + i);
+    for (int i = 4 * threadIdx.x; i < n; i += 4 * blockDim.x) st4(sd + i, ld4(dG + (size_t)b * n + i));
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int idx = warp; idx < K * F; idx += nw) {  // one warp per (k,f): lanes stride o
-        const int k = idx / F, f = idx - k * F;
-        float acc = 0.f;
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < K * F; idx += gridDim.y * blockDim.x) {
+        const int k = idx / F, f = idx - k * F;  // consecutive threads: consecutive f (distinct V rows), same dG row
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int t = 0; t < 9; ++t) {
             const float* Vr = V + ((size_t)t * (F + K) + f) * Co;
             const float* dr = sd + (t * K + k) * Co;
-            for (int o = lane; o < Co; o += 32) acc = fmaf(dr[o], __ldg(Vr + o), acc);
+            for (int o = 0; o < Co; o += 4) {
+                const float4 v = ld4(Vr + o);
+                const float4 d = *reinterpret_cast<const float4*>(dr + o);
+                a0 = fmaf(d.x, v.x, a0); a1 = fmaf(d.y, v.y, a1); a2 = fmaf(d.z, v.z, a2); a3 = fmaf(d.w, v.w, a3);
+            }
         }
-        acc = group_sum<32>(acc);
-        if (lane == 0) dfeat[((size_t)b * K + k) * F + f] = acc;
+        dfeat[((size_t)b * K + k) * F + f] = (a0 + a1) + (a2 + a3);
     }
 }
 
-// dV[t,c,o] = sum_{b,k} feat[b,k,c] dG[b,t,k,o]  (c < F);   dV[t,F+k,o] = sum_b dG[b,t,k,o]
-__global__ void __launch_bounds__(128) inject_conv_table_bwd_filter_kernel(const float* __restrict__ dG,
+// dV[t,c,o] = sum_{b,k} feat[b,k,c] dG[b,t,k,o]  (c < F);   dV[t,F+k,o] = sum_b dG[b,t,k,o].
+// grid (ceil((F+K)/4), 9): one CTA per 4 filter rows; warp w sums the samples b = w, w+8, ... (lane = o), then the
+// 8 partial rows are added in warp order: deterministic.
+__global__ void __launch_bounds__(256) inject_conv_table_bwd_filter_kernel(const float* __restrict__ dG,
                                                                            const float* __restrict__ feat,
                                                                            float* __restrict__ dV, int B, int K, int F,
                                                                            int Co) {
-    const int t = blockIdx.y;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (F+K)*Co
-    if (idx >= (F + K) * Co) return;
-    const int c = idx / Co, o = idx - c * Co;
-    float acc = 0.f;
-    if (c < F) {
-        for (int b = 0; b < B; ++b) {
-            const float* d = dG + (((size_t)b * 9 + t) * K) * Co + o;
-            const float* fr = feat + (size_t)b * K * F + c;
-            for (int k = 0; k < K; ++k) acc = fmaf(__ldg(fr + (size_t)k * F), __ldg(d + (size_t)k * Co), acc);
+    extern __shared__ float sp[];  // [8 warps][4][Co]
+    const int c0 = 4 * blockIdx.x, t = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o0 = 0; o0 < Co; o0 += 32) {
+        const int o = o0 + lane;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (o < Co) {
+            for (int b = warp; b < B; b += 8) {
+                const float* d = dG + (((size_t)b * 9 + t) * K) * Co + o;
+                const float* fr = feat + (size_t)b * K * F;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = c0 + j;
+                    if (c < F) {
+#pragma unroll 8
+                        for (int k = 0; k < K; ++k)
+                            acc[j] = fmaf(__ldg(fr + (size_t)k * F + c), __ldg(d + (size_t)k * Co), acc[j]);
+                    } else if (c < F + K) {
+                        acc[j] += __ldg(d + (size_t)(c - F) * Co);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sp[(warp * 4 + j) * Co + o] = acc[j];
         }
-    } else {
-        const int k = c - F;
-        for (int b = 0; b < B; ++b) acc += __ldg(dG + (((size_t)b * 9 + t) * K + k) * Co + o);
     }
-    dV[((size_t)t * (F + K) + c) * Co + o] = acc;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * Co; i += blockDim.x) {
+        const int j = i / Co, o = i - j * Co;
+        if (c0 + j >= F + K) continue;
+        float s2 = 0.f;
+        for (int w = 0; w < 8; ++w) s2 += sp[(w * 4 + j) * Co + o];
+        dV[((size_t)t * (F + K) + c0 + j) * Co + o] = s2;
+    }
 }
 
 // ------------------------------------------------------------------ forward
-// grid (splits, B); a CTA walks `strips_per_cta` strips of 8 rows x W of one sample; warp = row, lane = o.
-template <int CCH>
+// grid (splits, B); a CTA walks `strips_per_cta` strips of 8 rows x W of one sample.  The strip's mask pixels
+// (with a 1-pixel halo) are compacted to (table row offset, value) in shared memory; then one thread per
+// (pixel, 4 output channels): 9 x (LDS.64 entry, LDS.128 table row, 4 FMA), one 16-byte streaming store.
+template <bool DENSE>
+__device__ __forceinline__ void inject_conv_fwd_rows(const float* __restrict__ sG, const float* __restrict__ sB,
+                                                     const int2* __restrict__ sM, const float* __restrict__ mb,
+                                                     float* __restrict__ ob, int y0, int rows, int H, int W, int K,
+                                                     int Co, int Co4, int tid) {
+    const int Wp = W + 2, KCo = K * Co;
+    for (int idx = tid; idx < rows * W * Co4; idx += IC_FWD_THREADS) {
+        const int px = idx / Co4, o = 4 * (idx - px * Co4);
+        const int r = px / W, x = px - r * W;
+        float4 acc = *reinterpret_cast<const float4*>(sB + o);
+        const int2* e0 = sM + r * Wp + x;
+        const float* g0 = sG + o;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t - 3 * dy;
+            const int2 e = e0[dy * Wp + dx];
+            if (!DENSE || e.x >= 0) {
+                const float v = __int_as_float(e.y);
+                const float4 g = *reinterpret_cast<const float4*>(g0 + t * KCo + e.x);
+                acc.x = fmaf(v, g.x, acc.x); acc.y = fmaf(v, g.y, acc.y);
+                acc.z = fmaf(v, g.z, acc.z); acc.w = fmaf(v, g.w, acc.w);
+            } else {  // several non-zeros: dense over k
+                const float* m = mb + ((size_t)(y0 + r + dy - 1) * W + (x + dx - 1)) * K;
+                for (int k = 0; k < K; ++k) {
+                    const float v = __ldg(m + k);
+                    if (v != 0.f) {
+                        const float4 g = *reinterpret_cast<const float4*>(g0 + t * KCo + k * Co);
+                        acc.x = fmaf(v, g.x, acc.x); acc.y = fmaf(v, g.y, acc.y);
+                        acc.z = fmaf(v, g.z, acc.z); acc.w = fmaf(v, g.w, acc.w);
+                    }
+                }
+            }
+        }
+        st4_stream(ob + ((size_t)(y0 + r) * W + x) * Co + o, acc);
+    }
+}
+
 __global__ void __launch_bounds__(IC_FWD_THREADS) inject_conv_fwd_kernel(const float* __restrict__ mask,
                                                                          const float* __restrict__ G,
                                                                          const float* __restrict__ bias,
@@ -123,65 +185,42 @@ __global__ void __launch_bounds__(IC_FWD_THREADS) inject_conv_fwd_kernel(const f
                                                                          int Co, int strips_per_cta) {
     extern __shared__ float4 smem4[];
     float* sG = reinterpret_cast<float*>(smem4);          // [9][K][Co]
-    int2* sM = reinterpret_cast<int2*>(sG + 9 * K * Co);  // [(8+2)][W+2]  (9*K*Co % 4 == 0 -> 8-byte aligned)
-    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nG = 9 * K * Co;
+    float* sB = sG + 9 * K * Co;                          // [Co]
+    int2* sM = reinterpret_cast<int2*>(sB + Co);          // [(8+2)][W+2] (offset of the table row = label*Co, value)
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int nG = 9 * K * Co, Co4 = Co >> 2;
     const float* Gb = G + (size_t)b * nG;
     for (int i = 4 * tid; i < nG; i += 4 * IC_FWD_THREADS) st4(sG + i, ld4(Gb + i));
-    float bo[CCH];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) bo[c] = (lane + 32 * c < Co) ? __ldg(bias + lane + 32 * c) : 0.f;
+    for (int i = tid; i < Co; i += IC_FWD_THREADS) sB[i] = __ldg(bias + i);
 
     const int n_strips = (H + IC_FWD_ROWS - 1) / IC_FWD_ROWS;
     const int s_beg = blockIdx.x * strips_per_cta;
     const int s_end = min(n_strips, s_beg + strips_per_cta);
     const int Wp = W + 2;
     const float* mb = mask + (size_t)b * H * W * K;
+    float* ob = out + (size_t)b * H * W * Co;
     for (int s = s_beg; s < s_end; ++s) {
         const int y0 = s * IC_FWD_ROWS;
+        const int rows = min(IC_FWD_ROWS, H - y0);
         __syncthreads();  // sG visible / previous strip's readers done
-        for (int i = tid; i < (IC_FWD_ROWS + 2) * Wp; i += IC_FWD_THREADS) {
+        int dense = 0;
+        for (int i = tid; i < (rows + 2) * Wp; i += IC_FWD_THREADS) {
             const int r = i / Wp, c = i - r * Wp;
             const int y = y0 - 1 + r, x = c - 1;
-            int2 e = make_int2(-2, 0);
-            if (y >= 0 && y < H && x >= 0 && x < W) e = compact_pixel(mb + ((size_t)y * W + x) * K, K);
+            int2 e = make_int2(0, 0);  // empty / outside: row 0 scaled by 0
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                e = compact_pixel(mb + ((size_t)y * W + x) * K, K);
+                if (e.x == -1) dense = 1;
+                else if (e.x < 0) e = make_int2(0, 0);
+                else e.x *= Co;
+            }
             sM[i] = e;
         }
-        __syncthreads();
-        const int y = y0 + warp;
-        if (y >= H) continue;  // whole warp; it still reaches the barriers of the next iteration
-        float* orow = out + (((size_t)b * H + y) * W) * Co;
-        for (int x = 0; x < W; ++x) {
-            float acc[CCH];
-#pragma unroll
-            for (int c = 0; c < CCH; ++c) acc[c] = bo[c];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int dy = t / 3, dx = t - 3 * dy;
-                const int2 e = sM[(warp + dy) * Wp + x + dx];
-                if (e.x >= 0) {
-                    const float v = __int_as_float(e.y);
-                    const float* g = sG + (t * K + e.x) * Co;
-#pragma unroll
-                    for (int c = 0; c < CCH; ++c)
-                        if (lane + 32 * c < Co) acc[c] = fmaf(v, g[lane + 32 * c], acc[c]);
-                } else if (e.x == -1) {  // several non-zeros: dense over k
-                    const float* m = mb + ((size_t)(y + dy - 1) * W + (x + dx - 1)) * K;
-                    for (int k = 0; k < K; ++k) {
-                        const float v = __ldg(m + k);
-                        if (v != 0.f) {
-                            const float* g = sG + (t * K + k) * Co;
-#pragma unroll
-                            for (int c = 0; c < CCH; ++c)
-                                if (lane + 32 * c < Co) acc[c] = fmaf(v, g[lane + 32 * c], acc[c]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < CCH; ++c)
-                if (lane + 32 * c < Co) __stcs(orow + (size_t)x * Co + lane + 32 * c, acc[c]);
-        }
+        dense = __syncthreads_or(dense);
+        if (dense)
+            inject_conv_fwd_rows<true>(sG, sB, sM, mb, ob, y0, rows, H, W, K, Co, Co4, tid);
+        else
+            inject_conv_fwd_rows<false>(sG, sB, sM, mb, ob, y0, rows, H, W, K, Co, Co4, tid);
     }
 }
 
@@ -418,6 +457,313 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, 1) inject_conv_bwd_kernel(
     }
 }
 
+// ---- tensor-core variant of the backward (Co in {8,16,32,64,128}) ---------------------------------
+// Same tiling, sort and outputs as inject_conv_bwd_kernel; the dense contraction
+//   dmask[q, k] = sum_{t,o} g_out[q - off_t, o] G[t,k,o]        (M = pixels, N = K, reduction = 9*Co)
+// runs as mma.sync.m16n8k8 TF32 with the 3xTF32 split (a = hi + lo, hi = the 19 bits the tensor core keeps;
+// hi*hi' + lo*hi' + hi*lo' accumulated in fp32: error ~2^-21 per product, inside the 1e-4/1e-5 tolerance).
+// A fragments come straight from the padded g_out tile (row stride Co+4 floats: conflict-free), B fragments from
+// the pre-split table in shared memory.  Warps 0-7 own TH/4 m-tiles (16 pixels of one tile row) each; the dG
+// phase is vectorised: a warp owns a (tap, label) unit, 4 channels per lane, 32/(Co/4) list entries in parallel.
+struct BwdMmaSmem {
+    int off_G, off_dG, off_db, off_g, off_list, off_tmp, off_dense, off_cnt, off_base, total, KPp;
+};
+__host__ __device__ inline BwdMmaSmem bwd_mma_smem_layout(int KP, int K, int Co, int TH) {
+    BwdMmaSmem s;
+    const int npx = TH * IC_TW, nch = npx / 32;
+    s.KPp = (KP % 32 == 8 || KP % 32 == 24) ? KP : KP + 8;  // B-fragment loads (4 o-rows x 8 k) hit 32 distinct banks
+    int o = 0;
+    s.off_G = o;     o += 4 * 9 * Co * s.KPp;
+    s.off_dG = o;    o += 4 * 9 * K * Co;
+    s.off_db = o;    o += 4 * 9 * Co;
+    o = (o + 15) & ~15;
+    s.off_g = o;     o += 4 * (TH + 2) * (IC_TW + 2) * (Co + 4);
+    o = (o + 7) & ~7;
+    s.off_list = o;  o += 8 * npx;
+    s.off_tmp = o;   o += 8 * npx;
+    s.off_dense = o; o += 4 * npx;
+    s.off_cnt = o;   o += 4 * nch * (K + 1);
+    s.off_base = o;  o += 4 * (2 * K + 2);
+    s.total = (o + 15) & ~15;
+    return s;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// a = hi + lo with both parts rounded to nearest TF32 (truncation would bias the dropped bits and the bias adds up
+// linearly over the 9*Co products)
+__device__ __forceinline__ void split_tf32(float a, unsigned& hi, unsigned& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(a));
+    const float r = __fsub_rn(a, __uint_as_float(hi));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+template <int NT, int MTW>  // N tiles of 8 parts: KP = 8*NT >= K;  m-tiles per warp: tile rows TH = 4*MTW
+__global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_bwd_mma_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ mask, const float* __restrict__ G,
+    const float* __restrict__ probs, const float* __restrict__ g_extra, float* __restrict__ dmask,
+    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co, int TH, int tiles_x, int n_tiles,
+    int tiles_per_cta) {
+    constexpr int KP = 8 * NT;
+    extern __shared__ float4 smem4[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>(smem4);
+    const BwdMmaSmem L = bwd_mma_smem_layout(KP, K, Co, TH);
+    const int KPp = L.KPp;
+    float* sGT = reinterpret_cast<float*>(sm + L.off_G);     // [9][Co][KPp]: G transposed (part index fastest)
+    float* sdG = reinterpret_cast<float*>(sm + L.off_dG);    // [9][K][Co]
+    float* sdb = reinterpret_cast<float*>(sm + L.off_db);    // [9 warps][Co]
+    float* sg = reinterpret_cast<float*>(sm + L.off_g);      // [(TH+2)][34][Co+4]
+    int2* sList = reinterpret_cast<int2*>(sm + L.off_list);
+    int2* sTmp = reinterpret_cast<int2*>(sm + L.off_tmp);
+    int* sDense = reinterpret_cast<int*>(sm + L.off_dense);
+    int* sCnt = reinterpret_cast<int*>(sm + L.off_cnt);
+    int* sBase = reinterpret_cast<int*>(sm + L.off_base);
+    int* sTot = sBase + K + 1;
+
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int CoP = Co + 4, Co4 = Co >> 2, TWp = IC_TW + 2;
+    const int npx = TH * IC_TW, nch = npx >> 5;
+    const size_t img = (size_t)b * H * W;
+
+    for (int i = tid; i < 9 * KP * Co; i += IC_BWD_THREADS) {  // o fastest: coalesced global reads
+        const int o = i % Co, k = (i / Co) % KP, t = i / (Co * KP);
+        const float v = k < K ? __ldg(G + (((size_t)b * 9 + t) * K + k) * Co + o) : 0.f;
+        sGT[(t * Co + o) * KPp + k] = v;
+    }
+    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) sdG[i] = 0.f;
+    for (int i = tid; i < 9 * Co; i += IC_BWD_THREADS) sdb[i] = 0.f;
+
+    // dG phase lane roles
+    const int lps_shift = 31 - __clz(Co4);       // Co4 is a power of two
+    const int slot = lane >> lps_shift, o4l = lane & (Co4 - 1), nslots = 32 >> lps_shift;
+    constexpr int mtw = MTW;                     // m-tiles per warp (warps 0..7): TH*2 m-tiles / 8
+
+    const int t_beg = blockIdx.x * tiles_per_cta;
+    const int t_end = min(n_tiles, t_beg + tiles_per_cta);
+    for (int tile = t_beg; tile < t_end; ++tile) {
+        const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * IC_TW;
+        __syncthreads();
+        for (int i = tid; i < (TH + 2) * TWp * Co4; i += IC_BWD_THREADS) {
+            const int px = i / Co4, o4 = i - px * Co4;
+            const int r = px / TWp, c = px - r * TWp;
+            const int y = y0 - 1 + r, x = x0 - 1 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = ld4_stream(g_out + ((img + (size_t)y * W + x) * Co + 4 * o4));
+            st4(sg + px * CoP + 4 * o4, v);
+        }
+        for (int i = tid; i < nch * (K + 1); i += IC_BWD_THREADS) sCnt[i] = 0;
+        __syncthreads();
+        for (int ch = warp; ch < nch; ch += IC_BWD_THREADS / 32) {
+            const int i = ch * 32 + lane;
+            const int y = y0 + (i >> 5), x = x0 + (i & 31);
+            int2 e = make_int2(-2, 0);
+            if (y < H && x < W) e = compact_pixel(mask + (img + (size_t)y * W + x) * K, K);
+            const unsigned peers = __match_any_sync(0xffffffffu, e.x);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0 && e.x >= -1) sCnt[ch * (K + 1) + (e.x >= 0 ? e.x : K)] = __popc(peers);
+            sTmp[i] = make_int2((e.x & 0xff) | (rank << 8), e.y);
+        }
+        __syncthreads();
+        if (tid <= K) {
+            int run = 0;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int c = sCnt[ch * (K + 1) + tid];
+                sCnt[ch * (K + 1) + tid] = run;
+                run += c;
+            }
+            sTot[tid] = run;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int k = 0; k < K; ++k) {
+                sBase[k] = run;
+                run += sTot[k];
+            }
+            sBase[K] = run;
+        }
+        __syncthreads();
+        for (int i = tid; i < npx; i += IC_BWD_THREADS) {
+            const int2 e = sTmp[i];
+            const int lab = (int)(signed char)(e.x & 0xff), rank = e.x >> 8, ch = i >> 5;
+            if (lab >= 0)
+                sList[sBase[lab] + sCnt[ch * (K + 1) + lab] + rank] = make_int2(i, e.y);
+            else if (lab == -1)
+                sDense[sCnt[ch * (K + 1) + K] + rank] = i;
+        }
+        __syncthreads();
+
+        // (3) dmask on the tensor cores: warp w < 8 owns m-tiles mt = 0..mtw-1: tile row w*mtw/2 + mt/2, x half mt&1
+        if (warp < 8) {
+            float acc[MTW][NT][4];   // accumulators start from g_extra: its loads fly during the MMA loop
+            float pr[MTW][NT][4];    // probabilities of the same elements (0 if unused / outside)
+            const int mt0 = warp * mtw;  // global m-tile index = mt0 + mt: row (mt0+mt)>>1, xbase ((mt0+mt)&1)*16
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                const int m = mt0 + mt;
+                const int y = y0 + (m >> 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int x = x0 + (m & 1) * 16 + gid + 8 * h;
+                    const bool in = y < H && x < W;
+                    const size_t base = (img + (size_t)y * W + x) * K;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int k = nt * 8 + 2 * tig + j;
+                            const bool ok = in && k < K;
+                            acc[mt][nt][2 * h + j] = (ok && g_extra != nullptr) ? __ldg(g_extra + base + k) : 0.f;
+                            pr[mt][nt][2 * h + j] = (ok && probs != nullptr) ? __ldg(probs + base + k) : 0.f;
+                        }
+                }
+            }
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t - 3 * dy;
+                for (int os = 0; os < Co; os += 8) {
+                    unsigned bh[NT][2], bl[NT][2];
+                    const float* gh = sGT + (t * Co + os + tig) * KPp + gid;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        split_tf32(gh[nt * 8], bh[nt][0], bl[nt][0]);
+                        split_tf32(gh[4 * KPp + nt * 8], bh[nt][1], bl[nt][1]);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MTW; ++mt) {
+                        {
+                            const int m = mt0 + mt;
+                            const int r = m >> 1, xb = (m & 1) * 16;
+                            const float* a = sg + ((r + 2 - dy) * TWp + xb + gid + 2 - dx) * CoP + os + tig;
+                            unsigned ah[4], al[4];
+                            split_tf32(a[0], ah[0], al[0]);
+                            split_tf32(a[8 * CoP], ah[1], al[1]);
+                            split_tf32(a[4], ah[2], al[2]);
+                            split_tf32(a[8 * CoP + 4], ah[3], al[3]);
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) {
+                                mma_tf32(acc[mt][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+                                mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+                                mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+                            }
+                        }
+                    }
+                }
+            }
+            // epilogue: thread holds, per m-tile and pixel half h (rows gid, gid+8), parts nt*8 + 2*tig + {0,1}
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                const int m = mt0 + mt;
+                const int y = y0 + (m >> 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int x = x0 + (m & 1) * 16 + gid + 8 * h;
+                    const bool in = y < H && x < W;
+                    const size_t base = (img + (size_t)y * W + x) * K;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dot = fmaf(acc[mt][nt][2 * h + j], pr[mt][nt][2 * h + j], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const int k = nt * 8 + 2 * tig;
+                        float v0 = acc[mt][nt][2 * h], v1 = acc[mt][nt][2 * h + 1];
+                        if (probs != nullptr) {
+                            v0 = pr[mt][nt][2 * h] * (v0 - dot);
+                            v1 = pr[mt][nt][2 * h + 1] * (v1 - dot);
+                        }
+                        if (in) {
+                            if ((K & 1) == 0) {
+                                if (k < K) __stcs(reinterpret_cast<float2*>(dmask + base + k), make_float2(v0, v1));
+                            } else {
+                                if (k < K) dmask[base + k] = v0;
+                                if (k + 1 < K) dmask[base + k + 1] = v1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // (4) dG: unit u = t*K + k owned by warp u % 9; lane = (list slot, 4 channels)
+        // (warp + 9*i) enumerates the units; t and k advance without a division: 9 = q9*K + r9
+        const int q9 = 9 / K, r9 = 9 - q9 * K;
+        int ut = warp / K, uk = warp - ut * K;
+        const int nd = sTot[K];
+        for (int u = warp; u < 9 * K; u += IC_BWD_THREADS / 32) {
+            const int t = ut, k = uk;
+            ut += q9; uk += r9;
+            if (uk >= K) { uk -= K; ++ut; }
+            const int dy = t / 3, dx = t - 3 * dy;
+            const float* gt = sg + ((2 - dy) * TWp + 2 - dx) * CoP + 4 * o4l;
+            const int beg = sBase[k], end = sBase[k + 1];
+            if (beg == end && nd == 0) continue;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = beg + slot;
+            for (; j + nslots < end; j += 2 * nslots) {
+                const int2 e = sList[j], e2 = sList[j + nslots];
+                const float v = __int_as_float(e.y), v2 = __int_as_float(e2.y);
+                const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
+                const float4 g2 = *reinterpret_cast<const float4*>(gt + ((e2.x >> 5) * TWp + (e2.x & 31)) * CoP);
+                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                a2.x = fmaf(v2, g2.x, a2.x); a2.y = fmaf(v2, g2.y, a2.y); a2.z = fmaf(v2, g2.z, a2.z); a2.w = fmaf(v2, g2.w, a2.w);
+            }
+            if (j < end) {
+                const int2 e = sList[j];
+                const float v = __int_as_float(e.y);
+                const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
+                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+            }
+            a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+            for (int j = slot; j < nd; j += nslots) {  // pixels with several non-zeros (exact ties, soft masks)
+                const int i = sDense[j];
+                const float v = __ldg(mask + (img + (size_t)(y0 + (i >> 5)) * W + (x0 + (i & 31))) * K + k);
+                const float4 g = *reinterpret_cast<const float4*>(gt + ((i >> 5) * TWp + (i & 31)) * CoP);
+                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+            }
+            for (int m = Co4; m < 32; m <<= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, m);
+                a.y += __shfl_xor_sync(0xffffffffu, a.y, m);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, m);
+                a.w += __shfl_xor_sync(0xffffffffu, a.w, m);
+            }
+            if (slot == 0) {
+                float4* dst = reinterpret_cast<float4*>(sdG + (t * K + k) * Co + 4 * o4l);
+                float4 c = *dst;
+                c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w;
+                *dst = c;
+            }
+        }
+        // db: column sums of the tile interior (zero outside the image): warp w sums rows w, w+9, ...
+        for (int oc = 0; oc < Co; oc += 32) {
+            const int o = oc + lane;
+            if (o < Co) {
+                float s = 0.f;
+                for (int ty = warp; ty < TH; ty += IC_BWD_THREADS / 32) {
+                    const float* row = sg + ((ty + 1) * TWp + 1) * CoP + o;
+                    for (int tx = 0; tx < IC_TW; ++tx) s += row[tx * CoP];
+                }
+                sdb[warp * Co + o] += s;
+            }
+        }
+    }
+    __syncthreads();
+    const size_t slot_ws = (size_t)b * gridDim.x + blockIdx.x;
+    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) ws_dG[slot_ws * 9 * K * Co + i] = sdG[i];
+    for (int o = tid; o < Co; o += IC_BWD_THREADS) {
+        float s = 0.f;
+        for (int w = 0; w < IC_BWD_THREADS / 32; ++w) s += sdb[w * Co + o];
+        ws_db[slot_ws * Co + o] = s;
+    }
+}
+
 // dG[b,i] = sum over the sample's splits (ascending); db[o] = sum over all (b, split) slots (ascending)
 __global__ void inject_conv_bwd_finalize_kernel(const float* __restrict__ ws_dG, const float* __restrict__ ws_db,
                                                 float* __restrict__ dG, float* __restrict__ db, int B, int splits,
@@ -455,25 +801,43 @@ int fwd_splits(int B, int H) {  // ~8 CTAs of 256 threads per SM
     return (int)want;
 }
 
-int bwd_tile_rows(int KP, int K, int Co) {
+bool bwd_use_mma(int Co) { return Co >= 8 && (Co & (Co - 1)) == 0; }
+int bwd_kp(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : 32; }
+int bwd_smem_bytes(bool mma, int KP, int K, int Co, int th) {
+    return mma ? bwd_mma_smem_layout(KP, K, Co, th).total : bwd_smem_layout(KP, K, Co, th).total;
+}
+int bwd_tile_rows(bool mma, int KP, int K, int Co) {
+    if (mma) {  // prefer two CTAs per SM (8-row tiles), then the largest tile that fits alone
+        if (bwd_smem_bytes(true, KP, K, Co, 8) <= IC_SMEM_HALF) return 8;
+        if (bwd_smem_bytes(true, KP, K, Co, 4) <= IC_SMEM_HALF) return 4;
+        for (int th = 8; th >= 4; th >>= 1)
+            if (bwd_smem_bytes(true, KP, K, Co, th) <= IC_SMEM_BUDGET) return th;
+        return 0;
+    }
     for (int th = 16; th >= 4; th >>= 1)
-        if (bwd_smem_layout(KP, K, Co, th).total <= IC_SMEM_BUDGET) return th;
+        if (bwd_smem_bytes(false, KP, K, Co, th) <= IC_SMEM_BUDGET) return th;
     return 0;
 }
-int bwd_kp(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : 32; }
 
 struct BwdPlan {
-    int KP, TH, tiles_x, tiles_y, n_tiles, splits, tiles_per_cta;
+    bool mma;
+    int KP, TH, tiles_x, tiles_y, n_tiles, splits, tiles_per_cta, smem;
 };
 BwdPlan bwd_plan(int B, int H, int W, int K, int Co) {
     BwdPlan p;
     p.KP = bwd_kp(K);
-    p.TH = bwd_tile_rows(p.KP, K, Co);
+    p.mma = bwd_use_mma(Co);
+    p.TH = bwd_tile_rows(p.mma, p.KP, K, Co);
+    if (p.TH == 0 && p.mma) {  // the pre-split table does not fit: CUDA-core variant
+        p.mma = false;
+        p.TH = bwd_tile_rows(false, p.KP, K, Co);
+    }
     if (p.TH == 0) { p.splits = 0; return p; }
+    p.smem = bwd_smem_bytes(p.mma, p.KP, K, Co, p.TH);
     p.tiles_x = (int)cdiv(W, IC_TW);
     p.tiles_y = (int)cdiv(H, p.TH);
     p.n_tiles = p.tiles_x * p.tiles_y;
-    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);  // one CTA per SM resident; several waves for balance
+    long long want = cdiv(16ll * NUM_SMS, B > 0 ? B : 1);  // one or two CTAs per SM resident; several waves for balance
     if (want < 1) want = 1;
     if (want > p.n_tiles) want = p.n_tiles;
     p.tiles_per_cta = (int)cdiv(p.n_tiles, want);
@@ -485,9 +849,21 @@ template <int KP>
 int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const float* G, const float* probs,
                const float* g_extra, float* dmask, float* ws_dG, float* ws_db, int B, int H, int W, int K, int Co,
                cudaStream_t st) {
-    const int smem = bwd_smem_layout(KP, K, Co, p.TH).total;
-    UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    inject_conv_bwd_kernel<KP><<<dim3(p.splits, B), IC_BWD_THREADS, smem, st>>>(
+    if (p.mma) {
+#define UPS_IC_MMA(MTW)                                                                                                   \
+    do {                                                                                                                  \
+        UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_mma_kernel<KP / 8, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      p.smem));                                                                           \
+        inject_conv_bwd_mma_kernel<KP / 8, MTW><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(                       \
+            g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.TH, p.tiles_x, p.n_tiles, p.tiles_per_cta); \
+    } while (0)
+        if (p.TH == 8) UPS_IC_MMA(2);
+        else UPS_IC_MMA(1);
+#undef UPS_IC_MMA
+        return after_launch("inject_conv_bwd_mma_kernel");
+    }
+    UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));
+    inject_conv_bwd_kernel<KP><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(
         g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.TH, p.tiles_x, p.n_tiles, p.tiles_per_cta);
     return after_launch("inject_conv_bwd_kernel");
 }
@@ -517,19 +893,21 @@ extern "C" int ups_inject_conv_table_fwd(const float* feat, const float* V, floa
 extern "C" int ups_inject_conv_table_bwd(const float* dG, const float* feat, const float* V, float* dfeat, float* dV,
                                          int B, int K, int F, int Co, void* stream) {
     UPS_REQUIRE(dG && feat && V, "inject_conv_table_bwd: null pointer");
-    UPS_REQUIRE(B >= 0 && K >= 1 && K <= 32 && F >= 1 && Co >= 1, "inject_conv_table_bwd: bad sizes");
+    UPS_REQUIRE(B >= 0 && K >= 1 && K <= 32 && F >= 1 && Co >= 4 && Co % 4 == 0, "inject_conv_table_bwd: bad sizes");
+    UPS_REQUIRE(aligned16(dG) && aligned16(V), "inject_conv_table_bwd: dG and V must be 16-byte aligned");
     const size_t smem = (size_t)9 * K * Co * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "inject_conv_table_bwd: 9*K*Co=%d too large", 9 * K * Co);
     cudaStream_t st = as_stream(stream);
     if (dfeat != nullptr && B > 0) {
         UPS_CUDA(cudaFuncSetAttribute(inject_conv_table_bwd_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        inject_conv_table_bwd_feat_kernel<<<B, 256, smem, st>>>(dG, V, dfeat, K, F, Co);
+        const int parts = (int)cdiv((long long)K * F, 256) < 4 ? (int)cdiv((long long)K * F, 256) : 4;
+        inject_conv_table_bwd_feat_kernel<<<dim3(B, parts), 256, smem, st>>>(dG, V, dfeat, K, F, Co);
         if (int rc = after_launch("inject_conv_table_bwd_feat_kernel")) return rc;
     }
     if (dV != nullptr) {
-        inject_conv_table_bwd_filter_kernel<<<dim3((unsigned)cdiv((long long)(F + K) * Co, 128), 9), 128, 0, st>>>(
-            dG, feat, dV, B, K, F, Co);
+        inject_conv_table_bwd_filter_kernel<<<dim3((unsigned)cdiv(F + K, 4), 9), 256, 32 * Co * sizeof(float), st>>>(dG, feat, dV, B,
+                                                                                                                        K, F, Co);
         if (int rc = after_launch("inject_conv_table_bwd_filter_kernel")) return rc;
     }
     return UPS_OK;
@@ -539,9 +917,9 @@ extern "C" int ups_inject_conv_fwd(const float* mask, const float* G, const floa
                                    int K, int Co, void* stream) {
     UPS_REQUIRE(mask && G && bias && out, "inject_conv_fwd: null pointer");
     if (int rc = check_dims("inject_conv_fwd", B, H, W, K, Co)) return rc;
-    UPS_REQUIRE(aligned16(mask) && aligned16(G), "inject_conv_fwd: mask and G must be 16-byte aligned");
+    UPS_REQUIRE(aligned16(mask) && aligned16(G) && aligned16(out), "inject_conv_fwd: mask, G and out must be 16-byte aligned");
     if (B == 0) return UPS_OK;
-    const size_t smem = (size_t)9 * K * Co * sizeof(float) + (size_t)(IC_FWD_ROWS + 2) * (W + 2) * sizeof(int2);
+    const size_t smem = (size_t)(9 * K * Co + Co) * sizeof(float) + (size_t)(IC_FWD_ROWS + 2) * (W + 2) * sizeof(int2);
     UPS_REQUIRE(smem <= (size_t)IC_SMEM_BUDGET, "inject_conv_fwd: K=%d Co=%d W=%d needs %zu bytes of shared memory", K, Co,
                 W, smem);
     const int splits = fwd_splits(B, H);
@@ -549,16 +927,8 @@ extern "C" int ups_inject_conv_fwd(const float* mask, const float* G, const floa
     const int spc = (int)cdiv(n_strips, splits);
     const dim3 grid((unsigned)cdiv(n_strips, spc), B);
     cudaStream_t st = as_stream(stream);
-#define UPS_IC_FWD(CCH)                                                                                               \
-    do {                                                                                                              \
-        UPS_CUDA(cudaFuncSetAttribute(inject_conv_fwd_kernel<CCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                      (int)smem));                                                                    \
-        inject_conv_fwd_kernel<CCH><<<grid, IC_FWD_THREADS, smem, st>>>(mask, G, bias, out, H, W, K, Co, spc);        \
-    } while (0)
-    if (Co <= 32) UPS_IC_FWD(1);
-    else if (Co <= 64) UPS_IC_FWD(2);
-    else UPS_IC_FWD(4);
-#undef UPS_IC_FWD
+    UPS_CUDA(cudaFuncSetAttribute(inject_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    inject_conv_fwd_kernel<<<grid, IC_FWD_THREADS, smem, st>>>(mask, G, bias, out, H, W, K, Co, spc);
     return after_launch("inject_conv_fwd_kernel");
 }
 

@@ -17,40 +17,48 @@
 namespace ups {
 namespace {
 
-constexpr int PC_THREADS = 256;  // 8 warps = 8 rows of a strip; lane = output channel
+constexpr int PC_THREADS = 256;
 constexpr int PC_ROWS = 8;
 
-// grid (splits, B); a CTA walks `strips_per_cta` strips of 8 rows x W of one sample.
-template <int CCH>
+__device__ __forceinline__ float4 dot3(float4 e, float4 v0, float4 v1, float4 v2) {
+    return make_float4(fmaf(e.z, v2.x, fmaf(e.y, v1.x, __fmul_rn(e.x, v0.x))), fmaf(e.z, v2.y, fmaf(e.y, v1.y, __fmul_rn(e.x, v0.y))),
+                       fmaf(e.z, v2.z, fmaf(e.y, v1.z, __fmul_rn(e.x, v0.z))), fmaf(e.z, v2.w, fmaf(e.y, v1.w, __fmul_rn(e.x, v0.w))));
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// grid (splits, B); a CTA walks `strips_per_cta` strips of 8 rows x W of one sample.  The strip's pixels (1-pixel
+// halo) are staged as (c0*m, c1*m, c2*m, label); then one thread per (pixel, 4 output channels): the 9 tap
+// contributions w_t = part_pixel . V[t], the K-|labels| planes that only see the bias get the bias, and each
+// distinct label among the 9 taps gets bias + the sum of its taps.  Everything is per-thread predication; a
+// pixel whose neighbourhood holds a several-non-zero mask pixel takes the dense loop over k.
 __global__ void __launch_bounds__(PC_THREADS) parts_conv_fwd_kernel(const float* __restrict__ img,
                                                                     const float* __restrict__ mask,
                                                                     const float* __restrict__ V,
                                                                     const float* __restrict__ bias,
                                                                     float* __restrict__ out, int B, int H, int W, int K,
                                                                     int Co, int strips_per_cta) {
-    extern __shared__ float4 sPx[];  // [(8+2)][W+2] : (c0, c1, c2, label) — premultiplied by the mask value if label >= 0
-    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float Vr[9][3][CCH], bo[CCH];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) {
-        const int o = lane + 32 * c;
-        bo[c] = o < Co ? __ldg(bias + o) : 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) Vr[t][ch][c] = o < Co ? __ldg(V + (t * 3 + ch) * Co + o) : 0.f;
-    }
+    extern __shared__ float4 smem4[];
+    float* sV = reinterpret_cast<float*>(smem4);  // [9][3][Co]
+    float* sB = sV + 27 * Co;                     // [Co]
+    float4* sPx = reinterpret_cast<float4*>(sB + Co);  // [(8+2)][W+2] : (c0, c1, c2, label), premultiplied if label >= 0
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int Co4 = Co >> 2;
+    for (int i = tid; i < 27 * Co; i += PC_THREADS) sV[i] = __ldg(V + i);
+    for (int i = tid; i < Co; i += PC_THREADS) sB[i] = __ldg(bias + i);
     const int n_strips = (H + PC_ROWS - 1) / PC_ROWS;
     const int s_beg = blockIdx.x * strips_per_cta;
     const int s_end = min(n_strips, s_beg + strips_per_cta);
     const int Wp = W + 2;
     const size_t P = (size_t)H * W;
+    const size_t plane = (size_t)B * P * Co;  // stride between part planes k -> k+1
     const float* mb = mask + (size_t)b * P * K;
     const float* ib = img + (size_t)b * P * 3;
+    float* ob = out + (size_t)b * P * Co;
     for (int s = s_beg; s < s_end; ++s) {
         const int y0 = s * PC_ROWS;
+        const int rows = min(PC_ROWS, H - y0);
         __syncthreads();
-        for (int i = tid; i < (PC_ROWS + 2) * Wp; i += PC_THREADS) {
+        for (int i = tid; i < (rows + 2) * Wp; i += PC_THREADS) {
             const int r = i / Wp, c = i - r * Wp;
             const int y = y0 - 1 + r, x = c - 1;
             float4 e = make_float4(0.f, 0.f, 0.f, __int_as_float(-2));
@@ -67,63 +75,72 @@ __global__ void __launch_bounds__(PC_THREADS) parts_conv_fwd_kernel(const float*
                     }
                 }
                 if (nz > 1) { lab = -1; val = 1.f; }
-                if (nz > 0)  // mask_parts: fl(image * mask) per channel (dense pixels keep the raw image)
+                if (nz > 0)  // mask_parts: fl(image * mask) per channel (several-non-zero pixels keep the raw image)
                     e = make_float4(__fmul_rn(__ldg(ib + q * 3 + 0), val), __fmul_rn(__ldg(ib + q * 3 + 1), val),
                                     __fmul_rn(__ldg(ib + q * 3 + 2), val), __int_as_float(lab));
             }
             sPx[i] = e;
         }
         __syncthreads();
-        const int y = y0 + warp;
-        if (y >= H) continue;
-        for (int x = 0; x < W; ++x) {
+        for (int idx = tid; idx < rows * W * Co4; idx += PC_THREADS) {
+            const int px = idx / Co4, o = 4 * (idx - px * Co4);
+            const int r = px / W, x = px - r * W;
+            const float4 bo = *reinterpret_cast<const float4*>(sB + o);
+            const float4* e0 = sPx + r * Wp + x;
             int labs[9];
-            float w[9][CCH];
+            float4 w[9];
             unsigned present = 0;
-            bool any_dense = false;
+            bool dense = false;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int dy = t / 3, dx = t - 3 * dy;
-                const float4 e = sPx[(warp + dy) * Wp + x + dx];
+                const float4 e = e0[dy * Wp + dx];
                 labs[t] = __float_as_int(e.w);
-#pragma unroll
-                for (int c = 0; c < CCH; ++c)
-                    w[t][c] = fmaf(e.z, Vr[t][2][c], fmaf(e.y, Vr[t][1][c], __fmul_rn(e.x, Vr[t][0][c])));
+                const float* v = sV + t * 3 * Co + o;
+                w[t] = dot3(e, *reinterpret_cast<const float4*>(v), *reinterpret_cast<const float4*>(v + Co),
+                            *reinterpret_cast<const float4*>(v + 2 * Co));
                 if (labs[t] >= 0) present |= 1u << labs[t];
-                any_dense |= labs[t] == -1;
+                dense |= labs[t] == -1;
             }
-            const size_t p = (size_t)y * W + x;
-            for (int k = 0; k < K; ++k) {
-                float acc[CCH];
+            float* op = ob + ((size_t)(y0 + r) * W + x) * Co + o;
+            if (!dense) {
+                for (int k = 0; k < K; ++k)
+                    if (!((present >> k) & 1u)) st4_stream(op + k * plane, bo);
+                unsigned seen = 0;
 #pragma unroll
-                for (int c = 0; c < CCH; ++c) acc[c] = bo[c];
-                if ((present >> k) & 1u) {
+                for (int t = 0; t < 9; ++t) {
+                    const int lab = labs[t];
+                    if (lab >= 0 && !((seen >> lab) & 1u)) {
+                        seen |= 1u << lab;
+                        float4 sacc = add4(bo, w[t]);
 #pragma unroll
-                    for (int t = 0; t < 9; ++t)
-                        if (labs[t] == k) {
-#pragma unroll
-                            for (int c = 0; c < CCH; ++c) acc[c] += w[t][c];
-                        }
+                        for (int u = t + 1; u < 9; ++u)
+                            if (labs[u] == lab) sacc = add4(sacc, w[u]);
+                        st4_stream(op + lab * plane, sacc);
+                    }
                 }
-                if (any_dense) {
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    float4 sacc = bo;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t)
-                        if (labs[t] == -1) {
+                    for (int t = 0; t < 9; ++t) {
+                        if (labs[t] == k) {
+                            sacc = add4(sacc, w[t]);
+                        } else if (labs[t] == -1) {
                             const int dy = t / 3, dx = t - 3 * dy;
-                            const float mv = __ldg(mb + ((size_t)(y + dy - 1) * W + (x + dx - 1)) * K + k);
+                            const float mv = __ldg(mb + ((size_t)(y0 + r + dy - 1) * W + (x + dx - 1)) * K + k);
                             if (mv != 0.f) {
-                                const float4 e = sPx[(warp + dy) * Wp + x + dx];  // raw image
-                                const float p0 = __fmul_rn(e.x, mv), p1 = __fmul_rn(e.y, mv), p2 = __fmul_rn(e.z, mv);
-#pragma unroll
-                                for (int c = 0; c < CCH; ++c)
-                                    acc[c] += fmaf(p2, Vr[t][2][c], fmaf(p1, Vr[t][1][c], __fmul_rn(p0, Vr[t][0][c])));
+                                float4 e = e0[dy * Wp + dx];  // raw image
+                                e.x = __fmul_rn(e.x, mv); e.y = __fmul_rn(e.y, mv); e.z = __fmul_rn(e.z, mv);
+                                const float* v = sV + t * 3 * Co + o;
+                                sacc = add4(sacc, dot3(e, *reinterpret_cast<const float4*>(v),
+                                                       *reinterpret_cast<const float4*>(v + Co),
+                                                       *reinterpret_cast<const float4*>(v + 2 * Co)));
                             }
                         }
+                    }
+                    st4_stream(op + k * plane, sacc);
                 }
-                float* orow = out + (((size_t)k * B + b) * P + p) * Co;
-#pragma unroll
-                for (int c = 0; c < CCH; ++c)
-                    if (lane + 32 * c < Co) __stcs(orow + lane + 32 * c, acc[c]);
             }
         }
     }
@@ -140,11 +157,12 @@ extern "C" int ups_parts_conv_fwd(const float* img, const float* mask, const flo
     UPS_REQUIRE(B >= 0 && H > 0 && W > 0, "parts_conv_fwd: bad sizes B=%d H=%d W=%d", B, H, W);
     UPS_REQUIRE(K >= 1 && K <= 32, "parts_conv_fwd: K=%d outside [1,32]", K);
     UPS_REQUIRE(C == 3, "parts_conv_fwd: C=%d (the part images are 3-channel, model.py:316-327)", C);
-    UPS_REQUIRE(Co >= 1 && Co <= 128, "parts_conv_fwd: Co=%d outside [1,128]", Co);
+    UPS_REQUIRE(Co >= 4 && Co <= 128 && Co % 4 == 0, "parts_conv_fwd: Co=%d must be a multiple of 4 in [4,128]", Co);
     UPS_REQUIRE((long long)B * H * W * K < (1ll << 31), "parts_conv_fwd: K*B*H*W >= 2^31");
+    UPS_REQUIRE(aligned16(V) && aligned16(bias) && aligned16(out_pm), "parts_conv_fwd: V, bias, out must be 16-byte aligned");
     if (B == 0) return UPS_OK;
-    const size_t smem = (size_t)(PC_ROWS + 2) * (W + 2) * sizeof(float4);
-    UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_fwd: W=%d needs %zu bytes of shared memory", W, smem);
+    const size_t smem = (size_t)28 * Co * sizeof(float) + (size_t)(PC_ROWS + 2) * (W + 2) * sizeof(float4);
+    UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_fwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
     const int n_strips = (int)cdiv(H, PC_ROWS);
     long long want = cdiv(8ll * NUM_SMS, B);
     if (want < 1) want = 1;
@@ -152,15 +170,7 @@ extern "C" int ups_parts_conv_fwd(const float* img, const float* mask, const flo
     const int spc = (int)cdiv(n_strips, want);
     const dim3 grid((unsigned)cdiv(n_strips, spc), B);
     cudaStream_t st = as_stream(stream);
-#define UPS_PC_FWD(CCH)                                                                                              \
-    do {                                                                                                             \
-        UPS_CUDA(cudaFuncSetAttribute(parts_conv_fwd_kernel<CCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                      (int)smem));                                                                   \
-        parts_conv_fwd_kernel<CCH><<<grid, PC_THREADS, smem, st>>>(img, mask, V, bias, out_pm, B, H, W, K, Co, spc); \
-    } while (0)
-    if (Co <= 32) UPS_PC_FWD(1);
-    else if (Co <= 64) UPS_PC_FWD(2);
-    else UPS_PC_FWD(4);
-#undef UPS_PC_FWD
+    UPS_CUDA(cudaFuncSetAttribute(parts_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    parts_conv_fwd_kernel<<<grid, PC_THREADS, smem, st>>>(img, mask, V, bias, out_pm, B, H, W, K, Co, spc);
     return after_launch("parts_conv_fwd_kernel");
 }
