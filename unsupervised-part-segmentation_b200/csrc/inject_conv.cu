@@ -20,7 +20,7 @@ constexpr int IC_FWD_ROWS = 8;
 constexpr int IC_BWD_THREADS = 288;  // 9 warps: one per filter tap in the dG phase
 constexpr int IC_TW = 32;            // backward tile width (pixels); thread = pixels (x, x+16)
 constexpr int IC_SMEM_BUDGET = 224 * 1024;   // per CTA (227 KB is the hardware limit)
-constexpr int IC_SMEM_HALF = 112 * 1024;     // two CTAs per SM
+constexpr int IC_SMEM_HALF = 112 * 1024 + 512;     // two CTAs per SM
 
 // (label, value) of a mask pixel: label >= 0 one non-zero; -1 several non-zeros; -2 none
 __device__ __forceinline__ int2 compact_pixel(const float* __restrict__ m, int K) {
@@ -460,20 +460,24 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, 1) inject_conv_bwd_kernel(
 // ---- tensor-core variant of the backward (Co in {8,16,32,64,128}) ---------------------------------
 // Same tiling, sort and outputs as inject_conv_bwd_kernel; the dense contraction
 //   dmask[q, k] = sum_{t,o} g_out[q - off_t, o] G[t,k,o]        (M = pixels, N = K, reduction = 9*Co)
-// runs as mma.sync.m16n8k8 TF32 with the 3xTF32 split (a = hi + lo, hi = the 19 bits the tensor core keeps;
-// hi*hi' + lo*hi' + hi*lo' accumulated in fp32: error ~2^-21 per product, inside the 1e-4/1e-5 tolerance).
+// runs as mma.sync.m16n8k8 TF32 with the 3xTF32 split a = hi + lo (hi = the 19 bits the tensor core keeps):
+// hi*hi' + lo*hi' + hi*lo'.  The tensor core adds into its accumulator with truncation, a bias that grows with
+// the length of the accumulation chain (measured: 2.5e-5 after 216 chained MMAs), so the hi*hi' products are
+// chained over at most 4 k-steps from zero and then added to an fp32 running sum by the CUDA cores (round to
+// nearest); the two small terms, 2^-11 of the magnitude, keep one accumulator for the whole reduction.
 // A fragments come straight from the padded g_out tile (row stride Co+4 floats: conflict-free), B fragments from
-// the pre-split table in shared memory.  Warps 0-7 own TH/4 m-tiles (16 pixels of one tile row) each; the dG
-// phase is vectorised: a warp owns a (tap, label) unit, 4 channels per lane, 32/(Co/4) list entries in parallel.
+// the pre-split, XOR-swizzled table in shared memory.  Warps 0-7 own MTW m-tiles (16 pixels of one tile row)
+// each; in the dG phase Co/4 lanes own a (tap, label) unit and walk its label-sorted pixel list, 4 channels per
+// lane, 32/(Co/4) units per warp side by side.
 struct BwdMmaSmem {
-    int off_G, off_dG, off_db, off_g, off_list, off_tmp, off_dense, off_cnt, off_base, total, KPp;
+    int off_Ghi, off_Glo, off_dG, off_db, off_g, off_list, off_tmp, off_dense, off_cnt, off_base, total;
 };
 __host__ __device__ inline BwdMmaSmem bwd_mma_smem_layout(int KP, int K, int Co, int TH) {
     BwdMmaSmem s;
     const int npx = TH * IC_TW, nch = npx / 32;
-    s.KPp = (KP % 32 == 8 || KP % 32 == 24) ? KP : KP + 8;  // B-fragment loads (4 o-rows x 8 k) hit 32 distinct banks
     int o = 0;
-    s.off_G = o;     o += 4 * 9 * Co * s.KPp;
+    s.off_Ghi = o;   o += 4 * 9 * Co * KP;
+    s.off_Glo = o;   o += 4 * 9 * Co * KP;
     s.off_dG = o;    o += 4 * 9 * K * Co;
     s.off_db = o;    o += 4 * 9 * Co;
     o = (o + 15) & ~15;
@@ -494,26 +498,30 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], unsigned a0, unsigned a1
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// a = hi + lo with both parts rounded to nearest TF32 (truncation would bias the dropped bits and the bias adds up
-// linearly over the 9*Co products)
+// a = hi + lo exactly; hi carries the bits the tensor core reads, lo the remaining 13 (the core keeps its top 11)
 __device__ __forceinline__ void split_tf32(float a, unsigned& hi, unsigned& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(a));
-    const float r = __fsub_rn(a, __uint_as_float(hi));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(a) & 0xffffe000u;
+    lo = __float_as_uint(__fsub_rn(a, __uint_as_float(hi)));
+}
+// column swizzle of the [o][KP] table rows so that a B-fragment load (o = os+tig(+4), k = nt*8+gid) touches 32 banks
+template <int NT>
+__device__ __forceinline__ int b_swizzle(int o) {
+    return NT == 2 ? 8 * ((o >> 1) & 1) : NT == 4 ? 8 * (o & 3) : 0;
 }
 
 template <int NT, int MTW>  // N tiles of 8 parts: KP = 8*NT >= K;  m-tiles per warp: tile rows TH = 4*MTW
 __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_bwd_mma_kernel(
     const float* __restrict__ g_out, const float* __restrict__ mask, const float* __restrict__ G,
     const float* __restrict__ probs, const float* __restrict__ g_extra, float* __restrict__ dmask,
-    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co, int TH, int tiles_x, int n_tiles,
+    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co, int tiles_x, int n_tiles,
     int tiles_per_cta) {
-    constexpr int KP = 8 * NT;
+    constexpr int KP = 8 * NT, TH = 4 * MTW;
+    constexpr int TWp = IC_TW + 2, npx = TH * IC_TW, nch = npx >> 5;
     extern __shared__ float4 smem4[];
     unsigned char* sm = reinterpret_cast<unsigned char*>(smem4);
     const BwdMmaSmem L = bwd_mma_smem_layout(KP, K, Co, TH);
-    const int KPp = L.KPp;
-    float* sGT = reinterpret_cast<float*>(sm + L.off_G);     // [9][Co][KPp]: G transposed (part index fastest)
+    float* sGhi = reinterpret_cast<float*>(sm + L.off_Ghi);  // [9][Co][KP] swizzled: the TF32 part of G
+    float* sGlo = reinterpret_cast<float*>(sm + L.off_Glo);  // [9][Co][KP] swizzled: G - hi
     float* sdG = reinterpret_cast<float*>(sm + L.off_dG);    // [9][K][Co]
     float* sdb = reinterpret_cast<float*>(sm + L.off_db);    // [9 warps][Co]
     float* sg = reinterpret_cast<float*>(sm + L.off_g);      // [(TH+2)][34][Co+4]
@@ -526,35 +534,41 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
 
     const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int CoP = Co + 4, Co4 = Co >> 2, TWp = IC_TW + 2;
-    const int npx = TH * IC_TW, nch = npx >> 5;
+    const int CoP = Co + 4, Co4 = Co >> 2;
     const size_t img = (size_t)b * H * W;
 
     for (int i = tid; i < 9 * KP * Co; i += IC_BWD_THREADS) {  // o fastest: coalesced global reads
-        const int o = i % Co, k = (i / Co) % KP, t = i / (Co * KP);
+        const int o = i % Co, tk = i / Co, k = tk % KP, t = tk / KP;
         const float v = k < K ? __ldg(G + (((size_t)b * 9 + t) * K + k) * Co + o) : 0.f;
-        sGT[(t * Co + o) * KPp + k] = v;
+        unsigned hi, lo;
+        split_tf32(v, hi, lo);
+        const int at = (t * Co + o) * KP + (k ^ b_swizzle<NT>(o));
+        sGhi[at] = __uint_as_float(hi);
+        sGlo[at] = __uint_as_float(lo);
     }
     for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) sdG[i] = 0.f;
     for (int i = tid; i < 9 * Co; i += IC_BWD_THREADS) sdb[i] = 0.f;
 
-    // dG phase lane roles
-    const int lps_shift = 31 - __clz(Co4);       // Co4 is a power of two
-    const int slot = lane >> lps_shift, o4l = lane & (Co4 - 1), nslots = 32 >> lps_shift;
-    constexpr int mtw = MTW;                     // m-tiles per warp (warps 0..7): TH*2 m-tiles / 8
+    // tile-load roles: Co4 (a power of two) divides 288, so a thread keeps its channel quad
+    const int ld_o4 = tid & (Co4 - 1), ld_px0 = tid / Co4, ld_step = IC_BWD_THREADS / Co4;
+    // dG roles: Co4 lanes per (tap, label) unit, 32/Co4 units per warp
+    const int lpu_shift = 31 - __clz(Co4);
+    const int usub = lane >> lpu_shift, o4l = lane & (Co4 - 1), upw = 32 >> lpu_shift;
+    int koff[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) koff[nt] = (nt * 8 + gid) ^ b_swizzle<NT>(tig);
 
     const int t_beg = blockIdx.x * tiles_per_cta;
     const int t_end = min(n_tiles, t_beg + tiles_per_cta);
     for (int tile = t_beg; tile < t_end; ++tile) {
         const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * IC_TW;
         __syncthreads();
-        for (int i = tid; i < (TH + 2) * TWp * Co4; i += IC_BWD_THREADS) {
-            const int px = i / Co4, o4 = i - px * Co4;
+        for (int px = ld_px0; px < (TH + 2) * TWp; px += ld_step) {
             const int r = px / TWp, c = px - r * TWp;
             const int y = y0 - 1 + r, x = x0 - 1 + c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < H && x >= 0 && x < W) v = ld4_stream(g_out + ((img + (size_t)y * W + x) * Co + 4 * o4));
-            st4(sg + px * CoP + 4 * o4, v);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = ld4_stream(g_out + ((img + (size_t)y * W + x) * Co + 4 * ld_o4));
+            st4(sg + px * CoP + 4 * ld_o4, v);
         }
         for (int i = tid; i < nch * (K + 1); i += IC_BWD_THREADS) sCnt[i] = 0;
         __syncthreads();
@@ -598,11 +612,11 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
         }
         __syncthreads();
 
-        // (3) dmask on the tensor cores: warp w < 8 owns m-tiles mt = 0..mtw-1: tile row w*mtw/2 + mt/2, x half mt&1
+        // (3) dmask on the tensor cores: warp w < 8 owns m-tiles m = w*MTW + mt: tile row m>>1, x half m&1
         if (warp < 8) {
-            float acc[MTW][NT][4];   // accumulators start from g_extra: its loads fly during the MMA loop
-            float pr[MTW][NT][4];    // probabilities of the same elements (0 if unused / outside)
-            const int mt0 = warp * mtw;  // global m-tile index = mt0 + mt: row (mt0+mt)>>1, xbase ((mt0+mt)&1)*16
+            float run[MTW][NT][4];   // fp32 running sum, starts from g_extra (its loads fly during the MMA loop)
+            float small[MTW][NT][4]; // lo*hi' + hi*lo'
+            const int mt0 = warp * MTW;
 #pragma unroll
             for (int mt = 0; mt < MTW; ++mt) {
                 const int m = mt0 + mt;
@@ -617,25 +631,34 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const int k = nt * 8 + 2 * tig + j;
-                            const bool ok = in && k < K;
-                            acc[mt][nt][2 * h + j] = (ok && g_extra != nullptr) ? __ldg(g_extra + base + k) : 0.f;
-                            pr[mt][nt][2 * h + j] = (ok && probs != nullptr) ? __ldg(probs + base + k) : 0.f;
+                            run[mt][nt][2 * h + j] = (in && k < K && g_extra != nullptr) ? __ldg(g_extra + base + k) : 0.f;
+                            small[mt][nt][2 * h + j] = 0.f;
                         }
                 }
             }
             for (int t = 0; t < 9; ++t) {
                 const int dy = t / 3, dx = t - 3 * dy;
-                for (int os = 0; os < Co; os += 8) {
-                    unsigned bh[NT][2], bl[NT][2];
-                    const float* gh = sGT + (t * Co + os + tig) * KPp + gid;
+                for (int oc = 0; oc < Co; oc += 32) {  // chains of at most 4 k-steps
+                    float main[MTW][NT][4];
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        split_tf32(gh[nt * 8], bh[nt][0], bl[nt][0]);
-                        split_tf32(gh[4 * KPp + nt * 8], bh[nt][1], bl[nt][1]);
-                    }
+                    for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
-                    for (int mt = 0; mt < MTW; ++mt) {
-                        {
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) main[mt][nt][j] = 0.f;
+                    const int oe = min(Co, oc + 32);
+                    for (int os = oc; os < oe; os += 8) {
+                        unsigned bh[NT][2], bl[NT][2];
+                        const int row = (t * Co + os + tig) * KP;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            bh[nt][0] = __float_as_uint(sGhi[row + koff[nt]]);
+                            bh[nt][1] = __float_as_uint(sGhi[row + 4 * KP + koff[nt]]);
+                            bl[nt][0] = __float_as_uint(sGlo[row + koff[nt]]);
+                            bl[nt][1] = __float_as_uint(sGlo[row + 4 * KP + koff[nt]]);
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < MTW; ++mt) {
                             const int m = mt0 + mt;
                             const int r = m >> 1, xb = (m & 1) * 16;
                             const float* a = sg + ((r + 2 - dy) * TWp + xb + gid + 2 - dx) * CoP + os + tig;
@@ -646,12 +669,18 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
                             split_tf32(a[8 * CoP + 4], ah[3], al[3]);
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) {
-                                mma_tf32(acc[mt][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
-                                mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
-                                mma_tf32(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+                                mma_tf32(small[mt][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+                                mma_tf32(small[mt][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+                                mma_tf32(main[mt][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
                             }
                         }
                     }
+#pragma unroll
+                    for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) run[mt][nt][j] += main[mt][nt][j];
                 }
             }
             // epilogue: thread holds, per m-tile and pixel half h (rows gid, gid+8), parts nt*8 + 2*tig + {0,1}
@@ -664,20 +693,26 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
                     const int x = x0 + (m & 1) * 16 + gid + 8 * h;
                     const bool in = y < H && x < W;
                     const size_t base = (img + (size_t)y * W + x) * K;
+                    float d[NT][2], p[NT][2];
                     float dot = 0.f;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) dot = fmaf(acc[mt][nt][2 * h + j], pr[mt][nt][2 * h + j], dot);
+                        for (int j = 0; j < 2; ++j) {
+                            const int k = nt * 8 + 2 * tig + j;
+                            d[nt][j] = run[mt][nt][2 * h + j] + small[mt][nt][2 * h + j];
+                            p[nt][j] = (in && k < K && probs != nullptr) ? __ldg(probs + base + k) : 0.f;
+                            dot = fmaf(d[nt][j], p[nt][j], dot);
+                        }
                     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
                     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         const int k = nt * 8 + 2 * tig;
-                        float v0 = acc[mt][nt][2 * h], v1 = acc[mt][nt][2 * h + 1];
+                        float v0 = d[nt][0], v1 = d[nt][1];
                         if (probs != nullptr) {
-                            v0 = pr[mt][nt][2 * h] * (v0 - dot);
-                            v1 = pr[mt][nt][2 * h + 1] * (v1 - dot);
+                            v0 = p[nt][0] * (v0 - dot);
+                            v1 = p[nt][1] * (v1 - dot);
                         }
                         if (in) {
                             if ((K & 1) == 0) {
@@ -692,53 +727,46 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
             }
         }
 
-        // (4) dG: unit u = t*K + k owned by warp u % 9; lane = (list slot, 4 channels)
-        // (warp + 9*i) enumerates the units; t and k advance without a division: 9 = q9*K + r9
-        const int q9 = 9 / K, r9 = 9 - q9 * K;
-        int ut = warp / K, uk = warp - ut * K;
-        const int nd = sTot[K];
-        for (int u = warp; u < 9 * K; u += IC_BWD_THREADS / 32) {
-            const int t = ut, k = uk;
-            ut += q9; uk += r9;
-            if (uk >= K) { uk -= K; ++ut; }
-            const int dy = t / 3, dx = t - 3 * dy;
-            const float* gt = sg + ((2 - dy) * TWp + 2 - dx) * CoP + 4 * o4l;
-            const int beg = sBase[k], end = sBase[k + 1];
-            if (beg == end && nd == 0) continue;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int j = beg + slot;
-            for (; j + nslots < end; j += 2 * nslots) {
-                const int2 e = sList[j], e2 = sList[j + nslots];
-                const float v = __int_as_float(e.y), v2 = __int_as_float(e2.y);
-                const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
-                const float4 g2 = *reinterpret_cast<const float4*>(gt + ((e2.x >> 5) * TWp + (e2.x & 31)) * CoP);
-                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
-                a2.x = fmaf(v2, g2.x, a2.x); a2.y = fmaf(v2, g2.y, a2.y); a2.z = fmaf(v2, g2.z, a2.z); a2.w = fmaf(v2, g2.w, a2.w);
-            }
-            if (j < end) {
-                const int2 e = sList[j];
-                const float v = __int_as_float(e.y);
-                const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
-                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
-            }
-            a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
-            for (int j = slot; j < nd; j += nslots) {  // pixels with several non-zeros (exact ties, soft masks)
-                const int i = sDense[j];
-                const float v = __ldg(mask + (img + (size_t)(y0 + (i >> 5)) * W + (x0 + (i & 31))) * K + k);
-                const float4 g = *reinterpret_cast<const float4*>(gt + ((i >> 5) * TWp + (i & 31)) * CoP);
-                a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
-            }
-            for (int m = Co4; m < 32; m <<= 1) {
-                a.x += __shfl_xor_sync(0xffffffffu, a.x, m);
-                a.y += __shfl_xor_sync(0xffffffffu, a.y, m);
-                a.z += __shfl_xor_sync(0xffffffffu, a.z, m);
-                a.w += __shfl_xor_sync(0xffffffffu, a.w, m);
-            }
-            if (slot == 0) {
-                float4* dst = reinterpret_cast<float4*>(sdG + (t * K + k) * Co + 4 * o4l);
-                float4 c = *dst;
-                c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w;
-                *dst = c;
+        // (4) dG: unit u = t*K + k; Co4 lanes own a unit and walk its sorted pixel list with two chains
+        {
+            const int nd = sTot[K];
+            for (int u0 = warp * upw; u0 < 9 * K; u0 += (IC_BWD_THREADS / 32) * upw) {
+                const int u = u0 + usub;
+                if (u < 9 * K) {
+                    const int t = u / K, k = u - t * K;
+                    const int dy = t / 3, dx = t - 3 * dy;
+                    const float* gt = sg + ((2 - dy) * TWp + 2 - dx) * CoP + 4 * o4l;
+                    const int beg = sBase[k], end = sBase[k + 1];
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int j = beg;
+                    for (; j + 1 < end; j += 2) {
+                        const int2 e = sList[j], e2 = sList[j + 1];
+                        const float v = __int_as_float(e.y), v2 = __int_as_float(e2.y);
+                        const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
+                        const float4 g2 = *reinterpret_cast<const float4*>(gt + ((e2.x >> 5) * TWp + (e2.x & 31)) * CoP);
+                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                        a2.x = fmaf(v2, g2.x, a2.x); a2.y = fmaf(v2, g2.y, a2.y); a2.z = fmaf(v2, g2.z, a2.z);
+                        a2.w = fmaf(v2, g2.w, a2.w);
+                    }
+                    if (j < end) {
+                        const int2 e = sList[j];
+                        const float v = __int_as_float(e.y);
+                        const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
+                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                    }
+                    for (int jd = 0; jd < nd; ++jd) {  // pixels with several non-zeros (exact ties, soft masks)
+                        const int i = sDense[jd];
+                        const float v = __ldg(mask + (img + (size_t)(y0 + (i >> 5)) * W + (x0 + (i & 31))) * K + k);
+                        const float4 g = *reinterpret_cast<const float4*>(gt + ((i >> 5) * TWp + (i & 31)) * CoP);
+                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                    }
+                    if (beg != end || nd != 0) {
+                        float4* dst = reinterpret_cast<float4*>(sdG + (t * K + k) * Co + 4 * o4l);
+                        float4 c = *dst;
+                        c.x += a.x + a2.x; c.y += a.y + a2.y; c.z += a.z + a2.z; c.w += a.w + a2.w;
+                        *dst = c;
+                    }
+                }
             }
         }
         // db: column sums of the tile interior (zero outside the image): warp w sums rows w, w+9, ...
@@ -748,6 +776,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
                 float s = 0.f;
                 for (int ty = warp; ty < TH; ty += IC_BWD_THREADS / 32) {
                     const float* row = sg + ((ty + 1) * TWp + 1) * CoP + o;
+#pragma unroll 8
                     for (int tx = 0; tx < IC_TW; ++tx) s += row[tx * CoP];
                 }
                 sdb[warp * Co + o] += s;
@@ -807,11 +836,10 @@ int bwd_smem_bytes(bool mma, int KP, int K, int Co, int th) {
     return mma ? bwd_mma_smem_layout(KP, K, Co, th).total : bwd_smem_layout(KP, K, Co, th).total;
 }
 int bwd_tile_rows(bool mma, int KP, int K, int Co) {
-    if (mma) {  // prefer two CTAs per SM (8-row tiles), then the largest tile that fits alone
-        if (bwd_smem_bytes(true, KP, K, Co, 8) <= IC_SMEM_HALF) return 8;
-        if (bwd_smem_bytes(true, KP, K, Co, 4) <= IC_SMEM_HALF) return 4;
-        for (int th = 8; th >= 4; th >>= 1)
-            if (bwd_smem_bytes(true, KP, K, Co, th) <= IC_SMEM_BUDGET) return th;
+    if (mma) {  // two CTAs per SM: 8-row tiles (two m-tiles per warp) up to K = 16, 4-row tiles beyond (registers)
+        const int th = KP <= 16 ? 8 : 4;
+        if (bwd_smem_bytes(true, KP, K, Co, th) <= IC_SMEM_HALF) return th;
+        if (bwd_smem_bytes(true, KP, K, Co, 4) <= IC_SMEM_BUDGET) return 4;
         return 0;
     }
     for (int th = 16; th >= 4; th >>= 1)
@@ -837,7 +865,7 @@ BwdPlan bwd_plan(int B, int H, int W, int K, int Co) {
     p.tiles_x = (int)cdiv(W, IC_TW);
     p.tiles_y = (int)cdiv(H, p.TH);
     p.n_tiles = p.tiles_x * p.tiles_y;
-    long long want = cdiv(16ll * NUM_SMS, B > 0 ? B : 1);  // one or two CTAs per SM resident; several waves for balance
+    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);  // one or two CTAs per SM resident; several waves for balance
     if (want < 1) want = 1;
     if (want > p.n_tiles) want = p.n_tiles;
     p.tiles_per_cta = (int)cdiv(p.n_tiles, want);
@@ -855,7 +883,7 @@ int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const fl
         UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_mma_kernel<KP / 8, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       p.smem));                                                                           \
         inject_conv_bwd_mma_kernel<KP / 8, MTW><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(                       \
-            g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.TH, p.tiles_x, p.n_tiles, p.tiles_per_cta); \
+            g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.tiles_x, p.n_tiles, p.tiles_per_cta);       \
     } while (0)
         if (p.TH == 8) UPS_IC_MMA(2);
         else UPS_IC_MMA(1);
