@@ -509,12 +509,21 @@ __device__ __forceinline__ int b_swizzle(int o) {
     return NT == 2 ? 8 * ((o >> 1) & 1) : NT == 4 ? 8 * (o & 3) : 0;
 }
 
-template <int NT, int MTW>  // N tiles of 8 parts: KP = 8*NT >= K;  m-tiles per warp: tile rows TH = 4*MTW
+// 16-byte global -> shared copy that bypasses registers; n_src = 0 writes zeros (outside the image)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, int n_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(n_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// N tiles of 8 parts: KP = 8*NT >= K;  m-tiles per warp: tile rows TH = 4*MTW;  CO > 0: Co known at compile time
+template <int NT, int MTW, int CO>
 __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_bwd_mma_kernel(
     const float* __restrict__ g_out, const float* __restrict__ mask, const float* __restrict__ G,
     const float* __restrict__ probs, const float* __restrict__ g_extra, float* __restrict__ dmask,
-    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co, int tiles_x, int n_tiles,
+    float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co_rt, int tiles_x, int n_tiles,
     int tiles_per_cta) {
+    const int Co = CO > 0 ? CO : Co_rt;
     constexpr int KP = 8 * NT, TH = 4 * MTW;
     constexpr int TWp = IC_TW + 2, npx = TH * IC_TW, nch = npx >> 5;
     extern __shared__ float4 smem4[];
@@ -563,12 +572,12 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
     for (int tile = t_beg; tile < t_end; ++tile) {
         const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * IC_TW;
         __syncthreads();
-        for (int px = ld_px0; px < (TH + 2) * TWp; px += ld_step) {
+        for (int px = ld_px0; px < (TH + 2) * TWp; px += ld_step) {  // asynchronous: lands during the mask sort
             const int r = px / TWp, c = px - r * TWp;
             const int y = y0 - 1 + r, x = x0 - 1 + c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < H && x >= 0 && x < W) v = ld4_stream(g_out + ((img + (size_t)y * W + x) * Co + 4 * ld_o4));
-            st4(sg + px * CoP + 4 * ld_o4, v);
+            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+            const float* src = in ? g_out + ((img + (size_t)y * W + x) * Co + 4 * ld_o4) : g_out;
+            cp_async16(sg + px * CoP + 4 * ld_o4, src, in ? 16 : 0);
         }
         for (int i = tid; i < nch * (K + 1); i += IC_BWD_THREADS) sCnt[i] = 0;
         __syncthreads();
@@ -605,11 +614,12 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
         for (int i = tid; i < npx; i += IC_BWD_THREADS) {
             const int2 e = sTmp[i];
             const int lab = (int)(signed char)(e.x & 0xff), rank = e.x >> 8, ch = i >> 5;
-            if (lab >= 0)
-                sList[sBase[lab] + sCnt[ch * (K + 1) + lab] + rank] = make_int2(i, e.y);
+            if (lab >= 0)  // (offset of the pixel in the g_out tile, value)
+                sList[sBase[lab] + sCnt[ch * (K + 1) + lab] + rank] = make_int2(((i >> 5) * TWp + (i & 31)) * CoP, e.y);
             else if (lab == -1)
                 sDense[sCnt[ch * (K + 1) + K] + rank] = i;
         }
+        cp_async_wait_all();
         __syncthreads();
 
         // (3) dmask on the tensor cores: warp w < 8 owns m-tiles m = w*MTW + mt: tile row m>>1, x half m&1
@@ -727,44 +737,49 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
             }
         }
 
-        // (4) dG: unit u = t*K + k; Co4 lanes own a unit and walk its sorted pixel list with two chains
+        // (4) dG: unit u = (filter row dy, label k): Co4 lanes walk the label's sorted pixel list once for the three
+        // taps of the row (3 x float4 accumulators), 32/Co4 units per warp side by side
         {
             const int nd = sTot[K];
-            for (int u0 = warp * upw; u0 < 9 * K; u0 += (IC_BWD_THREADS / 32) * upw) {
+            for (int u0 = warp * upw; u0 < 3 * K; u0 += (IC_BWD_THREADS / 32) * upw) {
                 const int u = u0 + usub;
-                if (u < 9 * K) {
-                    const int t = u / K, k = u - t * K;
-                    const int dy = t / 3, dx = t - 3 * dy;
-                    const float* gt = sg + ((2 - dy) * TWp + 2 - dx) * CoP + 4 * o4l;
+                if (u < 3 * K) {
+                    const int dy = u / K, k = u - dy * K;
+                    const float* gt = sg + ((2 - dy) * TWp + 2) * CoP + 4 * o4l;  // tap dx reads gt - dx*CoP
                     const int beg = sBase[k], end = sBase[k + 1];
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int j = beg;
-                    for (; j + 1 < end; j += 2) {
-                        const int2 e = sList[j], e2 = sList[j + 1];
-                        const float v = __int_as_float(e.y), v2 = __int_as_float(e2.y);
-                        const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
-                        const float4 g2 = *reinterpret_cast<const float4*>(gt + ((e2.x >> 5) * TWp + (e2.x & 31)) * CoP);
-                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
-                        a2.x = fmaf(v2, g2.x, a2.x); a2.y = fmaf(v2, g2.y, a2.y); a2.z = fmaf(v2, g2.z, a2.z);
-                        a2.w = fmaf(v2, g2.w, a2.w);
-                    }
-                    if (j < end) {
+                    float4 a[3];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) a[dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = beg; j < end; ++j) {
                         const int2 e = sList[j];
                         const float v = __int_as_float(e.y);
-                        const float4 g = *reinterpret_cast<const float4*>(gt + ((e.x >> 5) * TWp + (e.x & 31)) * CoP);
-                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                        const float* gp = gt + e.x;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float4 g = *reinterpret_cast<const float4*>(gp - dx * CoP);
+                            a[dx].x = fmaf(v, g.x, a[dx].x); a[dx].y = fmaf(v, g.y, a[dx].y);
+                            a[dx].z = fmaf(v, g.z, a[dx].z); a[dx].w = fmaf(v, g.w, a[dx].w);
+                        }
                     }
                     for (int jd = 0; jd < nd; ++jd) {  // pixels with several non-zeros (exact ties, soft masks)
                         const int i = sDense[jd];
                         const float v = __ldg(mask + (img + (size_t)(y0 + (i >> 5)) * W + (x0 + (i & 31))) * K + k);
-                        const float4 g = *reinterpret_cast<const float4*>(gt + ((i >> 5) * TWp + (i & 31)) * CoP);
-                        a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+                        const float* gp = gt + ((i >> 5) * TWp + (i & 31)) * CoP;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float4 g = *reinterpret_cast<const float4*>(gp - dx * CoP);
+                            a[dx].x = fmaf(v, g.x, a[dx].x); a[dx].y = fmaf(v, g.y, a[dx].y);
+                            a[dx].z = fmaf(v, g.z, a[dx].z); a[dx].w = fmaf(v, g.w, a[dx].w);
+                        }
                     }
                     if (beg != end || nd != 0) {
-                        float4* dst = reinterpret_cast<float4*>(sdG + (t * K + k) * Co + 4 * o4l);
-                        float4 c = *dst;
-                        c.x += a.x + a2.x; c.y += a.y + a2.y; c.z += a.z + a2.z; c.w += a.w + a2.w;
-                        *dst = c;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            float4* dst = reinterpret_cast<float4*>(sdG + ((3 * dy + dx) * K + k) * Co + 4 * o4l);
+                            float4 c = *dst;
+                            c.x += a[dx].x; c.y += a[dx].y; c.z += a[dx].z; c.w += a[dx].w;
+                            *dst = c;
+                        }
                     }
                 }
             }
@@ -878,15 +893,16 @@ int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const fl
                const float* g_extra, float* dmask, float* ws_dG, float* ws_db, int B, int H, int W, int K, int Co,
                cudaStream_t st) {
     if (p.mma) {
-#define UPS_IC_MMA(MTW)                                                                                                   \
-    do {                                                                                                                  \
-        UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_mma_kernel<KP / 8, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      p.smem));                                                                           \
-        inject_conv_bwd_mma_kernel<KP / 8, MTW><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(                       \
-            g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.tiles_x, p.n_tiles, p.tiles_per_cta);       \
+#define UPS_IC_MMA(MTW, CO)                                                                                      \
+    do {                                                                                                         \
+        UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_mma_kernel<KP / 8, MTW, CO>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));                     \
+        inject_conv_bwd_mma_kernel<KP / 8, MTW, CO><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(          \
+            g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.tiles_x, p.n_tiles, p.tiles_per_cta); \
     } while (0)
-        if (p.TH == 8) UPS_IC_MMA(2);
-        else UPS_IC_MMA(1);
+        if (p.TH == 8 && Co == 32) UPS_IC_MMA(2, 32);  // the reference's first-layer width (final_hour.config[0])
+        else if (p.TH == 8) UPS_IC_MMA(2, 0);
+        else UPS_IC_MMA(1, 0);
 #undef UPS_IC_MMA
         return after_launch("inject_conv_bwd_mma_kernel");
     }
