@@ -17,7 +17,8 @@ namespace {
 
 constexpr int IC_FWD_THREADS = 256;  // 8 warps = 8 rows of a strip
 constexpr int IC_FWD_ROWS = 8;
-constexpr int IC_BWD_THREADS = 288;  // 9 warps: one per filter tap in the dG phase
+constexpr int IC_BWD_THREADS = 288;  // CUDA-core backward: 9 warps, one per filter tap in the dG phase
+constexpr int IC_MMA_THREADS = 256;  // tensor-core backward: 8 warps, MTW m-tiles each
 constexpr int IC_TW = 32;            // backward tile width (pixels); thread = pixels (x, x+16)
 constexpr int IC_SMEM_BUDGET = 224 * 1024;   // per CTA (227 KB is the hardware limit)
 constexpr int IC_SMEM_HALF = 112 * 1024 + 512;     // two CTAs per SM
@@ -147,9 +148,14 @@ __device__ __forceinline__ void inject_conv_fwd_rows(const float* __restrict__ s
                                                      float* __restrict__ ob, int y0, int rows, int H, int W, int K,
                                                      int Co, int Co4, int tid) {
     const int Wp = W + 2, KCo = K * Co;
-    for (int idx = tid; idx < rows * W * Co4; idx += IC_FWD_THREADS) {
-        const int px = idx / Co4, o = 4 * (idx - px * Co4);
-        const int r = px / W, x = px - r * W;
+    // idx = (r*W + x)*Co4 + o4 advances by the block size: carry-propagate instead of dividing
+    const int d_px = IC_FWD_THREADS / Co4, d_o4 = IC_FWD_THREADS - d_px * Co4;
+    int px0 = tid / Co4, o4 = tid - px0 * Co4;
+    int r = px0 / W, x = px0 - r * W;
+    for (int idx = tid; idx < rows * W * Co4; idx += IC_FWD_THREADS, o4 += d_o4, x += d_px) {
+        if (o4 >= Co4) { o4 -= Co4; ++x; }
+        while (x >= W) { x -= W; ++r; }
+        const int o = 4 * o4;
         float4 acc = *reinterpret_cast<const float4*>(sB + o);
         const int2* e0 = sM + r * Wp + x;
         const float* g0 = sG + o;
@@ -518,7 +524,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // N tiles of 8 parts: KP = 8*NT >= K;  m-tiles per warp: tile rows TH = 4*MTW;  CO > 0: Co known at compile time
 template <int NT, int MTW, int CO>
-__global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_bwd_mma_kernel(
+__global__ void __launch_bounds__(IC_MMA_THREADS, MTW <= 2 ? 2 : 1) inject_conv_bwd_mma_kernel(
     const float* __restrict__ g_out, const float* __restrict__ mask, const float* __restrict__ G,
     const float* __restrict__ probs, const float* __restrict__ g_extra, float* __restrict__ dmask,
     float* __restrict__ ws_dG, float* __restrict__ ws_db, int H, int W, int K, int Co_rt, int tiles_x, int n_tiles,
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
     float* sGhi = reinterpret_cast<float*>(sm + L.off_Ghi);  // [9][Co][KP] swizzled: the TF32 part of G
     float* sGlo = reinterpret_cast<float*>(sm + L.off_Glo);  // [9][Co][KP] swizzled: G - hi
     float* sdG = reinterpret_cast<float*>(sm + L.off_dG);    // [9][K][Co]
-    float* sdb = reinterpret_cast<float*>(sm + L.off_db);    // [9 warps][Co]
+    float* sdb = reinterpret_cast<float*>(sm + L.off_db);    // [8 warps][Co] (sized for 9)
     float* sg = reinterpret_cast<float*>(sm + L.off_g);      // [(TH+2)][34][Co+4]
     int2* sList = reinterpret_cast<int2*>(sm + L.off_list);
     int2* sTmp = reinterpret_cast<int2*>(sm + L.off_tmp);
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
     const int CoP = Co + 4, Co4 = Co >> 2;
     const size_t img = (size_t)b * H * W;
 
-    for (int i = tid; i < 9 * KP * Co; i += IC_BWD_THREADS) {  // o fastest: coalesced global reads
+    for (int i = tid; i < 9 * KP * Co; i += IC_MMA_THREADS) {  // o fastest: coalesced global reads
         const int o = i % Co, tk = i / Co, k = tk % KP, t = tk / KP;
         const float v = k < K ? __ldg(G + (((size_t)b * 9 + t) * K + k) * Co + o) : 0.f;
         unsigned hi, lo;
@@ -555,11 +561,11 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
         sGhi[at] = __uint_as_float(hi);
         sGlo[at] = __uint_as_float(lo);
     }
-    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) sdG[i] = 0.f;
-    for (int i = tid; i < 9 * Co; i += IC_BWD_THREADS) sdb[i] = 0.f;
+    for (int i = tid; i < 9 * K * Co; i += IC_MMA_THREADS) sdG[i] = 0.f;
+    for (int i = tid; i < 9 * Co; i += IC_MMA_THREADS) sdb[i] = 0.f;
 
-    // tile-load roles: Co4 (a power of two) divides 288, so a thread keeps its channel quad
-    const int ld_o4 = tid & (Co4 - 1), ld_px0 = tid / Co4, ld_step = IC_BWD_THREADS / Co4;
+    // tile-load roles: Co4 (a power of two) divides the block size, so a thread keeps its channel quad
+    const int ld_o4 = tid & (Co4 - 1), ld_px0 = tid / Co4, ld_step = IC_MMA_THREADS / Co4;
     // dG roles: Co4 lanes per (tap, label) unit, 32/Co4 units per warp
     const int lpu_shift = 31 - __clz(Co4);
     const int usub = lane >> lpu_shift, o4l = lane & (Co4 - 1), upw = 32 >> lpu_shift;
@@ -579,9 +585,9 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
             const float* src = in ? g_out + ((img + (size_t)y * W + x) * Co + 4 * ld_o4) : g_out;
             cp_async16(sg + px * CoP + 4 * ld_o4, src, in ? 16 : 0);
         }
-        for (int i = tid; i < nch * (K + 1); i += IC_BWD_THREADS) sCnt[i] = 0;
+        for (int i = tid; i < nch * (K + 1); i += IC_MMA_THREADS) sCnt[i] = 0;
         __syncthreads();
-        for (int ch = warp; ch < nch; ch += IC_BWD_THREADS / 32) {
+        for (int ch = warp; ch < nch; ch += IC_MMA_THREADS / 32) {
             const int i = ch * 32 + lane;
             const int y = y0 + (i >> 5), x = x0 + (i & 31);
             int2 e = make_int2(-2, 0);
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
             sBase[K] = run;
         }
         __syncthreads();
-        for (int i = tid; i < npx; i += IC_BWD_THREADS) {
+        for (int i = tid; i < npx; i += IC_MMA_THREADS) {
             const int2 e = sTmp[i];
             const int lab = (int)(signed char)(e.x & 0xff), rank = e.x >> 8, ch = i >> 5;
             if (lab >= 0)  // (offset of the pixel in the g_out tile, value)
@@ -626,6 +632,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
         if (warp < 8) {
             float run[MTW][NT][4];   // fp32 running sum, starts from g_extra (its loads fly during the MMA loop)
             float small[MTW][NT][4]; // lo*hi' + hi*lo'
+            float pr[MTW][NT][4];    // probabilities of the same elements (0 if unused / outside)
             const int mt0 = warp * MTW;
 #pragma unroll
             for (int mt = 0; mt < MTW; ++mt) {
@@ -642,6 +649,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
                         for (int j = 0; j < 2; ++j) {
                             const int k = nt * 8 + 2 * tig + j;
                             run[mt][nt][2 * h + j] = (in && k < K && g_extra != nullptr) ? __ldg(g_extra + base + k) : 0.f;
+                            pr[mt][nt][2 * h + j] = (in && k < K && probs != nullptr) ? __ldg(probs + base + k) : 0.f;
                             small[mt][nt][2 * h + j] = 0.f;
                         }
                 }
@@ -709,9 +717,8 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const int k = nt * 8 + 2 * tig + j;
                             d[nt][j] = run[mt][nt][2 * h + j] + small[mt][nt][2 * h + j];
-                            p[nt][j] = (in && k < K && probs != nullptr) ? __ldg(probs + base + k) : 0.f;
+                            p[nt][j] = pr[mt][nt][2 * h + j];
                             dot = fmaf(d[nt][j], p[nt][j], dot);
                         }
                     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
         // taps of the row (3 x float4 accumulators), 32/Co4 units per warp side by side
         {
             const int nd = sTot[K];
-            for (int u0 = warp * upw; u0 < 3 * K; u0 += (IC_BWD_THREADS / 32) * upw) {
+            for (int u0 = warp * upw; u0 < 3 * K; u0 += (IC_MMA_THREADS / 32) * upw) {
                 const int u = u0 + usub;
                 if (u < 3 * K) {
                     const int dy = u / K, k = u - dy * K;
@@ -789,7 +796,7 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
             const int o = oc + lane;
             if (o < Co) {
                 float s = 0.f;
-                for (int ty = warp; ty < TH; ty += IC_BWD_THREADS / 32) {
+                for (int ty = warp; ty < TH; ty += IC_MMA_THREADS / 32) {
                     const float* row = sg + ((ty + 1) * TWp + 1) * CoP + o;
 #pragma unroll 8
                     for (int tx = 0; tx < IC_TW; ++tx) s += row[tx * CoP];
@@ -800,10 +807,10 @@ __global__ void __launch_bounds__(IC_BWD_THREADS, MTW <= 2 ? 2 : 1) inject_conv_
     }
     __syncthreads();
     const size_t slot_ws = (size_t)b * gridDim.x + blockIdx.x;
-    for (int i = tid; i < 9 * K * Co; i += IC_BWD_THREADS) ws_dG[slot_ws * 9 * K * Co + i] = sdG[i];
-    for (int o = tid; o < Co; o += IC_BWD_THREADS) {
+    for (int i = tid; i < 9 * K * Co; i += IC_MMA_THREADS) ws_dG[slot_ws * 9 * K * Co + i] = sdG[i];
+    for (int o = tid; o < Co; o += IC_MMA_THREADS) {
         float s = 0.f;
-        for (int w = 0; w < IC_BWD_THREADS / 32; ++w) s += sdb[w * Co + o];
+        for (int w = 0; w < IC_MMA_THREADS / 32; ++w) s += sdb[w * Co + o];
         ws_db[slot_ws * Co + o] = s;
     }
 }
@@ -897,7 +904,7 @@ int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const fl
     do {                                                                                                         \
         UPS_CUDA(cudaFuncSetAttribute(inject_conv_bwd_mma_kernel<KP / 8, MTW, CO>,                               \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));                     \
-        inject_conv_bwd_mma_kernel<KP / 8, MTW, CO><<<dim3(p.splits, B), IC_BWD_THREADS, p.smem, st>>>(          \
+        inject_conv_bwd_mma_kernel<KP / 8, MTW, CO><<<dim3(p.splits, B), IC_MMA_THREADS, p.smem, st>>>(          \
             g_out, mask, G, probs, g_extra, dmask, ws_dG, ws_db, H, W, K, Co, p.tiles_x, p.n_tiles, p.tiles_per_cta); \
     } while (0)
         if (p.TH == 8 && Co == 32) UPS_IC_MMA(2, 32);  // the reference's first-layer width (final_hour.config[0])

@@ -82,9 +82,14 @@ __global__ void __launch_bounds__(PC_THREADS) parts_conv_fwd_kernel(const float*
             sPx[i] = e;
         }
         __syncthreads();
-        for (int idx = tid; idx < rows * W * Co4; idx += PC_THREADS) {
-            const int px = idx / Co4, o = 4 * (idx - px * Co4);
-            const int r = px / W, x = px - r * W;
+        // idx = (r*W + x)*Co4 + o4 advances by the block size: carry-propagate instead of dividing
+        const int d_px = PC_THREADS / Co4, d_o4 = PC_THREADS - d_px * Co4;
+        int px0 = tid / Co4, o4 = tid - px0 * Co4;
+        int r = px0 / W, x = px0 - r * W;
+        for (int idx = tid; idx < rows * W * Co4; idx += PC_THREADS, o4 += d_o4, x += d_px) {
+            if (o4 >= Co4) { o4 -= Co4; ++x; }
+            while (x >= W) { x -= W; ++r; }
+            const int o = 4 * o4;
             const float4 bo = *reinterpret_cast<const float4*>(sB + o);
             const float4* e0 = sPx + r * Wp + x;
             int labs[9];
