@@ -313,6 +313,19 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, med, cores, sample = cpu_port_rate(wl, steps=5, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    # ---- SURVEY.md 8f N4 (next row): the first decoder / encoder convolutions on the part assignment, per C-ABI
+    # call with CUDA events, L2 flushed between calls; the library (cuDNN) legs on the materialised tensors beside them
+    if rank == 0 and world == 1 and args.workload == "cub" and not args.no_n4:
+        try:
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_inject_conv
+            n4 = bench_inject_conv.measure(B, S, K, library=True, iters=5)
+            line["n4_first_conv"] = {"shape": n4["shape"], "l2": n4["l2"],
+                                     "calls": {k: ({"ms": round(v["ms"], 4), "frac_of_measured_hbm": round(v["frac_of_measured_hbm"], 4)}
+                                                   if "ms" in v else v) for k, v in n4["calls"].items()}}
+        except Exception as e:  # the N4 leg must never cost the headline line
+            line["n4_first_conv"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -438,6 +451,7 @@ def main():
     ap.add_argument("--bucket-mb", type=int, default=256, help="all-reduce bucket size; the stand-in buffer is ready at once, so one bucket")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-n4", action="store_true", help="skip the N4 first-convolution microbenchmark leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,15 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--tag", default="r01d")
-    ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--size", type=int, default=128)
-    ap.add_argument("--parts", type=int, default=16)
-    ap.add_argument("--no-library", action="store_true", help="skip the cuDNN comparison legs")
-    ap.add_argument("--once", action="store_true", help="call every entry once and exit (for ncu)")
-    a = ap.parse_args()
+def measure(batch=256, size=128, parts=16, library=True, once=False, iters=10):
+    """Returns {call: {ms, algorithmic_bytes, gbs, frac_of_measured_hbm}} (None with once=True)."""
+    import types
+    a = types.SimpleNamespace(batch=batch, size=size, parts=parts, no_library=not library, once=once)
     import torch
     import ups_b200  # noqa: F401
     from ups_b200 import _cabi as C
@@ -97,7 +92,7 @@ def main():
         for name, (fn, by) in calls.items():
             fn()
         torch.cuda.synchronize()
-        return
+        return None
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
     res = {}
     for name, (fn, by) in calls.items():
@@ -105,7 +100,7 @@ def main():
             for _ in range(3):
                 fn()
             ts = []
-            for _ in range(10):
+            for _ in range(iters):
                 flush.sum()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); fn(); e1.record()
@@ -117,11 +112,26 @@ def main():
                              frac_of_measured_hbm=by / (ms * 1e-3) / 1e9 / peak)
         except Exception as e:  # a library leg that cannot run must not hide our own numbers
             res[name] = dict(error=repr(e)[:300])
-        print(name, json.dumps(res[name]), flush=True)
+    return dict(shape=dict(B=B, H=H, W=W, K=K, F=F, Co=Co), peak_gbs=peak,
+                l2="flushed between timed calls (256 MB read)", calls=res)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tag", default="r01d")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--parts", type=int, default=16)
+    ap.add_argument("--no-library", action="store_true", help="skip the cuDNN comparison legs")
+    ap.add_argument("--once", action="store_true", help="call every entry once and exit (for ncu)")
+    a = ap.parse_args()
+    out = measure(a.batch, a.size, a.parts, library=not a.no_library, once=a.once)
+    if out is None:
+        return
+    for name, r in out["calls"].items():
+        print(name, json.dumps(r), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(dict(shape=dict(B=B, H=H, W=W, K=K, F=F, Co=Co), peak_gbs=peak,
-                   l2="flushed between timed calls (256 MB read)", calls=res),
-              open(os.path.join(ROOT, "gpurun_out", f"{a.tag}_inject_conv.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"{a.tag}_inject_conv.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -206,3 +206,41 @@ def test_decode_bwd_tensor_core_path(ups, B, S, K, seed):
     m0b = OP.softmax(lo)
     (dl0_o2,) = torch.autograd.grad(OP.inject(feat, OP.straight_through_estimator(OP.hard_max(m0b, 3), m0b)), lo, g_inj)
     assert_close(dl0, dl0_o2, "tc dl0 (no g_m0)")
+
+
+@pytest.mark.parametrize("B,S,K,F,Co", [(2, 64, 16, 64, 32), (3, 32, 25, 16, 16), (1, 48, 8, 32, 64)])
+def test_first_conv_step(ups, B, S, K, F, Co):
+    """PartStep(first_conv=Co) ends the decode side in the decoder's first convolution
+    (cub/code/SB_model48i/model.py:96,485) without forming `inj`; everything else is the same step."""
+    import math
+    from oracle import inject_conv as IC
+    from oracle import parts as OP
+    from ups_b200.step import PartStep
+    inp = make_inputs(B, S, K, F, 3, seed=B + Co, ties=True)
+    g = torch.Generator().manual_seed(Co)
+    stdv = math.sqrt(1.0 / ((F + K) * 9))
+    V = (torch.rand(3, 3, F + K, Co, generator=g) * 2 - 1) * stdv
+    b = (torch.rand(Co, generator=g) * 2 - 1) * stdv
+    g_h0 = torch.randn(B, S, S, Co, generator=g)
+    c = inp["cot"]
+    out_o, grad_o = OS.step_forward_backward([v for v in inp["views"]], inp["coord"], inp["t_vector"], inp["l0"],
+                                             inp["l1"], inp["feat"], dict(c, g_warped=None))
+    lo = [t.clone().requires_grad_(True) for t in (inp["l0"], inp["feat"], V, b)]
+    m0_o = OP.softmax(lo[0])
+    h0_o = IC.inject_conv2d(lo[1], OP.hard_max_straight_through(m0_o, 3), lo[2], lo[3])
+    dl0_o, dfeat_o, dV_o, db_o = torch.autograd.grad([h0_o, m0_o], lo, [g_h0, c["g_m0"]])
+    step = PartStep(B, S, K, F, n_views=3, first_conv=Co)
+    d = cuda(inp)
+    out = step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"], V.cuda(), b.cuda())
+    grad = step.backward(g_h0.cuda(), d["cot"]["g_parts"], d["cot"]["g_pooled"], d["cot"]["g_m0"], d["cot"]["g_m1"])
+    torch.cuda.synchronize()
+    assert "inj" not in out
+    assert_bitexact(out["m0"], out_o["m0"], "m0")
+    assert torch.equal(out["labels0"].cpu(), out_o["labels0"])
+    assert_bitexact(out["parts"], out_o["parts"], "parts")
+    assert_close(out["h0"], h0_o.detach(), "h0")
+    assert_close(grad["dl1"], grad_o["dl1"], "dl1")
+    assert_close(grad["dl0"], dl0_o, "dl0", atol=reduce_atol(9 * Co))
+    assert_close(grad["dfeat"], dfeat_o, "dfeat", atol=4 * reduce_atol(S * S * 9))
+    assert_close(grad["dV"], dV_o, "dV", atol=4 * reduce_atol(B * S * S))
+    assert_close(grad["db"], db_o, "db", atol=4 * reduce_atol(B * S * S))

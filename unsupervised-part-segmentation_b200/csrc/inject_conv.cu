@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) inject_conv_table_bwd_feat_kernel(const f
         for (int t = 0; t < 9; ++t) {
             const float* Vr = V + ((size_t)t * (F + K) + f) * Co;
             const float* dr = sd + (t * K + k) * Co;
-            for (int o = 0; o < Co; o += 4) {
+#pragma unroll 8
+            for (int o = 0; o < Co; o += 4) {  // unrolled: the 8 loads of a tap are in flight together
                 const float4 v = ld4(Vr + o);
                 const float4 d = *reinterpret_cast<const float4*>(dr + o);
                 a0 = fmaf(d.x, v.x, a0); a1 = fmaf(d.y, v.y, a1); a2 = fmaf(d.z, v.z, a2); a3 = fmaf(d.w, v.w, a3);
@@ -109,18 +110,29 @@ __global__ void __launch_bounds__(256) inject_conv_table_bwd_filter_kernel(const
         const int o = o0 + lane;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (o < Co) {
+            const bool quad = (F & 3) == 0 && c0 + 3 < F;  // four feature rows: one 16-byte feat load per (b,k)
             for (int b = warp; b < B; b += 8) {
                 const float* d = dG + (((size_t)b * 9 + t) * K) * Co + o;
                 const float* fr = feat + (size_t)b * K * F;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = c0 + j;
-                    if (c < F) {
+                if (quad) {
 #pragma unroll 8
-                        for (int k = 0; k < K; ++k)
-                            acc[j] = fmaf(__ldg(fr + (size_t)k * F + c), __ldg(d + (size_t)k * Co), acc[j]);
-                    } else if (c < F + K) {
-                        acc[j] += __ldg(d + (size_t)(c - F) * Co);
+                    for (int k = 0; k < K; ++k) {
+                        const float dv = __ldg(d + (size_t)k * Co);
+                        const float4 f4 = ld4(fr + (size_t)k * F + c0);
+                        acc[0] = fmaf(f4.x, dv, acc[0]); acc[1] = fmaf(f4.y, dv, acc[1]);
+                        acc[2] = fmaf(f4.z, dv, acc[2]); acc[3] = fmaf(f4.w, dv, acc[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = c0 + j;
+                        if (c < F) {
+#pragma unroll 8
+                            for (int k = 0; k < K; ++k)
+                                acc[j] = fmaf(__ldg(fr + (size_t)k * F + c), __ldg(d + (size_t)k * Co), acc[j]);
+                        } else if (c < F + K) {
+                            acc[j] += __ldg(d + (size_t)(c - F) * Co);
+                        }
                     }
                 }
             }
@@ -945,7 +957,7 @@ extern "C" int ups_inject_conv_table_bwd(const float* dG, const float* feat, con
                                          int B, int K, int F, int Co, void* stream) {
     UPS_REQUIRE(dG && feat && V, "inject_conv_table_bwd: null pointer");
     UPS_REQUIRE(B >= 0 && K >= 1 && K <= 32 && F >= 1 && Co >= 4 && Co % 4 == 0, "inject_conv_table_bwd: bad sizes");
-    UPS_REQUIRE(aligned16(dG) && aligned16(V), "inject_conv_table_bwd: dG and V must be 16-byte aligned");
+    UPS_REQUIRE(aligned16(dG) && aligned16(V) && aligned16(feat), "inject_conv_table_bwd: dG, V and feat must be 16-byte aligned");
     const size_t smem = (size_t)9 * K * Co * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "inject_conv_table_bwd: 9*K*Co=%d too large", 9 * K * Co);
     cudaStream_t st = as_stream(stream);

@@ -10,6 +10,8 @@ What the reference builds per training step in TrainModel.define_graph
     parts           = apply_partwise-fold(mask_parts(warped[1], m1h))   model.py:478 ; nn.py:100-103
     pooled          = mean_hw(parts)        (tail of e_alpha)           model.py:50-52
     inj             = concat(sum_k unpool_features(feat, m0h), m0h)     model.py:482-484
+    [h0             = conv2d(inj, V) + b   (first layer of `dd`)        model.py:96,485 ; nn.py:617-664
+                      with first_conv=Co: computed from m0h and feat directly, `inj` is never formed]
 
 The CNNs between those pieces are not part of the path: `l0`, `l1` (mask decoder output) and
 `feat` (appearance encoder output) are inputs, and the cotangents of every output are inputs
@@ -29,7 +31,7 @@ def _cur_stream():
 
 class PartStep:
     def __init__(self, batch_size, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, device="cuda", decode_bwd="auto"):
+                 views_grad=False, device="cuda", decode_bwd="auto", first_conv=0):
         B, S, K, F, V = int(batch_size), int(spatial_size), int(n_parts), int(local_app_size), int(n_views)
         self.B, self.S, self.K, self.F, self.V = B, S, K, F, V
         self.P = S * S
@@ -53,7 +55,19 @@ class PartStep:
         self.labels0 = e(B, S, S, dtype=torch.int64, device=self.device)
         self.parts = e(K * B, S, S, 3, **f32)
         self.pooled = e(B, K, 3, **f32)
-        self.inj = e(B, S, S, F + K, **f32)
+        # first_conv = Co > 0: the decode side ends in the decoder's first 3x3 convolution (h0 [B,S,S,Co]) instead of
+        # the injected map; forward takes the filter (conv_V [3,3,F+K,Co], conv_b [Co]), backward g_h0
+        self.Co = int(first_conv)
+        if self.Co:
+            self.inj = None
+            self.h0 = e(B, S, S, self.Co, **f32)
+            self.mh0c = e(B, S, S, K, **f32)
+            self.G, self.dG = e(B, 9, K, self.Co, **f32), e(B, 9, K, self.Co, **f32)
+            self.dV, self.db = e(3, 3, F + K, self.Co, **f32), e(self.Co, **f32)
+            self.ws_ic = e(C.inject_conv_workspace_bytes(B, S, S, K, self.Co), dtype=torch.uint8, device=self.device)
+            self._conv_V = None
+        else:
+            self.inj = e(B, S, S, F + K, **f32)
         self.dl0, self.dl1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
         self.dfeat = e(B, K, F, **f32)
         nws = C.workspace_bytes(C.OP_STEP, B, self.P, K, F)
@@ -79,7 +93,20 @@ class PartStep:
             self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, views, coord, t_vector, l0, l1, feat):
+    def _decode_fwd(self, l0, feat, conv_V, conv_b, st):
+        """decode side on stream `st`: K3, or with first_conv softmax -> table -> 3x3 conv on the assignment"""
+        B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
+        if not self.Co:
+            C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
+                   self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
+            return
+        C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
+               self.mh0c.data_ptr(), B * P, K, st)
+        C.call("ups_inject_conv_table_fwd", feat.data_ptr(), conv_V.data_ptr(), self.G.data_ptr(), B, K, F, self.Co, st)
+        C.call("ups_inject_conv_fwd", self.mh0c.data_ptr(), self.G.data_ptr(), conv_b.data_ptr(), self.h0.data_ptr(),
+               B, S, S, K, self.Co, st)
+
+    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None):
         """views [V,B,S,S,3] (view0, view1[, view0_target]), fp32 in [-1, 1] or the dataset's uint8
         (normalised on the device exactly as cub/code/data/data.py:134 does on the host); coord,
         t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
@@ -95,13 +122,17 @@ class PartStep:
         assert views.is_contiguous() and l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
         assert tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        if self.Co:
+            assert conv_V is not None and conv_b is not None, "first_conv: pass conv_V [3,3,F+K,Co] and conv_b [Co]"
+            assert tuple(conv_V.shape) == (3, 3, F + K, self.Co) and tuple(conv_b.shape) == (self.Co,)
+            assert conv_V.is_contiguous() and conv_b.is_contiguous()
+            self._conv_V = conv_V
         if self.overlap_fwd:
             main = torch.cuda.current_stream()
             self._fork.record(main)
             self._side.wait_event(self._fork)
             with torch.cuda.stream(self._side):
-                C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
-                       self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, self._side.cuda_stream)
+                self._decode_fwd(l0, feat, conv_V, conv_b, self._side.cuda_stream)
                 self._join.record(self._side)
         if self.use_tps:
             assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
@@ -124,8 +155,13 @@ class PartStep:
             if self.overlap_fwd:
                 torch.cuda.current_stream().wait_event(self._join)
             else:
-                C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
-                       self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
+                self._decode_fwd(l0, feat, conv_V, conv_b, st)
+        elif self.Co:
+            C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
+            C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
+            C.call("ups_part_pool_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.pooled.data_ptr(), B, P, K, 3, 0,
+                   1.0 / P, self.ws.data_ptr(), self.ws.numel(), st)
+            self._decode_fwd(l0, feat, conv_V, conv_b, st)
         else:
             C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
@@ -134,30 +170,45 @@ class PartStep:
             C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
                    self.mh0.data_ptr(), B * P, K, st)
             C.call("ups_part_inject_fwd", feat.data_ptr(), self.mh0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
-        return dict(warped=warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
-                    pooled=self.pooled, inj=self.inj)
+        out = dict(warped=warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts, pooled=self.pooled)
+        if self.Co:
+            out["h0"] = self.h0
+        else:
+            out["inj"] = self.inj
+        return out
 
     # ------------------------------------------------------------------ backward
     def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None):
-        """Cotangents: g_inj [B,S,S,F+K], g_parts [K*B,S,S,3] (part-major), g_pooled [B,K,3],
-        g_m0/g_m1 [B,S,S,K] (from the mask losses), g_warped [V,B,S,S,3] (views_grad only).
-        Returns dict(dl0, dl1, dfeat[, dviews])."""
+        """Cotangents: g_inj [B,S,S,F+K] (with first_conv: g_h0 [B,S,S,Co] in its place), g_parts [K*B,S,S,3]
+        (part-major), g_pooled [B,K,3], g_m0/g_m1 [B,S,S,K] (from the mask losses), g_warped [V,B,S,S,3]
+        (views_grad only).  Returns dict(dl0, dl1, dfeat[, dV, db][, dviews])."""
         B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
         st = _cur_stream()
         img1, feat = self._img1, self._feat
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         want_dimg = self.views_grad
-        if self.fused:
+        if self.Co:
+            assert tuple(g_inj.shape) == (B, S, S, self.Co), list(g_inj.shape)
+            C.call("ups_inject_conv_bwd", g_inj.data_ptr(), self.mh0c.data_ptr(), self.G.data_ptr(), self.m0.data_ptr(),
+                   p(g_m0), self.dl0.data_ptr(), self.dG.data_ptr(), self.db.data_ptr(), B, S, S, K, self.Co,
+                   self.ws_ic.data_ptr(), self.ws_ic.numel(), st)
+            C.call("ups_inject_conv_table_bwd", self.dG.data_ptr(), feat.data_ptr(), self._conv_V.data_ptr(),
+                   self.dfeat.data_ptr(), self.dV.data_ptr(), B, K, F, self.Co, st)
+        if self.fused and self.Co:
+            C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
+                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
+        elif self.fused:
             C.call("ups_step_decode_bwd_tc" if self.decode_bwd == "tc" else "ups_step_decode_bwd",
                    g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
                    self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
             C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
                    p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
         else:
-            C.call("ups_part_inject_bwd", g_inj.data_ptr(), feat.data_ptr(), self.mh0.data_ptr(),
-                   self.dfeat.data_ptr(), self.dm.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
-            g0 = self.dm if g_m0 is None else self.dm.add_(g_m0)
-            C.call("ups_part_softmax_bwd", self.m0.data_ptr(), g0.data_ptr(), self.dl0.data_ptr(), B * P, K, st)
+            if not self.Co:
+                C.call("ups_part_inject_bwd", g_inj.data_ptr(), feat.data_ptr(), self.mh0.data_ptr(),
+                       self.dfeat.data_ptr(), self.dm.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
+                g0 = self.dm if g_m0 is None else self.dm.add_(g_m0)
+                C.call("ups_part_softmax_bwd", self.m0.data_ptr(), g0.data_ptr(), self.dl0.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
                    self.dimg1.data_ptr() if want_dimg else None, self.dm.data_ptr(), B, P, K, 3, 1, st)
             if g_pooled is not None:
@@ -170,6 +221,8 @@ class PartStep:
                 self.dm.add_(g_m1)
             C.call("ups_part_softmax_bwd", self.m1.data_ptr(), self.dm.data_ptr(), self.dl1.data_ptr(), B * P, K, st)
         out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
+        if self.Co:
+            out["dV"], out["db"] = self.dV, self.db
         if self.views_grad:
             if self.use_tps:
                 if g_warped is None:
