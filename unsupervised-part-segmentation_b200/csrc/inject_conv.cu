@@ -839,11 +839,22 @@ __global__ void inject_conv_bwd_finalize_kernel(const float* __restrict__ ws_dG,
         for (int sp = 0; sp < splits; ++sp) s += ws_dG[(b * splits + sp) * n_per + r];
         dG[i] = s;
     }
-    if (db != nullptr && blockIdx.x == 0) {
-        for (int o = threadIdx.x; o < Co; o += blockDim.x) {
-            float s = 0.f;
-            for (int sl = 0; sl < B * splits; ++sl) s += ws_db[(size_t)sl * Co + o];
-            db[o] = s;
+    if (db != nullptr && blockIdx.x == 0) {  // groups of Co threads sum interleaved slots, then the groups in order
+        __shared__ float part[256];
+        const int ngrp = Co <= 256 ? 256 / Co : 0;
+        if (ngrp >= 1) {
+            const int g = threadIdx.x / Co, o = threadIdx.x - g * Co;
+            if (g < ngrp) {
+                float s = 0.f;
+                for (int sl = g; sl < B * splits; sl += ngrp) s += ws_db[(size_t)sl * Co + o];
+                part[g * Co + o] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x < Co) {
+                float s = 0.f;
+                for (int gg = 0; gg < ngrp; ++gg) s += part[gg * Co + threadIdx.x];
+                db[threadIdx.x] = s;
+            }
         }
     }
 }
@@ -899,7 +910,7 @@ BwdPlan bwd_plan(int B, int H, int W, int K, int Co) {
     p.tiles_x = (int)cdiv(W, IC_TW);
     p.tiles_y = (int)cdiv(H, p.TH);
     p.n_tiles = p.tiles_x * p.tiles_y;
-    long long want = cdiv(8ll * NUM_SMS, B > 0 ? B : 1);  // one or two CTAs per SM resident; several waves for balance
+    long long want = cdiv(16ll * NUM_SMS, B > 0 ? B : 1);  // one or two CTAs per SM resident; ~8 waves: a short tail
     if (want < 1) want = 1;
     if (want > p.n_tiles) want = p.n_tiles;
     p.tiles_per_cta = (int)cdiv(p.n_tiles, want);
