@@ -33,8 +33,7 @@ out = [f"# N4 kernels — ncu full capture ({tag}_n4_prof.ncu-rep)\n",
        "| kernel | " + " | ".join(n for _, n in want) + " |", "|---|" + "---|" * len(want)]
 seen = set()
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0]
-    name = name.replace("void ", "").split("::")[-1] if "<" not in name else name.replace("void ", "").replace("ups::", "")
+    name = r[idx["Kernel Name"]].split("(const")[0].split("(float")[0].replace("void ", "").split("::")[-1]
     if name in seen:
         continue
     seen.add(name)

@@ -199,3 +199,27 @@ def test_parts_conv2d_vs_oracle(ups, B, H, W, K, Co, kind):
     # equals this library's own un-fused path: conv over the materialised part-major part images
     parts_pm = ups.model.mask_parts_partmajor(image.cuda(), mask.cuda())
     assert_close(IC.conv2d_same(parts_pm.cpu(), V, b), y_o, "conv(mask_parts_partmajor)")
+
+
+def test_full_size_backward_properties(ups):
+    """CUB B=64 slice of BASELINE configs[1]: properties of the decode+conv backward that need no oracle —
+    softmax-backward rows sum to zero, db is the plain sum of the cotangent, the backward is linear in the
+    cotangent, and the hard-mask conv equals the un-fused inject -> conv path of this library on a sample."""
+    B, H, W, K, F, Co = 64, 128, 128, 16, 64, 32
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    logits, feat = rn(B, H, W, K).requires_grad_(True), rn(B, K, F).requires_grad_(True)
+    V, b = (rn(3, 3, F + K, Co) * 0.04).requires_grad_(True), (rn(Co) * 0.04).requires_grad_(True)
+    m0, labels, mh, y = ups.model.decode_conv2d(logits, feat, V, b)
+    assert labels.dtype == torch.int64 and torch.equal(labels, m0.argmax(-1))
+    g1, g2 = rn(B, H, W, Co), rn(B, H, W, Co)
+    d1 = torch.autograd.grad(y, [logits, feat, V, b], g1, retain_graph=True)
+    d2 = torch.autograd.grad(y, [logits, feat, V, b], g2, retain_graph=True)
+    d12 = torch.autograd.grad(y, [logits, feat, V, b], g1 + g2)
+    assert float(d1[0].sum(-1).abs().max()) < 2e-4                       # sum_k p_k (g_k - <g,p>) = 0
+    assert_close(d1[3], g1.sum((0, 1, 2)).cpu(), "db", rtol=1e-4, atol=reduce_atol(B * H * W) * 4)
+    for a, c, e, name in zip(d1, d2, d12, ("dlogits", "dfeat", "dV", "db")):
+        scale = float(e.abs().max())
+        assert float((a + c - e).abs().max()) <= 2e-5 * max(1.0, scale), name
+    inj = ups.model.inject_features(feat.detach()[:2], mh.detach()[:2])
+    assert_close(IC.conv2d_same(inj.cpu(), V.detach().cpu(), b.detach().cpu()), y.detach()[:2].cpu(), "conv(inject)")
