@@ -265,9 +265,16 @@ size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co);
  *            e_alpha's first layer nn.conv2d(x, config[0]) (3x3, SAME, + bias)    model.py:40, cub/code/nn.py:617-664
  * without materialising the part images: img [B,H,W,3], mask [B,H,W,K], V [9,3,Co] (HWIO flattened), bias [Co]
  * -> out_pm [K*B,H,W,Co] part-major (row k*B+b, the batch layout apply_partwise hands the encoder).
- * Forward only: the encoder's own backward produces g_parts, which ups_step_encode_bwd consumes. */
+ */
 int ups_parts_conv_fwd(const float* img, const float* mask, const float* V, const float* bias, float* out_pm, int B,
                        int H, int W, int K, int C, int Co, void* stream);
+/* backward: g_out_pm [K*B,H,W,Co] -> dmask [B,H,W,K] (the cotangent of the encoding mask: feed it, plus the loss terms,
+ * to ups_part_softmax_bwd), dV [9,3,Co] (may be NULL), db [Co] (may be NULL).  The image gets no gradient (the
+ * reference's inputs are placeholders, cub/code/SB_model48i/model.py:316-327).  Co in {8,16,32,64}.
+ * ws from ups_parts_conv_bwd_workspace_bytes (per-warp / per-plane partial sums, reduced in a fixed order). */
+int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V, float* dmask, float* dV,
+                       float* db, int B, int H, int W, int K, int C, int Co, void* ws, size_t ws_bytes, void* stream);
+size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
 
 #ifdef __cplusplus
 }

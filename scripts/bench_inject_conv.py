@@ -66,6 +66,12 @@ def measure(batch=256, size=128, parts=16, library=True, once=False, iters=10):
             lambda: C.call("ups_parts_conv_fwd", p(img), p(mh), p(Ve), p(be), p(out_pm), B, H, W, K, 3, Co, st),
             n_pix * 4 * (3 + K + K * Co)),
     }
+    g_pm = torch.empty(K * B, H, W, Co, device=dev).normal_(generator=g)
+    dm1, dVe, dbe = torch.empty_like(l0), torch.empty_like(Ve), torch.empty_like(be)
+    ws_pc = torch.empty(C.parts_conv_bwd_workspace_bytes(B, H, W, K, Co), dtype=torch.uint8, device=dev)
+    calls["ups_parts_conv_bwd (g [K*B,P,Co] -> dmask, dV, db)"] = (
+        lambda: C.call("ups_parts_conv_bwd", p(g_pm), p(img), p(mh), p(Ve), p(dm1), p(dVe), p(dbe), B, H, W, K, 3, Co,
+                       p(ws_pc), ws_pc.numel(), st), n_pix * 4 * (K * Co + 3 + 2 * K))
     C.call("ups_part_softmax_fwd", p(l0), p(m0), p(labels), p(mh), n_pix, K, st)
     C.call("ups_inject_conv_table_fwd", p(feat), p(V), p(G), B, K, F, Co, st)
     if not a.no_library:
@@ -88,6 +94,11 @@ def measure(batch=256, size=128, parts=16, library=True, once=False, iters=10):
             n_pix * 4 * (2 * (F + K) + Co))
         calls["library: cuDNN conv2d fwd on part images [K*B,P,3] (fp32)"] = (
             lambda: TF.conv2d(x_parts, we_nchw, be, padding=1), n_pix * 4 * K * (3 + Co))
+        gpm_nchw = g_pm.permute(0, 3, 1, 2)
+        calls["library: cuDNN conv2d bwd (dgrad + wgrad) on part images"] = (
+            lambda: (torch.ops.aten.convolution_backward(gpm_nchw, x_parts, we_nchw, [Co], [1, 1], [1, 1], [1, 1], False,
+                                                         [0, 0], 1, [True, True, True])),
+            n_pix * 4 * K * (2 * 3 + Co))
     if a.once:
         for name, (fn, by) in calls.items():
             fn()

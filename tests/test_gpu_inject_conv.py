@@ -177,8 +177,38 @@ PC_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 def test_parts_conv_reference_fixture(ups, tag):
     g = np.load(PC_GOLDEN)
     mask, image, V, b = (torch.from_numpy(g[f"{tag}_{n}"]).cuda() for n in ("mask", "image", "V", "b"))
+    mask, V, b = mask.requires_grad_(True), V.requires_grad_(True), b.requires_grad_(True)
     y = ups.model.parts_conv2d(image, mask, V, b)
     assert_close(y, torch.from_numpy(g[f"{tag}_out"]), "out")
+    if V.shape[-1] in (8, 16, 32, 64):
+        got = torch.autograd.grad(y, [mask, V, b], torch.from_numpy(g[f"{tag}_g_out"]).cuda())
+        B, H, W, K = mask.shape
+        for a, name, n in zip(got, ("dmask", "dV", "db"), (27 * V.shape[-1], B * H * W, K * B * H * W)):
+            assert_close(a, torch.from_numpy(g[f"{tag}_{name}"]), name, atol=4 * reduce_atol(n))
+
+
+@pytest.mark.parametrize("B,H,W,K,Co,kind", [(2, 64, 64, 16, 32, "hard"), (1, 128, 128, 16, 32, "ties"),
+                                             (3, 40, 50, 25, 32, "ties"), (2, 33, 31, 8, 64, "soft"),
+                                             (1, 16, 160, 4, 16, "hard"), (2, 9, 70, 5, 8, "soft"), (1, 1, 1, 16, 32, "hard")])
+def test_parts_conv2d_backward_vs_oracle(ups, B, H, W, K, Co, kind):
+    from oracle import parts_conv as PC
+    _, mask, _, _, _, _ = _case(B, H, W, K, 4, Co, kind, seed=B * 10 + K + 1)
+    g = torch.Generator().manual_seed(Co + 1)
+    image = torch.rand(B, H, W, 3, generator=g) * 2 - 1
+    V = (torch.rand(3, 3, 3, Co, generator=g) * 2 - 1) * math.sqrt(1.0 / 27)
+    b = (torch.rand(Co, generator=g) * 2 - 1) * math.sqrt(1.0 / 27)
+    gy = torch.randn(K * B, H, W, Co, generator=g)
+    fn = lambda m, v, bb: PC.parts_conv2d(image.to(m.dtype), m, v, bb)  # noqa: E731
+    _, g_o = _oracle_grads(fn, (mask, V, b), [gy], torch.float32)
+    _, g_o64 = _oracle_grads(fn, (mask, V, b), [gy], torch.float64)
+    lc = [t.cuda().requires_grad_(True) for t in (mask, V, b)]
+    y = ups.model.parts_conv2d(image.cuda(), *lc)
+    got = torch.autograd.grad(y, lc, gy.cuda())
+    for a, o, o64, name, n in zip(got, g_o, g_o64, ("dmask", "dV", "db"), (27 * Co, B * H * W, K * B * H * W)):
+        assert_close(a, o, name, atol=_sum_atol(n, o, o64))
+    with pytest.raises(Exception, match="no gradient with respect to the image"):
+        im = image.cuda().requires_grad_(True)
+        torch.autograd.grad(ups.model.parts_conv2d(im, *lc).sum(), [im])
 
 
 @pytest.mark.parametrize("B,H,W,K,Co,kind", [(2, 64, 64, 16, 32, "hard"), (1, 128, 128, 16, 32, "ties"),

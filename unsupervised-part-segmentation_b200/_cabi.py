@@ -60,6 +60,7 @@ _SIGS = {
     "ups_inject_conv_table_bwd": [c_f] * 5 + [c_i] * 4 + [c_f],
     "ups_inject_conv_fwd": [c_f] * 4 + [c_i] * 5 + [c_f],
     "ups_parts_conv_fwd": [c_f] * 5 + [c_i] * 6 + [c_f],
+    "ups_parts_conv_bwd": [c_f] * 7 + [c_i] * 6 + [c_f, c_sz, c_f],
     "ups_inject_conv_bwd": [c_f] * 8 + [c_i] * 5 + [c_f, c_sz, c_f],
 }
 
@@ -90,6 +91,8 @@ def _load():
     lib.ups_workspace_bytes.restype = c_sz
     lib.ups_inject_conv_workspace_bytes.argtypes = [c_i] * 5
     lib.ups_inject_conv_workspace_bytes.restype = c_sz
+    lib.ups_parts_conv_bwd_workspace_bytes.argtypes = [c_i] * 5
+    lib.ups_parts_conv_bwd_workspace_bytes.restype = c_sz
     return lib, path
 
 
@@ -116,6 +119,10 @@ def launch_count_reset():
 
 def inject_conv_workspace_bytes(B, H, W, K, Co):
     return int(lib.ups_inject_conv_workspace_bytes(B, H, W, K, Co))
+
+
+def parts_conv_bwd_workspace_bytes(B, H, W, K, Co):
+    return int(lib.ups_parts_conv_bwd_workspace_bytes(B, H, W, K, Co))
 
 
 def workspace_bytes(op, B, P, K, F):

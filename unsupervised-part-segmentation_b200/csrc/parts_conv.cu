@@ -151,6 +151,233 @@ __global__ void __launch_bounds__(PC_THREADS) parts_conv_fwd_kernel(const float*
     }
 }
 
+
+// ------------------------------------------------------------------ backward
+// g_h [K*B,H,W,Co] (part-major) -> dmask [B,H,W,K], dV [9,3,Co], db [Co].
+//   R_k[q,c]   = sum_{t,o} g_h[k*B+b, q - off_t, o] V[t,c,o]          (the cotangent of the part image: dense)
+//   dmask[q,k] = sum_c img[q,c] R_k[q,c]
+//   dV[t,c,o]  = sum_{k,b,q} img[q,c] mask[q,k] g_h[k*B+b, q - off_t, o]  (sparse: the pixels of part k only)
+//   db[o]      = sum of g_h over everything
+// Kernel 1 (dense, FMA-bound: 27*Co MAC per plane pixel): one CTA per plane (k,b) walks the rows top to bottom, two
+// rows per step.  A thread owns a column x: it reads its two g_h pixels (Co floats each, straight to registers, no
+// shared-memory staging), forms D[p][t][c] = sum_o g_h[p,o] V[t,c,o] (V from shared memory, broadcast) and parks
+// the 27 values per pixel in a 4-row ring; R_k of the two rows just completed is then 9 ring reads per channel:
+// R[q,c] = sum_t D[q - off_t][t][c].  No halo is recomputed (whole rows, whole plane).  db rides along as
+// per-thread column sums.
+// Kernel 2 (sparse gather): a warp owns a run of pixels of one sample; lane = output channel; for every pixel the
+// 9 rows g_h[label-plane, q - off_t, :] are gathered (128-byte coalesced) into 27 register accumulators.
+// Partials are reduced in a fixed order: deterministic.
+constexpr int PCB_THREADS = 128;
+
+template <int CO>
+__global__ void __launch_bounds__(PCB_THREADS) parts_conv_bwd_data_kernel(const float* __restrict__ g_h,
+                                                                          const float* __restrict__ img,
+                                                                          const float* __restrict__ V,
+                                                                          float* __restrict__ dmask,
+                                                                          float* __restrict__ ws_db, int B, int H, int W,
+                                                                          int K) {
+    constexpr int CO4 = CO / 4;
+    extern __shared__ float4 smem4[];
+    float* sV = reinterpret_cast<float*>(smem4);  // [27][CO]
+    float* sD = sV + 27 * CO;                     // ring [4][W][27]
+    float* sRed = sD + 4 * W * 27;                // [PCB_THREADS/32][CO] for the db reduction
+    const int n = blockIdx.x;                     // plane k*B + b
+    const int k = n / B, b = n - k * B;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 27 * CO; i += PCB_THREADS) sV[i] = __ldg(V + i);
+    for (int i = tid; i < 4 * W * 27; i += PCB_THREADS) sD[i] = 0.f;
+    const size_t P = (size_t)H * W;
+    const float* gp = g_h + (size_t)n * P * CO;
+    const float* ib = img + (size_t)b * P * 3;
+    float* dm = dmask + (size_t)b * P * K + k;
+    float dbacc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) dbacc[o] = 0.f;
+    __syncthreads();
+    // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; then R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1)
+    const int n_steps = (H + 1) / 2 + 1;
+    for (int s = 0; s < n_steps; ++s) {
+        for (int x = tid; x < W; x += PCB_THREADS) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = 2 * s + h;
+                float* dst = sD + ((y & 3) * W + x) * 27;
+                if (y < H) {
+                    float4 g[CO4];
+                    const float* src = gp + ((size_t)y * W + x) * CO;
+#pragma unroll
+                    for (int j = 0; j < CO4; ++j) g[j] = ld4_stream(src + 4 * j);
+#pragma unroll
+                    for (int j = 0; j < CO4; ++j) {
+                        dbacc[4 * j] += g[j].x; dbacc[4 * j + 1] += g[j].y;
+                        dbacc[4 * j + 2] += g[j].z; dbacc[4 * j + 3] += g[j].w;
+                    }
+#pragma unroll
+                    for (int tc = 0; tc < 27; ++tc) {
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CO4; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(sV + tc * CO + 4 * j);
+                            a0 = fmaf(g[j].x, v.x, a0); a1 = fmaf(g[j].y, v.y, a1);
+                            a0 = fmaf(g[j].z, v.z, a0); a1 = fmaf(g[j].w, v.w, a1);
+                        }
+                        dst[tc] = a0 + a1;
+                    }
+                } else {
+#pragma unroll
+                    for (int tc = 0; tc < 27; ++tc) dst[tc] = 0.f;  // rows below the image contribute nothing
+                }
+            }
+        }
+        __syncthreads();
+        for (int x = tid; x < W; x += PCB_THREADS) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = 2 * s - 1 + h;
+                if (y < 0 || y >= H) continue;
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int yy = y + 1 - dy;  // D row of tap row dy; rows -1 and H hold zeros in the ring
+                    if (yy < 0) continue;
+                    const float* row = sD + ((yy & 3) * W) * 27;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int xx = x + 1 - dx;
+                        if (xx < 0 || xx >= W) continue;
+                        const float* d = row + xx * 27 + (3 * dy + dx) * 3;
+                        r0 += d[0]; r1 += d[1]; r2 += d[2];
+                    }
+                }
+                const size_t q = (size_t)y * W + x;
+                const float v = fmaf(__ldg(ib + q * 3 + 2), r2, fmaf(__ldg(ib + q * 3 + 1), r1, __ldg(ib + q * 3) * r0));
+                dm[q * K] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // db: thread partials -> warp (fixed xor tree) -> CTA (warp order) -> ws_db[n][CO]
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        float v = dbacc[o];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if ((tid & 31) == 0) sRed[(tid >> 5) * CO + o] = v;
+    }
+    __syncthreads();
+    for (int o = tid; o < CO; o += PCB_THREADS) {
+        float v = 0.f;
+        for (int w = 0; w < PCB_THREADS / 32; ++w) v += sRed[w * CO + o];
+        ws_db[(size_t)n * CO + o] = v;
+    }
+}
+
+// dV partials: warp = run of `run` pixels of sample b; lane = output channel (+32*c)
+template <int CCH>
+__global__ void __launch_bounds__(256) parts_conv_bwd_filter_kernel(const float* __restrict__ g_h,
+                                                                    const float* __restrict__ img,
+                                                                    const float* __restrict__ mask,
+                                                                    float* __restrict__ ws_dV, int B, int H, int W, int K,
+                                                                    int Co, int run, int runs_per_sample) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // global warp = (b, run index)
+    if (gw >= B * runs_per_sample) return;
+    const int b = gw / runs_per_sample, ri = gw - b * runs_per_sample;
+    const size_t P = (size_t)H * W;
+    const float* mb = mask + (size_t)b * P * K;
+    const float* ib = img + (size_t)b * P * 3;
+    float acc[27][CCH];
+#pragma unroll
+    for (int i = 0; i < 27; ++i)
+#pragma unroll
+        for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
+    const long long q_beg = (long long)ri * run, q_end = min((long long)P, q_beg + run);
+    for (long long q0 = q_beg; q0 < q_end; q0 += 32) {
+        const long long qm = q0 + lane;
+        int lab = -2;
+        float sv = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f;
+        if (qm < q_end) {
+            int nz = 0;
+            for (int kk = 0; kk < K; ++kk) {
+                const float v = __ldg(mb + qm * K + kk);
+                if (v != 0.f) {
+                    if (nz == 0) { lab = kk; sv = v; }
+                    ++nz;
+                }
+            }
+            if (nz > 1) lab = -1;
+            i0 = __ldg(ib + qm * 3); i1 = __ldg(ib + qm * 3 + 1); i2 = __ldg(ib + qm * 3 + 2);
+        }
+        const int cnt = (int)min(32ll, q_end - q0);
+        for (int j = 0; j < cnt; ++j) {
+            const int lj = __shfl_sync(0xffffffffu, lab, j);
+            if (lj == -2) continue;
+            const float sj = __shfl_sync(0xffffffffu, sv, j);
+            const float c0 = __shfl_sync(0xffffffffu, i0, j), c1 = __shfl_sync(0xffffffffu, i1, j),
+                        c2 = __shfl_sync(0xffffffffu, i2, j);
+            const long long q = q0 + j;
+            const int y = (int)(q / W), x = (int)(q - (long long)y * W);
+            const int k_beg = lj >= 0 ? lj : 0, k_end = lj >= 0 ? lj + 1 : K;
+            for (int kk = k_beg; kk < k_end; ++kk) {
+                float m = sj;
+                if (lj < 0) {
+                    m = __ldg(mb + q * K + kk);
+                    if (m == 0.f) continue;
+                }
+                // mask_parts: fl(image * mask) per channel
+                const float p0 = __fmul_rn(c0, m), p1 = __fmul_rn(c1, m), p2 = __fmul_rn(c2, m);
+                const float* gpl = g_h + ((size_t)kk * B + b) * P * Co;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3, dx = t - 3 * dy;
+                    const int yy = y + 1 - dy, xx = x + 1 - dx;  // output pixel p = q - off_t
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const float* gr = gpl + ((size_t)yy * W + xx) * Co;
+#pragma unroll
+                    for (int c = 0; c < CCH; ++c) {
+                        const int o = lane + 32 * c;
+                        const float g = o < Co ? __ldg(gr + o) : 0.f;
+                        acc[3 * t][c] = fmaf(p0, g, acc[3 * t][c]);
+                        acc[3 * t + 1][c] = fmaf(p1, g, acc[3 * t + 1][c]);
+                        acc[3 * t + 2][c] = fmaf(p2, g, acc[3 * t + 2][c]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; ++i)
+#pragma unroll
+        for (int c = 0; c < CCH; ++c) {
+            const int o = lane + 32 * c;
+            if (o < Co) ws_dV[((size_t)gw * 27 + i) * Co + o] = acc[i][c];
+        }
+}
+
+// out[i] = sum_r part[r][i] in a fixed order: thread j of a 256-thread CTA sums r = j, j+256, ..., then a tree
+__global__ void __launch_bounds__(256) fixed_order_sum_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                              int n_rows, int n_cols) {
+    __shared__ float s[256];
+    const int i = blockIdx.x;
+    float v = 0.f;
+    for (int r = threadIdx.x; r < n_rows; r += 256) v += part[(size_t)r * n_cols + i];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int m = 128; m >= 1; m >>= 1) {
+        if (threadIdx.x < m) s[threadIdx.x] += s[threadIdx.x + m];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[i] = s[0];
+}
+
+int pcb_run_len(int B, int P) {  // pixels per warp of the filter kernel: ~32 warps per SM over the chip
+    long long warps = 32ll * NUM_SMS;
+    long long per_sample = cdiv(warps, B > 0 ? B : 1);
+    long long run = cdiv(P, per_sample);
+    run = cdiv(run, 32) * 32;
+    return (int)(run < 32 ? 32 : run);
+}
+
 }  // namespace
 }  // namespace ups
 
@@ -178,4 +405,63 @@ extern "C" int ups_parts_conv_fwd(const float* img, const float* mask, const flo
     UPS_CUDA(cudaFuncSetAttribute(parts_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     parts_conv_fwd_kernel<<<grid, PC_THREADS, smem, st>>>(img, mask, V, bias, out_pm, B, H, W, K, Co, spc);
     return after_launch("parts_conv_fwd_kernel");
+}
+
+extern "C" size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co) {
+    if (B <= 0 || H <= 0 || W <= 0 || K < 1 || Co < 1) return 256;
+    const int P = H * W;
+    const int run = pcb_run_len(B, P);
+    const size_t runs = (size_t)B * cdiv(P, run);
+    return (runs * 27 * Co + (size_t)K * B * Co) * sizeof(float) + 256;
+}
+
+extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V, float* dmask,
+                                  float* dV, float* db, int B, int H, int W, int K, int C, int Co, void* ws, size_t ws_bytes,
+                                  void* stream) {
+    UPS_REQUIRE(g_out_pm && img && mask && V && dmask, "parts_conv_bwd: null pointer");
+    UPS_REQUIRE(B >= 0 && H > 0 && W > 0, "parts_conv_bwd: bad sizes B=%d H=%d W=%d", B, H, W);
+    UPS_REQUIRE(K >= 1 && K <= 32, "parts_conv_bwd: K=%d outside [1,32]", K);
+    UPS_REQUIRE(C == 3, "parts_conv_bwd: C=%d (the part images are 3-channel)", C);
+    UPS_REQUIRE(Co == 8 || Co == 16 || Co == 32 || Co == 64, "parts_conv_bwd: Co=%d must be 8, 16, 32 or 64", Co);
+    UPS_REQUIRE((long long)B * H * W * K < (1ll << 31), "parts_conv_bwd: K*B*H*W >= 2^31");
+    UPS_REQUIRE(aligned16(g_out_pm) && aligned16(V), "parts_conv_bwd: g_out and V must be 16-byte aligned");
+    if (B == 0) return UPS_OK;
+    const size_t need = ups_parts_conv_bwd_workspace_bytes(B, H, W, K, Co);
+    UPS_REQUIRE(ws != nullptr && ws_bytes >= need, "parts_conv_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    const int P = H * W;
+    const int run = pcb_run_len(B, P);
+    const int runs_per_sample = (int)cdiv(P, run);
+    float* ws_dV = reinterpret_cast<float*>(ws);
+    float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
+    cudaStream_t st = as_stream(stream);
+    const size_t smem = (size_t)(27 * Co + 4 * W * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
+    UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
+#define UPS_PCB(CO)                                                                                                  \
+    do {                                                                                                             \
+        UPS_CUDA(cudaFuncSetAttribute(parts_conv_bwd_data_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                                   \
+        parts_conv_bwd_data_kernel<CO><<<K * B, PCB_THREADS, smem, st>>>(g_out_pm, img, V, dmask, ws_db, B, H, W, K); \
+    } while (0)
+    if (Co == 8) UPS_PCB(8);
+    else if (Co == 16) UPS_PCB(16);
+    else if (Co == 32) UPS_PCB(32);
+    else UPS_PCB(64);
+#undef UPS_PCB
+    if (int rc = after_launch("parts_conv_bwd_data_kernel")) return rc;
+    if (dV != nullptr) {
+        const int n_warps = B * runs_per_sample;
+        const unsigned grid = (unsigned)cdiv(n_warps, 8);
+        if (Co <= 32)
+            parts_conv_bwd_filter_kernel<1><<<grid, 256, 0, st>>>(g_out_pm, img, mask, ws_dV, B, H, W, K, Co, run, runs_per_sample);
+        else
+            parts_conv_bwd_filter_kernel<2><<<grid, 256, 0, st>>>(g_out_pm, img, mask, ws_dV, B, H, W, K, Co, run, runs_per_sample);
+        if (int rc = after_launch("parts_conv_bwd_filter_kernel")) return rc;
+        fixed_order_sum_kernel<<<27 * Co, 256, 0, st>>>(ws_dV, dV, n_warps, 27 * Co);
+        if (int rc = after_launch("fixed_order_sum_kernel")) return rc;
+    }
+    if (db != nullptr) {
+        fixed_order_sum_kernel<<<Co, 256, 0, st>>>(ws_db, db, K * B, Co);
+        if (int rc = after_launch("fixed_order_sum_kernel")) return rc;
+    }
+    return UPS_OK;
 }

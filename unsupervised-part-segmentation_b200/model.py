@@ -114,7 +114,8 @@ def parts_conv2d(image, mask, V, b):
     `mask_parts(image, mask)` (cub/code/SB_model48i/model.py:176-187, :478) folded part-major by
     `nn.apply_partwise` (cub/code/nn.py:100-103) and fed to encoder_model's `nn.conv2d(x, config[0])`
     (model.py:40; cub/code/nn.py:617-664).  image [B,h,w,3], mask [B,h,w,parts], V [3,3,3,Co], b [Co]
-    -> [parts*B,h,w,Co] (row k*B+b), what the rest of `e_alpha` consumes inside apply_partwise.  Forward only."""
+    -> [parts*B,h,w,Co] (row k*B+b), what the rest of `e_alpha` consumes inside apply_partwise.  Differentiable in
+    mask, V and b (the image gets no gradient: the reference's inputs are placeholders)."""
     bs, h, w, n_features = image.shape
     mshape = list(mask.shape)
     assert mshape[0] == bs and mshape[1] == h and mshape[2] == w, mshape

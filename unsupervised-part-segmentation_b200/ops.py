@@ -774,5 +774,29 @@ def _parts_conv(image: Tensor, mask: Tensor, V: Tensor, bias: Tensor) -> Tensor:
     return out
 
 
+def _parts_conv_grad(g_out: Tensor, image: Tensor, mask: Tensor, V: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    g_out, image, mask, V = _f32(g_out), _f32(image), _f32(mask), _f32(V)
+    B, H, W, K = mask.shape
+    Cin, Co = image.shape[-1], V.shape[-1]
+    dmask, dV = torch.empty_like(mask), torch.empty_like(V)
+    db = torch.empty(Co, dtype=torch.float32, device=mask.device)
+    ws = _ws(C.parts_conv_bwd_workspace_bytes(B, H, W, K, Co), mask)
+    C.call("ups_parts_conv_bwd", g_out.data_ptr(), image.data_ptr(), mask.data_ptr(), V.data_ptr(), dmask.data_ptr(),
+           dV.data_ptr(), db.data_ptr(), B, H, W, K, Cin, Co, ws.data_ptr(), ws.numel(), _stream())
+    return dmask, dV, db
+
+
+parts_conv_grad = _op("parts_conv_grad", _parts_conv_grad,
+                      lambda g, i, m, v: (torch.empty_like(m), torch.empty_like(v), v.new_empty(v.shape[-1])))
+
+
+def _parts_conv_bwd(ctx, g):
+    if ctx.needs_input_grad[0]:
+        raise C.UpsError("ups::parts_conv: no gradient with respect to the image (the reference's inputs are placeholders)")
+    dmask, dV, db = parts_conv_grad(g, *ctx.saved_tensors)
+    return None, dmask, dV, db
+
+
 parts_conv = _op("parts_conv", _parts_conv,
-                 lambda i, m, v, b: i.new_empty(m.shape[-1] * m.shape[0], m.shape[1], m.shape[2], v.shape[-1]))
+                 lambda i, m, v, b: i.new_empty(m.shape[-1] * m.shape[0], m.shape[1], m.shape[2], v.shape[-1]),
+                 _parts_conv_bwd, lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1], inputs[2]))
