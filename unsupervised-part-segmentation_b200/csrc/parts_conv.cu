@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(PC_THREADS) parts_conv_fwd_kernel(const float*
 constexpr int PCB_THREADS = 128;
 
 template <int CO>
-__global__ void __launch_bounds__(PCB_THREADS) parts_conv_bwd_data_kernel(const float* __restrict__ g_h,
+__global__ void __launch_bounds__(PCB_THREADS, 3) parts_conv_bwd_data_kernel(const float* __restrict__ g_h,
                                                                           const float* __restrict__ img,
                                                                           const float* __restrict__ V,
                                                                           float* __restrict__ dmask,
@@ -178,13 +178,16 @@ __global__ void __launch_bounds__(PCB_THREADS) parts_conv_bwd_data_kernel(const 
                                                                           int K) {
     constexpr int CO4 = CO / 4;
     extern __shared__ float4 smem4[];
-    float* sV = reinterpret_cast<float*>(smem4);  // [27][CO]
-    float* sD = sV + 27 * CO;                     // ring [4][W][27]
-    float* sRed = sD + 4 * W * 27;                // [PCB_THREADS/32][CO] for the db reduction
-    const int n = blockIdx.x;                     // plane k*B + b
+    float* sVT = reinterpret_cast<float*>(smem4);  // [CO][28]: V transposed, (tap, channel) pair index fastest, [27] = 0
+    float* sD = sVT + 28 * CO;                     // ring [4][W][27]
+    float* sRed = sD + 4 * W * 27;                 // [PCB_THREADS/32][CO] for the db reduction
+    const int n = blockIdx.x;                      // plane k*B + b
     const int k = n / B, b = n - k * B;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 27 * CO; i += PCB_THREADS) sV[i] = __ldg(V + i);
+    for (int i = tid; i < 28 * CO; i += PCB_THREADS) {
+        const int o = i / 28, tc = i - o * 28;
+        sVT[i] = tc < 27 ? __ldg(V + tc * CO + o) : 0.f;
+    }
     for (int i = tid; i < 4 * W * 27; i += PCB_THREADS) sD[i] = 0.f;
     const size_t P = (size_t)H * W;
     const float* gp = g_h + (size_t)n * P * CO;
@@ -197,36 +200,58 @@ __global__ void __launch_bounds__(PCB_THREADS) parts_conv_bwd_data_kernel(const 
     // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; then R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1)
     const int n_steps = (H + 1) / 2 + 1;
     for (int s = 0; s < n_steps; ++s) {
+        const int ya = 2 * s, yb = 2 * s + 1;
         for (int x = tid; x < W; x += PCB_THREADS) {
+            float* dsta = sD + ((ya & 3) * W + x) * 27;
+            float* dstb = sD + ((yb & 3) * W + x) * 27;
+            if (ya < H) {
+                // both rows side by side: one 16-byte load of V feeds 4 packed FMAs of each row (row b = zeros past H)
+                float4 ga[CO4], gb[CO4];
+                const float* srca = gp + ((size_t)ya * W + x) * CO;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int y = 2 * s + h;
-                float* dst = sD + ((y & 3) * W + x) * 27;
-                if (y < H) {
-                    float4 g[CO4];
-                    const float* src = gp + ((size_t)y * W + x) * CO;
+                for (int j = 0; j < CO4; ++j) ga[j] = ld4_stream(srca + 4 * j);
 #pragma unroll
-                    for (int j = 0; j < CO4; ++j) g[j] = ld4_stream(src + 4 * j);
+                for (int j = 0; j < CO4; ++j)
+                    gb[j] = yb < H ? ld4_stream(srca + (size_t)W * CO + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < CO4; ++j) {
-                        dbacc[4 * j] += g[j].x; dbacc[4 * j + 1] += g[j].y;
-                        dbacc[4 * j + 2] += g[j].z; dbacc[4 * j + 3] += g[j].w;
-                    }
-#pragma unroll
-                    for (int tc = 0; tc < 27; ++tc) {
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < CO4; ++j) {
-                            const float4 v = *reinterpret_cast<const float4*>(sV + tc * CO + 4 * j);
-                            a0 = fmaf(g[j].x, v.x, a0); a1 = fmaf(g[j].y, v.y, a1);
-                            a0 = fmaf(g[j].z, v.z, a0); a1 = fmaf(g[j].w, v.w, a1);
-                        }
-                        dst[tc] = a0 + a1;
-                    }
-                } else {
-#pragma unroll
-                    for (int tc = 0; tc < 27; ++tc) dst[tc] = 0.f;  // rows below the image contribute nothing
+                for (int j = 0; j < CO4; ++j) {
+                    dbacc[4 * j] += ga[j].x + gb[j].x; dbacc[4 * j + 1] += ga[j].y + gb[j].y;
+                    dbacc[4 * j + 2] += ga[j].z + gb[j].z; dbacc[4 * j + 3] += ga[j].w + gb[j].w;
                 }
+                pk::f2 acca[14], accb[14];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) acca[i] = accb[i] = 0ull;  // +0.0f pairs
+#pragma unroll
+                for (int j = 0; j < CO4; ++j) {
+                    const float av[4] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w};
+                    const float bv[4] = {gb[j].x, gb[j].y, gb[j].z, gb[j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const pk::f2 sa = pk::splat(av[e]), sb = pk::splat(bv[e]);
+                        const ulonglong2* vr = reinterpret_cast<const ulonglong2*>(sVT + (4 * j + e) * 28);
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) {
+                            const ulonglong2 v = vr[q];  // (V[tc], V[tc+1]), (V[tc+2], V[tc+3])
+                            acca[2 * q] = pk::fma2(sa, v.x, acca[2 * q]);
+                            accb[2 * q] = pk::fma2(sb, v.x, accb[2 * q]);
+                            acca[2 * q + 1] = pk::fma2(sa, v.y, acca[2 * q + 1]);
+                            accb[2 * q + 1] = pk::fma2(sb, v.y, accb[2 * q + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    float lo, hi;
+                    pk::unpack(acca[i], lo, hi);
+                    dsta[2 * i] = lo;
+                    if (2 * i + 1 < 27) dsta[2 * i + 1] = hi;
+                    pk::unpack(accb[i], lo, hi);
+                    dstb[2 * i] = lo;
+                    if (2 * i + 1 < 27) dstb[2 * i + 1] = hi;
+                }
+            } else {
+#pragma unroll
+                for (int tc = 0; tc < 27; ++tc) dsta[tc] = dstb[tc] = 0.f;  // rows below the image contribute nothing
             }
         }
         __syncthreads();
@@ -272,7 +297,9 @@ __global__ void __launch_bounds__(PCB_THREADS) parts_conv_bwd_data_kernel(const 
     }
 }
 
-// dV partials: warp = run of `run` pixels of sample b; lane = output channel (+32*c)
+// dV partials: warp = run of `run` pixels of sample b (run % 32 == 0); lane = output channel (+32*c).
+// Per pixel q with label k: 9 gathers g_h[k-plane][q - off_t][lane] and 27 FMAs; (y, x), the tap offsets and the
+// tap validity come from incremental integer updates (no division, no 64-bit arithmetic in the loop).
 template <int CCH>
 __global__ void __launch_bounds__(256) parts_conv_bwd_filter_kernel(const float* __restrict__ g_h,
                                                                     const float* __restrict__ img,
@@ -283,65 +310,73 @@ __global__ void __launch_bounds__(256) parts_conv_bwd_filter_kernel(const float*
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // global warp = (b, run index)
     if (gw >= B * runs_per_sample) return;
     const int b = gw / runs_per_sample, ri = gw - b * runs_per_sample;
-    const size_t P = (size_t)H * W;
+    const int P = H * W;
     const float* mb = mask + (size_t)b * P * K;
     const float* ib = img + (size_t)b * P * 3;
+    const size_t plane = (size_t)P * Co;
+    const float* gb = g_h + (size_t)b * plane;  // plane kk of this sample: gb + kk*B*plane
     float acc[27][CCH];
 #pragma unroll
     for (int i = 0; i < 27; ++i)
 #pragma unroll
         for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
-    const long long q_beg = (long long)ri * run, q_end = min((long long)P, q_beg + run);
-    for (long long q0 = q_beg; q0 < q_end; q0 += 32) {
-        const long long qm = q0 + lane;
+    int toff[9];  // element offset of the output pixel q - off_t relative to q
+#pragma unroll
+    for (int t = 0; t < 9; ++t) toff[t] = ((1 - t / 3) * W + (1 - t % 3)) * Co;
+    const int q_beg = ri * run, q_end = min(P, q_beg + run);
+    int y = q_beg / W, x = q_beg - y * W;
+    for (int q0 = q_beg; q0 < q_end; q0 += 32) {
+        const int qm = q0 + lane;
         int lab = -2;
         float sv = 0.f, i0 = 0.f, i1 = 0.f, i2 = 0.f;
         if (qm < q_end) {
             int nz = 0;
             for (int kk = 0; kk < K; ++kk) {
-                const float v = __ldg(mb + qm * K + kk);
+                const float v = __ldg(mb + (size_t)qm * K + kk);
                 if (v != 0.f) {
                     if (nz == 0) { lab = kk; sv = v; }
                     ++nz;
                 }
             }
             if (nz > 1) lab = -1;
-            i0 = __ldg(ib + qm * 3); i1 = __ldg(ib + qm * 3 + 1); i2 = __ldg(ib + qm * 3 + 2);
+            i0 = __ldg(ib + (size_t)qm * 3); i1 = __ldg(ib + (size_t)qm * 3 + 1); i2 = __ldg(ib + (size_t)qm * 3 + 2);
         }
-        const int cnt = (int)min(32ll, q_end - q0);
-        for (int j = 0; j < cnt; ++j) {
+        const int cnt = min(32, q_end - q0);
+        for (int j = 0; j < cnt; ++j, ++x) {
+            if (x == W) { x = 0; ++y; }
             const int lj = __shfl_sync(0xffffffffu, lab, j);
             if (lj == -2) continue;
             const float sj = __shfl_sync(0xffffffffu, sv, j);
             const float c0 = __shfl_sync(0xffffffffu, i0, j), c1 = __shfl_sync(0xffffffffu, i1, j),
                         c2 = __shfl_sync(0xffffffffu, i2, j);
-            const long long q = q0 + j;
-            const int y = (int)(q / W), x = (int)(q - (long long)y * W);
+            // output pixel of tap (dy,dx) is (y+1-dy, x+1-dx): row/column validity
+            const bool vy[3] = {y + 1 < H, true, y > 0};
+            const bool vx[3] = {x + 1 < W, true, x > 0};
+            const int qoff = (q0 + j) * Co + lane;
             const int k_beg = lj >= 0 ? lj : 0, k_end = lj >= 0 ? lj + 1 : K;
             for (int kk = k_beg; kk < k_end; ++kk) {
                 float m = sj;
                 if (lj < 0) {
-                    m = __ldg(mb + q * K + kk);
+                    m = __ldg(mb + (size_t)(q0 + j) * K + kk);
                     if (m == 0.f) continue;
                 }
                 // mask_parts: fl(image * mask) per channel
                 const float p0 = __fmul_rn(c0, m), p1 = __fmul_rn(c1, m), p2 = __fmul_rn(c2, m);
-                const float* gpl = g_h + ((size_t)kk * B + b) * P * Co;
+                const float* gq = gb + (size_t)kk * B * plane + qoff;
+                float g[9][CCH];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int dy = t / 3, dx = t - 3 * dy;
-                    const int yy = y + 1 - dy, xx = x + 1 - dx;  // output pixel p = q - off_t
-                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                    const float* gr = gpl + ((size_t)yy * W + xx) * Co;
+                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                    for (int c = 0; c < CCH; ++c)
+                        g[t][c] = (vy[t / 3] && vx[t % 3] && lane + 32 * c < Co) ? __ldg(gq + toff[t] + 32 * c) : 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
 #pragma unroll
                     for (int c = 0; c < CCH; ++c) {
-                        const int o = lane + 32 * c;
-                        const float g = o < Co ? __ldg(gr + o) : 0.f;
-                        acc[3 * t][c] = fmaf(p0, g, acc[3 * t][c]);
-                        acc[3 * t + 1][c] = fmaf(p1, g, acc[3 * t + 1][c]);
-                        acc[3 * t + 2][c] = fmaf(p2, g, acc[3 * t + 2][c]);
+                        acc[3 * t][c] = fmaf(p0, g[t][c], acc[3 * t][c]);
+                        acc[3 * t + 1][c] = fmaf(p1, g[t][c], acc[3 * t + 1][c]);
+                        acc[3 * t + 2][c] = fmaf(p2, g[t][c], acc[3 * t + 2][c]);
                     }
-                }
             }
         }
     }
@@ -370,8 +405,8 @@ __global__ void __launch_bounds__(256) fixed_order_sum_kernel(const float* __res
     if (threadIdx.x == 0) out[i] = s[0];
 }
 
-int pcb_run_len(int B, int P) {  // pixels per warp of the filter kernel: ~32 warps per SM over the chip
-    long long warps = 32ll * NUM_SMS;
+int pcb_run_len(int B, int P) {  // pixels per warp of the filter kernel: ~96 warps per SM over the chip (3-4 waves)
+    long long warps = 96ll * NUM_SMS;
     long long per_sample = cdiv(warps, B > 0 ? B : 1);
     long long run = cdiv(P, per_sample);
     run = cdiv(run, 32) * 32;
@@ -434,7 +469,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     float* ws_dV = reinterpret_cast<float*>(ws);
     float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
     cudaStream_t st = as_stream(stream);
-    const size_t smem = (size_t)(27 * Co + 4 * W * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
+    const size_t smem = (size_t)(28 * Co + 4 * W * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
 #define UPS_PCB(CO)                                                                                                  \
     do {                                                                                                             \
