@@ -268,12 +268,15 @@ size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co);
  */
 int ups_parts_conv_fwd(const float* img, const float* mask, const float* V, const float* bias, float* out_pm, int B,
                        int H, int W, int K, int C, int Co, void* stream);
-/* backward: g_out_pm [K*B,H,W,Co] -> dmask [B,H,W,K] (the cotangent of the encoding mask: feed it, plus the loss terms,
- * to ups_part_softmax_bwd), dV [9,3,Co] (may be NULL), db [Co] (may be NULL).  The image gets no gradient (the
- * reference's inputs are placeholders, cub/code/SB_model48i/model.py:316-327).  Co in {8,16,32,64}.
- * ws from ups_parts_conv_bwd_workspace_bytes (per-warp / per-plane partial sums, reduced in a fixed order). */
-int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V, float* dmask, float* dV,
-                       float* db, int B, int H, int W, int K, int C, int Co, void* ws, size_t ws_bytes, void* stream);
+/* backward: g_out_pm [K*B,H,W,Co] -> dmask [B,H,W,K] (the cotangent of the encoding mask), dV [9,3,Co] (may be NULL),
+ * db [Co] (may be NULL).  probs != NULL: the mask is ST(hard_max(probs)); dmask (+ g_extra, the cotangent reaching the
+ * probabilities from elsewhere, may be NULL) goes through the straight-through estimator and the softmax backward and
+ * `dmask` receives dlogits.  The image gets no gradient (the reference's inputs are placeholders,
+ * cub/code/SB_model48i/model.py:316-327).  Co in {8,16,32,64}.
+ * ws from ups_parts_conv_bwd_workspace_bytes (plane-major dmask staging + partial sums reduced in a fixed order). */
+int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V, const float* probs,
+                       const float* g_extra, float* dmask, float* dV, float* db, int B, int H, int W, int K, int C, int Co,
+                       void* ws, size_t ws_bytes, void* stream);
 size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
 
 #ifdef __cplusplus

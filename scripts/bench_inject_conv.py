@@ -69,9 +69,9 @@ def measure(batch=256, size=128, parts=16, library=True, once=False, iters=10):
     g_pm = torch.empty(K * B, H, W, Co, device=dev).normal_(generator=g)
     dm1, dVe, dbe = torch.empty_like(l0), torch.empty_like(Ve), torch.empty_like(be)
     ws_pc = torch.empty(C.parts_conv_bwd_workspace_bytes(B, H, W, K, Co), dtype=torch.uint8, device=dev)
-    calls["ups_parts_conv_bwd (g [K*B,P,Co] -> dmask, dV, db)"] = (
-        lambda: C.call("ups_parts_conv_bwd", p(g_pm), p(img), p(mh), p(Ve), p(dm1), p(dVe), p(dbe), B, H, W, K, 3, Co,
-                       p(ws_pc), ws_pc.numel(), st), n_pix * 4 * (K * Co + 3 + 2 * K))
+    calls["ups_parts_conv_bwd (g [K*B,P,Co], g_m1 -> dl1, dV, db)"] = (
+        lambda: C.call("ups_parts_conv_bwd", p(g_pm), p(img), p(mh), p(Ve), p(m0), p(g_m0), p(dm1), p(dVe), p(dbe),
+                       B, H, W, K, 3, Co, p(ws_pc), ws_pc.numel(), st), n_pix * 4 * (K * Co + 3 + 4 * K))
     C.call("ups_part_softmax_fwd", p(l0), p(m0), p(labels), p(mh), n_pix, K, st)
     C.call("ups_inject_conv_table_fwd", p(feat), p(V), p(G), B, K, F, Co, st)
     if not a.no_library:

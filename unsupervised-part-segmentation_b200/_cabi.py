@@ -60,7 +60,7 @@ _SIGS = {
     "ups_inject_conv_table_bwd": [c_f] * 5 + [c_i] * 4 + [c_f],
     "ups_inject_conv_fwd": [c_f] * 4 + [c_i] * 5 + [c_f],
     "ups_parts_conv_fwd": [c_f] * 5 + [c_i] * 6 + [c_f],
-    "ups_parts_conv_bwd": [c_f] * 7 + [c_i] * 6 + [c_f, c_sz, c_f],
+    "ups_parts_conv_bwd": [c_f] * 9 + [c_i] * 6 + [c_f, c_sz, c_f],
     "ups_inject_conv_bwd": [c_f] * 8 + [c_i] * 5 + [c_f, c_sz, c_f],
 }
 

@@ -173,7 +173,7 @@ template <int CO>
 __global__ void __launch_bounds__(PCB_THREADS, 3) parts_conv_bwd_data_kernel(const float* __restrict__ g_h,
                                                                           const float* __restrict__ img,
                                                                           const float* __restrict__ V,
-                                                                          float* __restrict__ dmask,
+                                                                          float* __restrict__ dm_planes,
                                                                           float* __restrict__ ws_db, int B, int H, int W,
                                                                           int K) {
     constexpr int CO4 = CO / 4;
@@ -192,13 +192,27 @@ __global__ void __launch_bounds__(PCB_THREADS, 3) parts_conv_bwd_data_kernel(con
     const size_t P = (size_t)H * W;
     const float* gp = g_h + (size_t)n * P * CO;
     const float* ib = img + (size_t)b * P * 3;
-    float* dm = dmask + (size_t)b * P * K + k;
+    float* dm = dm_planes + ((size_t)b * K + k) * P;  // plane-major [B][K][P]: coalesced; transposed by the finish kernel
     float dbacc[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) dbacc[o] = 0.f;
     __syncthreads();
-    // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; then R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1)
+    // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; then R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1).
+    // The g_h rows of step s+1 are requested right after the D values of step s are formed, so the loads fly
+    // under the ring stores, the two barriers and the R phase.  (Columns beyond the block size, W > 128, reload.)
     const int n_steps = (H + 1) / 2 + 1;
+    const bool one_col = W <= PCB_THREADS;
+    float4 ga[CO4], gb[CO4];
+    auto load_rows = [&](int s, int x) {
+        const int ya = 2 * s, yb = 2 * s + 1;
+        const float* srca = gp + ((size_t)ya * W + x) * CO;
+#pragma unroll
+        for (int j = 0; j < CO4; ++j) ga[j] = (ya < H && x < W) ? ld4_stream(srca + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < CO4; ++j)
+            gb[j] = (yb < H && x < W) ? ld4_stream(srca + (size_t)W * CO + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (one_col) load_rows(0, tid);
     for (int s = 0; s < n_steps; ++s) {
         const int ya = 2 * s, yb = 2 * s + 1;
         for (int x = tid; x < W; x += PCB_THREADS) {
@@ -206,53 +220,68 @@ __global__ void __launch_bounds__(PCB_THREADS, 3) parts_conv_bwd_data_kernel(con
             float* dstb = sD + ((yb & 3) * W + x) * 27;
             if (ya < H) {
                 // both rows side by side: one 16-byte load of V feeds 4 packed FMAs of each row (row b = zeros past H)
-                float4 ga[CO4], gb[CO4];
-                const float* srca = gp + ((size_t)ya * W + x) * CO;
-#pragma unroll
-                for (int j = 0; j < CO4; ++j) ga[j] = ld4_stream(srca + 4 * j);
-#pragma unroll
-                for (int j = 0; j < CO4; ++j)
-                    gb[j] = yb < H ? ld4_stream(srca + (size_t)W * CO + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!one_col) load_rows(s, x);
 #pragma unroll
                 for (int j = 0; j < CO4; ++j) {
                     dbacc[4 * j] += ga[j].x + gb[j].x; dbacc[4 * j + 1] += ga[j].y + gb[j].y;
                     dbacc[4 * j + 2] += ga[j].z + gb[j].z; dbacc[4 * j + 3] += ga[j].w + gb[j].w;
                 }
-                pk::f2 acca[14], accb[14];
+                // the 28 (tap, channel) columns in two halves of 16 and 12: 16 packed accumulators live at a time
 #pragma unroll
-                for (int i = 0; i < 14; ++i) acca[i] = accb[i] = 0ull;  // +0.0f pairs
+                for (int half = 0; half < 2; ++half) {
+                    const int q0 = 4 * half, nq = half ? 3 : 4;
+                    pk::f2 acca[8], accb[8];
 #pragma unroll
-                for (int j = 0; j < CO4; ++j) {
-                    const float av[4] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w};
-                    const float bv[4] = {gb[j].x, gb[j].y, gb[j].z, gb[j].w};
+                    for (int i = 0; i < 8; ++i) acca[i] = accb[i] = 0ull;  // +0.0f pairs
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const pk::f2 sa = pk::splat(av[e]), sb = pk::splat(bv[e]);
-                        const ulonglong2* vr = reinterpret_cast<const ulonglong2*>(sVT + (4 * j + e) * 28);
+                    for (int j = 0; j < CO4; ++j) {
+                        const float av[4] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w};
+                        const float bv[4] = {gb[j].x, gb[j].y, gb[j].z, gb[j].w};
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) {
-                            const ulonglong2 v = vr[q];  // (V[tc], V[tc+1]), (V[tc+2], V[tc+3])
-                            acca[2 * q] = pk::fma2(sa, v.x, acca[2 * q]);
-                            accb[2 * q] = pk::fma2(sb, v.x, accb[2 * q]);
-                            acca[2 * q + 1] = pk::fma2(sa, v.y, acca[2 * q + 1]);
-                            accb[2 * q + 1] = pk::fma2(sb, v.y, accb[2 * q + 1]);
+                        for (int e = 0; e < 4; ++e) {
+                            const pk::f2 sa = pk::splat(av[e]), sb = pk::splat(bv[e]);
+                            const ulonglong2* vr = reinterpret_cast<const ulonglong2*>(sVT + (4 * j + e) * 28) + q0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (q < nq) {
+                                    const ulonglong2 v = vr[q];  // (V[tc], V[tc+1]), (V[tc+2], V[tc+3])
+                                    acca[2 * q] = pk::fma2(sa, v.x, acca[2 * q]);
+                                    accb[2 * q] = pk::fma2(sb, v.x, accb[2 * q]);
+                                    acca[2 * q + 1] = pk::fma2(sa, v.y, acca[2 * q + 1]);
+                                    accb[2 * q + 1] = pk::fma2(sb, v.y, accb[2 * q + 1]);
+                                }
+                            }
                         }
                     }
-                }
+                    if (half == 1 && one_col) load_rows(s + 1, x);  // next step's rows: in flight until the next D phase
 #pragma unroll
-                for (int i = 0; i < 14; ++i) {
-                    float lo, hi;
-                    pk::unpack(acca[i], lo, hi);
-                    dsta[2 * i] = lo;
-                    if (2 * i + 1 < 27) dsta[2 * i + 1] = hi;
-                    pk::unpack(accb[i], lo, hi);
-                    dstb[2 * i] = lo;
-                    if (2 * i + 1 < 27) dstb[2 * i + 1] = hi;
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < 2 * nq) {
+                            const int tc = 2 * (2 * q0 + i);
+                            float lo, hi;
+                            pk::unpack(acca[i], lo, hi);
+                            dsta[tc] = lo;
+                            if (tc + 1 < 27) dsta[tc + 1] = hi;
+                            pk::unpack(accb[i], lo, hi);
+                            dstb[tc] = lo;
+                            if (tc + 1 < 27) dstb[tc + 1] = hi;
+                        }
+                    }
                 }
             } else {
 #pragma unroll
                 for (int tc = 0; tc < 27; ++tc) dsta[tc] = dstb[tc] = 0.f;  // rows below the image contribute nothing
             }
+        }
+        // the image pixels of the two R rows: requested before the barrier, used after it
+        float im[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int y = 2 * s - 1 + h;
+            const bool ok = one_col && tid < W && y >= 0 && y < H;
+            const size_t q = (size_t)(ok ? y : 0) * W + (ok ? tid : 0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) im[h][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
         }
         __syncthreads();
         for (int x = tid; x < W; x += PCB_THREADS) {
@@ -275,8 +304,9 @@ __global__ void __launch_bounds__(PCB_THREADS, 3) parts_conv_bwd_data_kernel(con
                     }
                 }
                 const size_t q = (size_t)y * W + x;
-                const float v = fmaf(__ldg(ib + q * 3 + 2), r2, fmaf(__ldg(ib + q * 3 + 1), r1, __ldg(ib + q * 3) * r0));
-                dm[q * K] = v;
+                float c0 = im[h][0], c1 = im[h][1], c2 = im[h][2];
+                if (!one_col) { c0 = __ldg(ib + q * 3); c1 = __ldg(ib + q * 3 + 1); c2 = __ldg(ib + q * 3 + 2); }
+                dm[q] = fmaf(c2, r2, fmaf(c1, r1, c0 * r0));
             }
         }
         __syncthreads();
@@ -389,6 +419,43 @@ __global__ void __launch_bounds__(256) parts_conv_bwd_filter_kernel(const float*
         }
 }
 
+// dm_planes [B][K][P] -> dmask [B][P][K]; with probs: (+ g_extra) through the straight-through estimator (identity)
+// and the softmax backward -> dlogits.  One thread per pixel; plane reads and the [P][K] writes are both coalesced
+// per warp (32 pixels x 4 bytes per plane; K*4 contiguous bytes per thread).
+template <int KP>
+__global__ void __launch_bounds__(256) parts_conv_bwd_finish_kernel(const float* __restrict__ dm_planes,
+                                                                    const float* __restrict__ probs,
+                                                                    const float* __restrict__ g_extra,
+                                                                    float* __restrict__ dmask, int B, int P, int K) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * P) return;
+    const size_t b = i / P, q = i - b * P;
+    const float* src = dm_planes + b * K * P + q;
+    float d[KP], p[KP];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        d[k] = k < K ? __ldcs(src + (size_t)k * P) : 0.f;
+        if (k < K && g_extra != nullptr) d[k] += __ldg(g_extra + i * K + k);
+        p[k] = (k < K && probs != nullptr) ? __ldg(probs + i * K + k) : 0.f;
+        dot = fmaf(d[k], p[k], dot);
+    }
+    if (probs != nullptr) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) d[k] = p[k] * (d[k] - dot);
+    }
+    float* dst = dmask + i * K;
+    if ((K & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < KP; k += 4)
+            if (k < K) st4_stream(dst + k, make_float4(d[k], d[k + 1], d[k + 2], d[k + 3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) dst[k] = d[k];
+    }
+}
+
 // out[i] = sum_r part[r][i] in a fixed order: thread j of a 256-thread CTA sums r = j, j+256, ..., then a tree
 __global__ void __launch_bounds__(256) fixed_order_sum_kernel(const float* __restrict__ part, float* __restrict__ out,
                                                               int n_rows, int n_cols) {
@@ -447,19 +514,19 @@ extern "C" size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K,
     const int P = H * W;
     const int run = pcb_run_len(B, P);
     const size_t runs = (size_t)B * cdiv(P, run);
-    return (runs * 27 * Co + (size_t)K * B * Co) * sizeof(float) + 256;
+    return (runs * 27 * Co + (size_t)K * B * Co + (size_t)B * K * P) * sizeof(float) + 256;
 }
 
-extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V, float* dmask,
-                                  float* dV, float* db, int B, int H, int W, int K, int C, int Co, void* ws, size_t ws_bytes,
-                                  void* stream) {
+extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mask, const float* V,
+                                  const float* probs, const float* g_extra, float* dmask, float* dV, float* db, int B,
+                                  int H, int W, int K, int C, int Co, void* ws, size_t ws_bytes, void* stream) {
     UPS_REQUIRE(g_out_pm && img && mask && V && dmask, "parts_conv_bwd: null pointer");
     UPS_REQUIRE(B >= 0 && H > 0 && W > 0, "parts_conv_bwd: bad sizes B=%d H=%d W=%d", B, H, W);
     UPS_REQUIRE(K >= 1 && K <= 32, "parts_conv_bwd: K=%d outside [1,32]", K);
     UPS_REQUIRE(C == 3, "parts_conv_bwd: C=%d (the part images are 3-channel)", C);
     UPS_REQUIRE(Co == 8 || Co == 16 || Co == 32 || Co == 64, "parts_conv_bwd: Co=%d must be 8, 16, 32 or 64", Co);
     UPS_REQUIRE((long long)B * H * W * K < (1ll << 31), "parts_conv_bwd: K*B*H*W >= 2^31");
-    UPS_REQUIRE(aligned16(g_out_pm) && aligned16(V), "parts_conv_bwd: g_out and V must be 16-byte aligned");
+    UPS_REQUIRE(aligned16(g_out_pm) && aligned16(V) && aligned16(dmask), "parts_conv_bwd: g_out, V and dmask must be 16-byte aligned");
     if (B == 0) return UPS_OK;
     const size_t need = ups_parts_conv_bwd_workspace_bytes(B, H, W, K, Co);
     UPS_REQUIRE(ws != nullptr && ws_bytes >= need, "parts_conv_bwd: workspace %zu < %zu bytes", ws_bytes, need);
@@ -468,6 +535,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     const int runs_per_sample = (int)cdiv(P, run);
     float* ws_dV = reinterpret_cast<float*>(ws);
     float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
+    float* dm_planes = ws_db + (size_t)K * B * Co;
     cudaStream_t st = as_stream(stream);
     const size_t smem = (size_t)(28 * Co + 4 * W * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
@@ -475,7 +543,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     do {                                                                                                             \
         UPS_CUDA(cudaFuncSetAttribute(parts_conv_bwd_data_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       (int)smem));                                                                   \
-        parts_conv_bwd_data_kernel<CO><<<K * B, PCB_THREADS, smem, st>>>(g_out_pm, img, V, dmask, ws_db, B, H, W, K); \
+        parts_conv_bwd_data_kernel<CO><<<K * B, PCB_THREADS, smem, st>>>(g_out_pm, img, V, dm_planes, ws_db, B, H, W, K); \
     } while (0)
     if (Co == 8) UPS_PCB(8);
     else if (Co == 16) UPS_PCB(16);
@@ -483,6 +551,14 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     else UPS_PCB(64);
 #undef UPS_PCB
     if (int rc = after_launch("parts_conv_bwd_data_kernel")) return rc;
+    {
+        const unsigned grid = (unsigned)cdiv((long long)B * P, 256);
+        if (K <= 8) parts_conv_bwd_finish_kernel<8><<<grid, 256, 0, st>>>(dm_planes, probs, g_extra, dmask, B, P, K);
+        else if (K <= 16) parts_conv_bwd_finish_kernel<16><<<grid, 256, 0, st>>>(dm_planes, probs, g_extra, dmask, B, P, K);
+        else if (K <= 24) parts_conv_bwd_finish_kernel<24><<<grid, 256, 0, st>>>(dm_planes, probs, g_extra, dmask, B, P, K);
+        else parts_conv_bwd_finish_kernel<32><<<grid, 256, 0, st>>>(dm_planes, probs, g_extra, dmask, B, P, K);
+        if (int rc = after_launch("parts_conv_bwd_finish_kernel")) return rc;
+    }
     if (dV != nullptr) {
         const int n_warps = B * runs_per_sample;
         const unsigned grid = (unsigned)cdiv(n_warps, 8);

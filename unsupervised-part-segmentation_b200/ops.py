@@ -781,8 +781,8 @@ def _parts_conv_grad(g_out: Tensor, image: Tensor, mask: Tensor, V: Tensor) -> T
     dmask, dV = torch.empty_like(mask), torch.empty_like(V)
     db = torch.empty(Co, dtype=torch.float32, device=mask.device)
     ws = _ws(C.parts_conv_bwd_workspace_bytes(B, H, W, K, Co), mask)
-    C.call("ups_parts_conv_bwd", g_out.data_ptr(), image.data_ptr(), mask.data_ptr(), V.data_ptr(), dmask.data_ptr(),
-           dV.data_ptr(), db.data_ptr(), B, H, W, K, Cin, Co, ws.data_ptr(), ws.numel(), _stream())
+    C.call("ups_parts_conv_bwd", g_out.data_ptr(), image.data_ptr(), mask.data_ptr(), V.data_ptr(), None, None,
+           dmask.data_ptr(), dV.data_ptr(), db.data_ptr(), B, H, W, K, Cin, Co, ws.data_ptr(), ws.numel(), _stream())
     return dmask, dV, db
 
 
