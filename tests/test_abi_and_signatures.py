@@ -56,6 +56,34 @@ def test_workspace_query_and_error_paths(ups):
     assert C.launch_count() == 0
 
 
+def test_n4_error_paths_without_a_gpu(ups):
+    """The first-convolution entry points validate sizes before touching the device."""
+    C = ups._cabi
+    assert C.inject_conv_workspace_bytes(256, 128, 128, 16, 32) > 256 * 9 * 16 * 32 * 4
+    assert C.parts_conv_bwd_workspace_bytes(256, 128, 128, 16, 32) > 256 * 16 * 128 * 128 * 4
+    with pytest.raises(C.UpsError, match="null pointer"):
+        C.call("ups_inject_conv_fwd", None, None, None, None, 1, 8, 8, 4, 8, None)
+    with pytest.raises(C.UpsError, match="Co=6"):
+        C.call("ups_inject_conv_fwd", 16, 16, 16, 16, 1, 8, 8, 4, 6, None)
+    with pytest.raises(C.UpsError, match="K=33"):
+        C.call("ups_inject_conv_bwd", 16, 16, 16, None, None, 16, 16, None, 1, 8, 8, 33, 8, None, 0, None)
+    with pytest.raises(C.UpsError, match="workspace"):
+        C.call("ups_inject_conv_bwd", 16, 16, 16, None, None, 16, 16, None, 1, 8, 8, 4, 8, None, 0, None)
+    with pytest.raises(C.UpsError, match="does not fit shared memory"):
+        C.call("ups_inject_conv_bwd", 16, 16, 16, None, None, 16, 16, None, 1, 8, 8, 32, 128, 16, 1 << 30, None)
+    with pytest.raises(C.UpsError, match="3-channel"):
+        C.call("ups_parts_conv_fwd", 16, 16, 16, 16, 16, 1, 8, 8, 4, 4, 8, None)
+    with pytest.raises(C.UpsError, match="Co=12"):
+        C.call("ups_parts_conv_bwd", 16, 16, 16, 16, None, None, 16, None, None, 1, 8, 8, 4, 3, 12, None, 0, None)
+    assert C.launch_count() == 0
+    with pytest.raises(AssertionError):                                 # feature / mask part counts differ
+        ups.inject_conv2d(torch.zeros(2, 4, 6), torch.zeros(2, 8, 8, 5), torch.zeros(3, 3, 11, 8), torch.zeros(8))
+    with pytest.raises(AssertionError):                                 # filter input channels != F + parts
+        ups.inject_conv2d(torch.zeros(2, 5, 6), torch.zeros(2, 8, 8, 5), torch.zeros(3, 3, 10, 8), torch.zeros(8))
+    with pytest.raises(AssertionError):                                 # image / mask spatial sizes differ (model.py:180)
+        ups.parts_conv2d(torch.zeros(2, 8, 8, 3), torch.zeros(2, 8, 4, 5), torch.zeros(3, 3, 3, 8), torch.zeros(8))
+
+
 REF_SIGNATURES = {
     # helper: parameter names (and defaults) in the reference, with file:line
     "softmax": "(x, spatial=False)",                                  # cub/code/nn.py:58
