@@ -181,8 +181,9 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
     constexpr int CO4 = CO / 4;
     extern __shared__ float4 smem4[];
     float* sVT = reinterpret_cast<float*>(smem4);  // [CO][28]: V transposed, (tap, channel) pair index fastest, [27] = 0
-    float* sD = sVT + 28 * CO;                     // ring [4][W][27]
-    float* sRed = sD + 4 * W * 27;                 // [PCB_THREADS/32][CO] for the db reduction
+    float* sD = sVT + 28 * CO;                     // ring [6][W+2][27]; columns 0 and W+1 stay zero
+    const int Wr = W + 2;
+    float* sRed = sD + 6 * Wr * 27;                // [PCB_THREADS/32][CO] for the db reduction
     const int n = blockIdx.x;                      // plane k*B + b
     const int k = n / B, b = n - k * B;
     const int tid = threadIdx.x;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
         const int o = i / 28, tc = i - o * 28;
         sVT[i] = tc < 27 ? __ldg(V + tc * CO + o) : 0.f;
     }
-    for (int i = tid; i < 4 * W * 27; i += PCB_THREADS) sD[i] = 0.f;
+    for (int i = tid; i < 6 * Wr * 27; i += PCB_THREADS) sD[i] = 0.f;
     const size_t P = (size_t)H * W;
     const float* gp = g_h + (size_t)n * P * CO;
     const float* ib = img + (size_t)b * P * 3;
@@ -199,9 +200,11 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
 #pragma unroll
     for (int o = 0; o < CO; ++o) dbacc[o] = 0.f;
     __syncthreads();
-    // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; then R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1).
+    // step s: D rows 2s, 2s+1 -> ring slots (2s)%6, (2s+1)%6; barrier; R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1).
+    // Six slots make one barrier per step enough: D(s+1) writes the two slots R(s) does not read, and D(s+2) reuses
+    // the slots of rows 2s-2, 2s-1 only after barrier s+1, which no thread passes before it has finished R(s).
     // The g_h rows of step s+1 are requested right after the D values of step s are formed, so the loads fly
-    // under the ring stores, the two barriers and the R phase.  (Columns beyond the block size, W > 128, reload.)
+    // under the ring stores, the barrier and the R phase.  (Columns beyond the block size, W > 128, reload.)
     const int n_steps = (H + 1) / 2 + 1;
     const bool one_col = W <= PCB_THREADS;
     float4 ga[CO4], gb[CO4];
@@ -215,11 +218,12 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
             gb[j] = (yb < H && x < W) ? ld4_stream(srca + (size_t)W * CO + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     if (one_col) load_rows(0, tid);
-    for (int s = 0; s < n_steps; ++s) {
+    int slot_a = 0;  // (2s) % 6
+    for (int s = 0; s < n_steps; ++s, slot_a = slot_a == 4 ? 0 : slot_a + 2) {
         const int ya = 2 * s, yb = 2 * s + 1;
         for (int x = tid; x < W; x += PCB_THREADS) {
-            float* dsta = sD + ((ya & 3) * W + x) * 27;
-            float* dstb = sD + ((yb & 3) * W + x) * 27;
+            float* dsta = sD + (slot_a * Wr + x + 1) * 27;
+            float* dstb = dsta + Wr * 27;
             if (ya < H) {
                 // both rows side by side: one 16-byte load of V feeds 4 packed FMAs of each row (row b = zeros past H)
                 if (!one_col) load_rows(s, x);
@@ -286,6 +290,9 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
             for (int c = 0; c < 3; ++c) im[h][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
         }
         __syncthreads();
+        // slot of D row 2s-2+i, i = 0..3: rows 2s-2 and 2s-1 sit in slots slot_a+4, slot_a+5 (mod 6)
+        const int sl0 = slot_a >= 2 ? slot_a - 2 : slot_a + 4;
+        const int slots[4] = {sl0, sl0 + 1, slot_a, slot_a + 1};
         for (int x = tid; x < W; x += PCB_THREADS) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -294,14 +301,11 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                    const int yy = y + 1 - dy;  // D row of tap row dy; rows -1 and H hold zeros in the ring
-                    if (yy < 0) continue;
-                    const float* row = sD + ((yy & 3) * W) * 27;
+                    // D row y+1-dy = 2s-2 + (h+2-dy); row -1 is the zero-initialised slot 5, rows >= H hold zeros
+                    const float* row = sD + (slots[h + 2 - dy] * Wr + x + 2) * 27 + 9 * dy;
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        const int xx = x + 1 - dx;
-                        if (xx < 0 || xx >= W) continue;
-                        const float* d = row + xx * 27 + (3 * dy + dx) * 3;
+                        const float* d = row + 3 * dx - dx * 27;  // column x+1-dx (+1 for the zero border)
                         r0 += d[0]; r1 += d[1]; r2 += d[2];
                     }
                 }
@@ -311,7 +315,6 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                 dm[q] = fmaf(c2, r2, fmaf(c1, r1, c0 * r0));
             }
         }
-        __syncthreads();
     }
     // db: thread partials -> warp (fixed xor tree) -> CTA (warp order) -> ws_db[n][CO]
 #pragma unroll
@@ -539,7 +542,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
     float* dm_planes = ws_db + (size_t)K * B * Co;
     cudaStream_t st = as_stream(stream);
-    const size_t smem = (size_t)(28 * Co + 4 * W * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
+    const size_t smem = (size_t)(28 * Co + 6 * (W + 2) * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
 #define UPS_PCB(CO, MINB)                                                                                              \
     do {                                                                                                               \
