@@ -181,9 +181,12 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
     constexpr int CO4 = CO / 4;
     extern __shared__ float4 smem4[];
     float* sVT = reinterpret_cast<float*>(smem4);  // [CO][28]: V transposed, (tap, channel) pair index fastest, [27] = 0
-    float* sD = sVT + 28 * CO;                     // ring [6][W+2][27]; columns 0 and W+1 stay zero
+    float* sD = sVT + 28 * CO;                     // ring [4][W+2][27]; columns 0 and W+1 stay zero
     const int Wr = W + 2;
-    float* sRed = sD + 6 * Wr * 27;                // [PCB_THREADS/32][CO] for the db reduction
+    float* sRed = sD + 4 * Wr * 27;                // [PCB_THREADS/32][CO] for the db reduction
+    constexpr int GST = CO + 4;                    // staging stride per pixel (16-byte loads of 8 lanes: conflict-free)
+    float* sStage = sRed + (PCB_THREADS / 32) * CO;  // [2 rows][PCB_THREADS][GST]: the thread's own two g_h pixels, one step ahead
+    sStage += (4 - ((28 * CO + 4 * Wr * 27 + (PCB_THREADS / 32) * CO) & 3)) & 3;  // 16-byte alignment
     const int n = blockIdx.x;                      // plane k*B + b
     const int k = n / B, b = n - k * B;
     const int tid = threadIdx.x;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
         const int o = i / 28, tc = i - o * 28;
         sVT[i] = tc < 27 ? __ldg(V + tc * CO + o) : 0.f;
     }
-    for (int i = tid; i < 6 * Wr * 27; i += PCB_THREADS) sD[i] = 0.f;
+    for (int i = tid; i < 4 * Wr * 27; i += PCB_THREADS) sD[i] = 0.f;
     const size_t P = (size_t)H * W;
     const float* gp = g_h + (size_t)n * P * CO;
     const float* ib = img + (size_t)b * P * 3;
@@ -200,14 +203,28 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
 #pragma unroll
     for (int o = 0; o < CO; ++o) dbacc[o] = 0.f;
     __syncthreads();
-    // step s: D rows 2s, 2s+1 -> ring slots (2s)%6, (2s+1)%6; barrier; R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1).
-    // Six slots make one barrier per step enough: D(s+1) writes the two slots R(s) does not read, and D(s+2) reuses
-    // the slots of rows 2s-2, 2s-1 only after barrier s+1, which no thread passes before it has finished R(s).
-    // The g_h rows of step s+1 are requested right after the D values of step s are formed, so the loads fly
-    // under the ring stores, the barrier and the R phase.  (Columns beyond the block size, W > 128, reload.)
+    // step s: D rows 2s, 2s+1 -> ring slots (2s)&3, (2s+1)&3; barrier; R rows 2s-1, 2s (need D rows 2s-2 .. 2s+1);
+    // barrier.  The g_h pixels of step s+1 are copied global -> shared (cp.async, the thread's own column, so no
+    // barrier is involved) at the start of step s and picked up at the start of step s+1: a whole step in flight.
+    // (Columns beyond the block size, W > 128, load directly.)
     const int n_steps = (H + 1) / 2 + 1;
     const bool one_col = W <= PCB_THREADS;
     float4 ga[CO4], gb[CO4];
+    float* st_a = sStage + tid * GST;
+    float* st_b = st_a + PCB_THREADS * GST;
+    auto stage_rows = [&](int s) {  // asynchronous copy of rows 2s, 2s+1 at column tid; zeros outside the image
+        const int ya = 2 * s, yb = 2 * s + 1;
+        const bool oka = ya < H && tid < W, okb = yb < H && tid < W;
+        const float* srca = oka ? gp + ((size_t)ya * W + tid) * CO : gp;
+        const float* srcb = okb ? gp + ((size_t)yb * W + tid) * CO : gp;
+#pragma unroll
+        for (int j = 0; j < CO4; ++j) {
+            const unsigned da = (unsigned)__cvta_generic_to_shared(st_a + 4 * j);
+            const unsigned db_ = (unsigned)__cvta_generic_to_shared(st_b + 4 * j);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(srca + 4 * j), "r"(oka ? 16 : 0) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(db_), "l"(srcb + 4 * j), "r"(okb ? 16 : 0) : "memory");
+        }
+    };
     auto load_rows = [&](int s, int x) {
         const int ya = 2 * s, yb = 2 * s + 1;
         const float* srca = gp + ((size_t)ya * W + x) * CO;
@@ -217,10 +234,28 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
         for (int j = 0; j < CO4; ++j)
             gb[j] = (yb < H && x < W) ? ld4_stream(srca + (size_t)W * CO + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (one_col) load_rows(0, tid);
-    int slot_a = 0;  // (2s) % 6
-    for (int s = 0; s < n_steps; ++s, slot_a = slot_a == 4 ? 0 : slot_a + 2) {
+    if (one_col) stage_rows(0);
+    for (int s = 0; s < n_steps; ++s) {
         const int ya = 2 * s, yb = 2 * s + 1;
+        const int slot_a = ya & 3;
+        // the image pixels of the two R rows of this step: requested now, used after the barrier
+        float im[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int y = 2 * s - 1 + h;
+            const bool ok = one_col && tid < W && y >= 0 && y < H;
+            const size_t q = (size_t)(ok ? y : 0) * W + (ok ? tid : 0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) im[h][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
+        }
+        if (one_col) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < CO4; ++j) {
+                ga[j] = *reinterpret_cast<const float4*>(st_a + 4 * j);
+                gb[j] = *reinterpret_cast<const float4*>(st_b + 4 * j);
+            }
+        }
         for (int x = tid; x < W; x += PCB_THREADS) {
             float* dsta = sD + (slot_a * Wr + x + 1) * 27;
             float* dstb = dsta + Wr * 27;
@@ -232,6 +267,7 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                     dbacc[4 * j] += ga[j].x + gb[j].x; dbacc[4 * j + 1] += ga[j].y + gb[j].y;
                     dbacc[4 * j + 2] += ga[j].z + gb[j].z; dbacc[4 * j + 3] += ga[j].w + gb[j].w;
                 }
+                if (one_col) stage_rows(s + 1);  // the staged pixels are in registers: refill for the next step
                 // the 28 (tap, channel) columns in two halves of 16 and 12: 16 packed accumulators live at a time
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -259,7 +295,6 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                             }
                         }
                     }
-                    if (half == 1 && one_col) load_rows(s + 1, x);  // next step's rows: in flight until the next D phase
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (i < 2 * nq) {
@@ -279,20 +314,9 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                 for (int tc = 0; tc < 27; ++tc) dsta[tc] = dstb[tc] = 0.f;  // rows below the image contribute nothing
             }
         }
-        // the image pixels of the two R rows: requested before the barrier, used after it
-        float im[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int y = 2 * s - 1 + h;
-            const bool ok = one_col && tid < W && y >= 0 && y < H;
-            const size_t q = (size_t)(ok ? y : 0) * W + (ok ? tid : 0);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) im[h][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
-        }
         __syncthreads();
-        // slot of D row 2s-2+i, i = 0..3: rows 2s-2 and 2s-1 sit in slots slot_a+4, slot_a+5 (mod 6)
-        const int sl0 = slot_a >= 2 ? slot_a - 2 : slot_a + 4;
-        const int slots[4] = {sl0, sl0 + 1, slot_a, slot_a + 1};
+        // slot of D row 2s-2+i, i = 0..3
+        const int slots[4] = {(slot_a + 2) & 3, (slot_a + 3) & 3, slot_a, slot_a + 1};
         for (int x = tid; x < W; x += PCB_THREADS) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                    // D row y+1-dy = 2s-2 + (h+2-dy); row -1 is the zero-initialised slot 5, rows >= H hold zeros
+                    // D row y+1-dy = 2s-2 + (h+2-dy); row -1 is the zero-initialised slot 3, rows >= H hold zeros
                     const float* row = sD + (slots[h + 2 - dy] * Wr + x + 2) * 27 + 9 * dy;
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
@@ -315,6 +339,7 @@ __global__ void __launch_bounds__(PCB_THREADS, MINB) parts_conv_bwd_data_kernel(
                 dm[q] = fmaf(c2, r2, fmaf(c1, r1, c0 * r0));
             }
         }
+        __syncthreads();
     }
     // db: thread partials -> warp (fixed xor tree) -> CTA (warp order) -> ws_db[n][CO]
 #pragma unroll
@@ -542,7 +567,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
     float* dm_planes = ws_db + (size_t)K * B * Co;
     cudaStream_t st = as_stream(stream);
-    const size_t smem = (size_t)(28 * Co + 6 * (W + 2) * 27 + (PCB_THREADS / 32) * Co) * sizeof(float);
+    const size_t smem = (size_t)(28 * Co + 4 * (W + 2) * 27 + (PCB_THREADS / 32) * Co + 4 + 2 * PCB_THREADS * (Co + 4)) * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
 #define UPS_PCB(CO, MINB)                                                                                              \
     do {                                                                                                               \
