@@ -32,6 +32,15 @@ WORKLOADS = {
 CPU_SAMPLE_B = 8   # BASELINE.json configs[0]: batch 8 on the host CPU
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -86,7 +95,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU restatement (oracle/) of the reference's TF-1.14 op chain; TF itself is not installable here",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -327,7 +336,7 @@ def run_gpu(args):
         except Exception as e:  # the N4 leg must never cost the headline line
             line["n4_first_conv"] = {"error": repr(e)[:300]}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -434,6 +443,12 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL prints its
+    # version banner there when the box sets NCCL_DEBUG) is sent to stderr; the line goes out through the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
