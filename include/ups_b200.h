@@ -258,6 +258,9 @@ int ups_inject_conv_bwd(const float* g_out, const float* mask, const float* G, c
                         float* dmask, float* dG, float* db, int B, int H, int W, int K, int Co, void* ws, size_t ws_bytes,
                         void* stream);
 size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co);
+/* host-only query of the backward tiling: out6 = (variant: 0 does not fit / 1 CUDA cores / 2 mma.sync, tile rows, CTAs per
+ * sample, tiles per CTA, dynamic shared memory bytes per CTA, tiles per sample).  No device work. */
+int ups_inject_conv_bwd_plan(int B, int H, int W, int K, int Co, int* out6);
 
 /* ---- the appearance encoder's first convolution on the masked part images (encoder side) ----
  * Replaces   view1_parts = mask_parts(view1, encoding_mask)                      cub/code/SB_model48i/model.py:176-187, :478

@@ -84,6 +84,28 @@ def test_n4_error_paths_without_a_gpu(ups):
         ups.parts_conv2d(torch.zeros(2, 8, 8, 3), torch.zeros(2, 8, 4, 5), torch.zeros(3, 3, 3, 8), torch.zeros(8))
 
 
+def test_inject_conv_backward_plan_fits_the_sm(ups):
+    """Every (K, Co) the entry point accepts either gets a tiling that fits one SM (227 KB dynamic shared memory per
+    CTA; two CTAs per SM need <= 113 KB each) or is refused up front; the workspace covers the per-CTA partials."""
+    C = ups._cabi
+    for K in (1, 4, 8, 16, 25, 32):
+        for Co in (4, 8, 12, 16, 32, 64, 128):
+            for (B, H, W) in ((256, 128, 128), (2, 8, 8), (128, 256, 256)):
+                p = C.inject_conv_bwd_plan(B, H, W, K, Co)
+                if p["variant"] == 0:
+                    assert 9 * K * Co * 4 * 2 > 100 * 1024, (K, Co, p)        # only big tables are refused
+                    continue
+                assert p["smem_bytes"] <= 227 * 1024, (K, Co, p)
+                assert p["tile_rows"] in (4, 8, 16) and p["tiles"] == -(-W // 32) * -(-H // p["tile_rows"])
+                assert p["ctas_per_sample"] * p["tiles_per_cta"] >= p["tiles"]
+                if p["variant"] == 2:
+                    assert Co in (8, 16, 32, 64, 128) and p["tile_rows"] in (4, 8)
+                need = B * p["ctas_per_sample"] * (9 * K * Co + Co) * 4
+                assert C.inject_conv_workspace_bytes(B, H, W, K, Co) >= need
+    cub = C.inject_conv_bwd_plan(256, 128, 128, 16, 32)                       # the bench shape: tensor cores, 2 CTAs/SM
+    assert cub["variant"] == 2 and cub["tile_rows"] == 8 and cub["smem_bytes"] <= 113 * 1024
+
+
 REF_SIGNATURES = {
     # helper: parameter names (and defaults) in the reference, with file:line
     "softmax": "(x, spatial=False)",                                  # cub/code/nn.py:58
@@ -170,3 +192,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: stdout carries exactly one JSON line (the reference arm runs on the host cores, so this
+    runs here); everything else, including whatever a library writes to file descriptor 1, goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

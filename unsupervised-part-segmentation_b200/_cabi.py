@@ -61,6 +61,7 @@ _SIGS = {
     "ups_inject_conv_fwd": [c_f] * 4 + [c_i] * 5 + [c_f],
     "ups_parts_conv_fwd": [c_f] * 5 + [c_i] * 6 + [c_f],
     "ups_parts_conv_bwd": [c_f] * 9 + [c_i] * 6 + [c_f, c_sz, c_f],
+    "ups_inject_conv_bwd_plan": [c_i] * 5 + [c_f],
     "ups_inject_conv_bwd": [c_f] * 8 + [c_i] * 5 + [c_f, c_sz, c_f],
 }
 
@@ -119,6 +120,12 @@ def launch_count_reset():
 
 def inject_conv_workspace_bytes(B, H, W, K, Co):
     return int(lib.ups_inject_conv_workspace_bytes(B, H, W, K, Co))
+
+
+def inject_conv_bwd_plan(B, H, W, K, Co):
+    out = (ctypes.c_int * 6)()
+    call("ups_inject_conv_bwd_plan", B, H, W, K, Co, ctypes.cast(out, ctypes.c_void_p))
+    return dict(zip(("variant", "tile_rows", "ctas_per_sample", "tiles_per_cta", "smem_bytes", "tiles"), list(out)))
 
 
 def parts_conv_bwd_workspace_bytes(B, H, W, K, Co):

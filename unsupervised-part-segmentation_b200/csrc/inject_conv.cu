@@ -947,6 +947,20 @@ int launch_bwd(const BwdPlan& p, const float* g_out, const float* mask, const fl
 
 using namespace ups;
 
+// host-only: the tiling ups_inject_conv_bwd will use (tests check it against the shared-memory limits without a GPU)
+extern "C" int ups_inject_conv_bwd_plan(int B, int H, int W, int K, int Co, int* out6) {
+    UPS_REQUIRE(out6 != nullptr, "inject_conv_bwd_plan: null pointer");
+    if (int rc = check_dims("inject_conv_bwd_plan", B, H, W, K, Co)) return rc;
+    const BwdPlan p = bwd_plan(B, H, W, K, Co);
+    out6[0] = p.splits > 0 ? (p.mma ? 2 : 1) : 0;  // 0 = does not fit, 1 = CUDA cores, 2 = mma.sync
+    out6[1] = p.splits > 0 ? p.TH : 0;
+    out6[2] = p.splits > 0 ? p.splits : 0;
+    out6[3] = p.splits > 0 ? p.tiles_per_cta : 0;
+    out6[4] = p.splits > 0 ? p.smem : 0;
+    out6[5] = p.splits > 0 ? p.n_tiles : 0;
+    return UPS_OK;
+}
+
 extern "C" size_t ups_inject_conv_workspace_bytes(int B, int H, int W, int K, int Co) {
     if (B <= 0 || H <= 0 || W <= 0 || K < 1 || K > 32 || Co < 4 || Co > 128 || (Co & 3)) return 256;
     const BwdPlan p = bwd_plan(B, H, W, K, Co);
