@@ -28,7 +28,7 @@ if os.path.exists(lp):
     ours = {n: v for n, v in agg.items() if n.startswith(("ups::", "tc::", "tma::"))}
     tot = sum(sum(v) for v in ours.values())
     out.append(f"## Launch list ({tag}_launches.csv: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-               "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e`)\n")
+               "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-n4`)\n")
     out.append("Library kernels only (torch's RNG/fill kernels that build the synthetic inputs are excluded from the share).\n")
     out.append("| kernel | launches | mean µs | share of path time |\n|---|---|---|---|")
     for n, v in ours.items():
