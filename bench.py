@@ -18,7 +18,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     # name: (spatial, K, F, views, per-GPU batch, tps ranges)  — BASELINE.json configs[1..3]
@@ -53,6 +52,7 @@ def load_peaks():
 def cpu_port_rate(wl, steps, warmup, threads=None):
     """fwd+bwd of the oracle (CPU restatement of the reference path) on a bounded sample."""
     import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))      # the CPU arm is the one place bench.py uses the checker's helpers
     from oracle import step as OS
     from util import make_inputs
     cores = threads or os.cpu_count() or 1
@@ -82,8 +82,10 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    steps = max(3, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 3))
+    # --steps / --warmup are honoured as given; one step = one fwd+bwd of a bounded sample (batch 8, ~0.7 s on 16 cores),
+    # so the driver's 20 + 5 take ~20 s; only a request that would run for more than ~4 minutes is cut short
+    steps = max(1, min(args.steps, 300))
+    warm = max(0, min(args.warmup, 50))
     rate, med, cores, sample = cpu_port_rate(wl, steps, warm)
     line = {
         "impl": "reference", "metric": "part-step images/sec (fwd+bwd)", "value": rate, "unit": "images/s",
@@ -178,150 +180,217 @@ def ncu_traffic(call, workload, B):
     return d["bytes_per_launch"].get(CALL_KERNEL.get(call, "")), d.get("source")
 
 
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    import ups_b200
-    from ups_b200 import _cabi as C
-    from ups_b200.dp import DataParallelPartStep, init_from_env, rank_seed
-    from util import CUB_TPS, PENN_TPS  # parameter ranges only (tests/util.py constants)
+def set_rank_affinity(local, world_local):
+    """Give every rank its own slice of the host cores BEFORE it allocates pinned memory (first touch) and starts its
+    helper threads: eight ranks that all float over all cores (the box reports one NUMA node, CPU affinity 0-31 for
+    every GPU) contend for the same cores with their launch, NCCL-proxy and clock-sampler threads.  Returns the cores."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world_local <= 1 or len(cores) < 2 * world_local:
+            return cores
+        per = len(cores) // world_local
+        mine = cores[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:  # noqa: BLE001 - affinity is an optimisation, never a requirement
+        return None
 
-    rank, local, world = init_from_env()
-    assert world == args.gpus or world == 1, (world, args.gpus)
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    wl = WORKLOADS[args.workload]
-    S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
+
+def make_workload_tensors(torch, ups_b200, wl, name, B, dev, rank, seed, tps_bwd):
+    from ups_b200.configs import CUB_TPS, PENN_TPS
+    from ups_b200.dp import rank_seed
+    S, K, F, V = wl["S"], wl["K"], wl["F"], wl["V"]
+    g = torch.Generator(device=dev).manual_seed(rank_seed(seed, rank))
+    t = dict(
+        views=torch.rand(V, B, S, S, 3, device=dev, generator=g) * 2 - 1,
+        l0=torch.randn(B, S, S, K, device=dev, generator=g), l1=torch.randn(B, S, S, K, device=dev, generator=g),
+        feat=torch.randn(B, K, F, device=dev, generator=g), g_inj=torch.randn(B, S, S, F + K, device=dev, generator=g),
+        g_parts=torch.randn(K * B, S, S, 3, device=dev, generator=g), g_pooled=torch.randn(B, K, 3, device=dev, generator=g),
+        g_m0=torch.randn(B, S, S, K, device=dev, generator=g), g_m1=torch.randn(B, S, S, K, device=dev, generator=g),
+        g_recon=torch.randn(B, S, S, 3, device=dev, generator=g),
+        g_warped=torch.randn(V, B, S, S, 3, device=dev, generator=g) if tps_bwd else None)
+    tps_kw = CUB_TPS if name == "cub" else PENN_TPS
+    prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234 + rank), device=dev, **tps_kw)
+    t["coord"], t["tv"] = ups_b200.make_input_tps_param(prm)
+    return t
+
+
+def measure_workload(args, torch, dist, ups_b200, name, B, dev, rank, world, reducer, steps, warmup, detailed):
+    """K timed steps of the data-parallel part step on workload `name` with inputs resident in HBM.
+    Returns (record, dp, tensors); `detailed` adds per-call CUDA events and the launch count."""
+    from ups_b200 import _cabi as C
+    from ups_b200.dp import DataParallelPartStep
+    wl = WORKLOADS[name]
+    S, K, F, V = wl["S"], wl["K"], wl["F"], wl["V"]
     P = S * S
     dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev,
-                              decode_bwd=args.decode_bwd, n_grad_params=int(args.grad_mb * 1e6 / 4),
-                              bucket_bytes=int(args.bucket_mb) << 20)
+                              decode_bwd=args.decode_bwd, reducer=reducer)
     step = dp.step
-
-    # ---- synthetic shard, resident in HBM (rank-offset seed)
-    g = torch.Generator(device=dev).manual_seed(rank_seed(args.seed, rank))
-    views = torch.rand(V, B, S, S, 3, device=dev, generator=g) * 2 - 1
-    l0 = torch.randn(B, S, S, K, device=dev, generator=g)
-    l1 = torch.randn(B, S, S, K, device=dev, generator=g)
-    feat = torch.randn(B, K, F, device=dev, generator=g)
-    g_inj = torch.randn(B, S, S, F + K, device=dev, generator=g)
-    g_parts = torch.randn(K * B, S, S, 3, device=dev, generator=g)
-    g_pooled = torch.randn(B, K, 3, device=dev, generator=g)
-    g_m0 = torch.randn(B, S, S, K, device=dev, generator=g)
-    g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
-    g_warped = torch.randn(V, B, S, S, 3, device=dev, generator=g) if args.tps_bwd else None
-    tps_kw = CUB_TPS if args.workload == "cub" else PENN_TPS
-    prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234 + rank), device=dev, **tps_kw)
-    coord, tv = ups_b200.make_input_tps_param(prm)
-    coord_h, tv_h = coord.cpu(), tv.cpu()
+    t = make_workload_tensors(torch, ups_b200, wl, name, B, dev, rank, args.seed, args.tps_bwd)
 
     def one_step():
-        dp.forward(views, coord, tv, l0, l1, feat)
-        dp.backward(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
+        dp.forward(t["views"], t["coord"], t["tv"], t["l0"], t["l1"], t["feat"])
+        dp.backward(t["g_inj"], t["g_parts"], t["g_pooled"], t["g_m0"], t["g_m1"], t["g_warped"], g_recon=t["g_recon"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         one_step()
     barrier()
 
-    # ---- timed region: exactly K steps, device time, per-call events on the launching stream
+    # ---- timed region: exactly `steps` steps, device time; per-call events on the launching stream
     marks = []
     raw_call = C.call
 
-    def timed_call(name, *a):
+    def timed_call(cname, *a):
+        if cname.startswith(("ups_standin", "ups_dp_")):     # enqueued on the reducer's side stream, not timed per call
+            return raw_call(cname, *a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        raw_call(name, *a)
+        raw_call(cname, *a)
         e1.record()
-        marks.append((name, e0, e1))
+        marks.append((cname, e0, e1))
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(dev.index) if detailed else None
+    if sampler:
+        sampler.start()
     C.launch_count_reset()
-    ups_b200.step.C.call = timed_call
+    if detailed:
+        C.call = timed_call
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_step()
+    dp.wait_grads()            # the last step's gradient buckets are part of the last step
     t1.record()
     barrier()
-    ups_b200.step.C.call = raw_call
+    C.call = raw_call
     launches = C.launch_count()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms = t0.elapsed_time(t1)
     if world > 1:
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms * 1e-3)
-
-    per_call = {}
-    for name, e0, e1 in marks:
-        per_call.setdefault(name, []).append(e0.elapsed_time(e1))
-    # calls per step of each name (tps_warp_fwd is called twice: 2B views, then the target view)
-    call_ms = {n: sum(v) / args.steps for n, v in per_call.items()}
+    ms_per_step = ms / steps
     peak, peak_src = load_peaks()
-    # Dominant kernel: the longest C-ABI call among those that run ALONE on the GPU.  With the forward
-    # overlap on (step.overlap_fwd: K3 on a side stream beside K1/K2) the events around K1/K3 bracket a
-    # period in which two kernels share the SMs, so those durations are not per-kernel times; they are
-    # reported in per_call_ms (flagged in co_scheduled_calls) but not used for the kernel roofline.
-    co = {"ups_tps_solve", "ups_tps_warp_fwd", "ups_tps_warp_pair_fwd", "ups_step_decode_fwd",
-          "ups_step_encode_fwd"} if getattr(step, "overlap_fwd", False) else set()
-    alone = {n: v for n, v in call_ms.items() if n not in co} or call_ms
-    dom = max(alone, key=alone.get)
-    px = V * B * P if dom.startswith("ups_tps_warp") else B * P
-    dom_bytes = KERNEL_BYTES_PER_PX[dom](K, F) * px if dom in KERNEL_BYTES_PER_PX else None
-    n_dom = len(per_call[dom]) / args.steps
-    dom_launch_ms = call_ms[dom] / n_dom
-    achieved = (dom_bytes / n_dom) / (dom_launch_ms * 1e-3) / 1e9 if dom_bytes else None
     step_bytes = step.algorithmic_bytes_per_image() * B
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    rec = {"value": world * B * steps / (ms * 1e-3), "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+           "per_gpu_batch": B, "workload": wl["desc"],
+           "step_roofline": {"algorithmic_bytes_per_image": step.algorithmic_bytes_per_image(), "achieved": step_gbs,
+                             "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0},
+           "gpu_launches": launches, "clocks": clocks}
+    if detailed:
+        per_call = {}
+        for cname, e0, e1 in marks:
+            per_call.setdefault(cname, []).append(e0.elapsed_time(e1))
+        call_ms = {n: sum(v) / steps for n, v in per_call.items()}
+        dom = max(call_ms, key=call_ms.get)
+        px = V * B * P if dom.startswith("ups_tps_warp") else B * P
+        dom_bytes = KERNEL_BYTES_PER_PX[dom](K, F) * px if dom in KERNEL_BYTES_PER_PX else None
+        n_dom = len(per_call[dom]) / steps
+        dom_launch_ms = call_ms[dom] / n_dom
+        achieved = (dom_bytes / n_dom) / (dom_launch_ms * 1e-3) / 1e9 if dom_bytes else None
+        traffic, traffic_src = ncu_traffic(dom, name, B)
+        rec["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                           "traffic_source": traffic_src, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": dom_bytes / n_dom if dom_bytes else None,
+                           "launch_ms": dom_launch_ms}
+        rec["per_call_ms"] = {k: round(v, 4) for k, v in sorted(call_ms.items())}
+        rec["per_call_frac_of_hbm"] = {
+            k: round(KERNEL_BYTES_PER_PX[k](K, F) * (V * B * P if k.startswith("ups_tps_warp") else B * P)
+                     / (v * 1e-3) / 1e9 / peak, 4)
+            for k, v in sorted(call_ms.items()) if k in KERNEL_BYTES_PER_PX and v > 0}
+    return rec, dp, t
 
-    traffic, traffic_src = ncu_traffic(dom, args.workload, B)
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import ups_b200
+    from ups_b200.dp import GradAllReducer, DECODER_SHARE, init_from_env
+
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    cores = set_rank_affinity(int(os.environ.get("LOCAL_RANK", "0")), local_world) if not args.no_affinity else None
+    rank, local, world = init_from_env()
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if cores:
+        torch.set_num_threads(max(1, min(len(cores), 8)))
+    wl = WORKLOADS[args.workload]
+    S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
+    # one flat gradient buffer (symmetric memory when N>1) shared by every workload measured in this process
+    n_grad = (int(args.grad_mb * 1e6 / 4) + 3) // 4 * 4
+    n_dec = (int(n_grad * DECODER_SHARE) + 3) // 4 * 4
+    reducer = GradAllReducer(n_grad, dev, buckets=[(0, n_dec), (n_dec, n_grad - n_dec)], impl=args.allreduce,
+                             n_ctas=args.allreduce_ctas)
+    warm = max(args.warmup, 3)
+    rec, dp, t = measure_workload(args, torch, dist, ups_b200, args.workload, B, dev, rank, world, reducer, args.steps, warm,
+                                  detailed=True)
+    step = dp.step
     line = {
-        "metric": "part-step images/sec (fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": "part-step images/sec (fwd+bwd)", "value": rec["value"], "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "spatial": S, "n_parts": K,
                    "local_app_size": F, "views": V, "tps_backward": bool(args.tps_bwd), "decode_bwd": step.decode_bwd,
-                   "parallelism": f"dp{world} (batch-sharded; no data-path collective; "
-                                  f"{dp.grads.numel() * 4 / 1e6:.0f} MB fp32 gradient all-reduce per step when N>1)",
-                   "l2": "inputs larger than L2: one step touches %.1f GB per GPU (L2 = 126 MB)" % (step_bytes / 1e9)},
-        "clocks": clocks,
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom_bytes / n_dom if dom_bytes else None,
-                     "launch_ms": dom_launch_ms},
-        "step_roofline": {"algorithmic_bytes_per_image": step.algorithmic_bytes_per_image(), "achieved": step_gbs,
-                          "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0},
-        "per_call_ms": {k: round(v, 4) for k, v in sorted(call_ms.items())},
-        "co_scheduled_calls": sorted(co & set(call_ms)),
+                   "parallelism": f"dp{world} (batch-sharded; no data-path collective; {reducer.flat.numel() * 4 / 1e6:.0f} MB fp32 "
+                                  f"gradient mean per step in two buckets when N>1; stand-in gradient kernels run at every N)",
+                   "allreduce": {"transport": reducer.transport, "impl": reducer.impl, "ctas": reducer.n_ctas,
+                                 "fallback_reason": reducer.fallback_reason,
+                                 "buckets_mb": [round(n * 4 / 1e6, 1) for _, n in reducer.bounds]},
+                   "host_cores_of_rank": (len(cores) if cores else None),
+                   "l2": "inputs larger than L2: one step touches %.1f GB per GPU (L2 = 126 MB)"
+                         % (step.algorithmic_bytes_per_image() * B / 1e9)},
+        "clocks": rec["clocks"],
+        "gpu_launches": rec["gpu_launches"],
+        "roofline": rec["roofline"],
+        "step_roofline": rec["step_roofline"],
+        "per_call_ms": rec["per_call_ms"],
+        "per_call_frac_of_hbm": rec["per_call_frac_of_hbm"],
     }
 
     # ---- e2e: same metric through the public API with HOST buffers (pinned), copies in the timed region
-    e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dist, dp, dev, world, dict(views=views, coord=coord_h, tv=tv_h, l0=l0, l1=l1, feat=feat,
-                                                              g_inj=g_inj, g_parts=g_parts, g_pooled=g_pooled, g_m0=g_m0,
-                                                              g_m1=g_m1, g_warped=g_warped), B)
-        line["e2e"] = e2e
+        targs = dict(views=t["views"], coord=t["coord"].cpu(), tv=t["tv"].cpu(), l0=t["l0"], l1=t["l1"], feat=t["feat"],
+                     g_inj=t["g_inj"], g_parts=t["g_parts"], g_pooled=t["g_pooled"], g_m0=t["g_m0"], g_m1=t["g_m1"],
+                     g_warped=t["g_warped"], g_recon=t["g_recon"])
+        line["e2e"] = run_e2e(args, torch, dist, dp, dev, world, targs, B)
         # same step with the views crossing PCIe as the dataset's uint8 pixels (reported beside, not instead of, e2e)
-        targs = dict(views=views, coord=coord_h, tv=tv_h, l0=l0, l1=l1, feat=feat, g_inj=g_inj, g_parts=g_parts,
-                     g_pooled=g_pooled, g_m0=g_m0, g_m1=g_m1, g_warped=g_warped)
         line["e2e_uint8_views"] = run_e2e(args, torch, dist, dp, dev, world, targs, B, u8=True)
+
+    # ---- BASELINE.json configs[2], configs[3] at this N (the other workloads, device-resident, fewer steps)
+    if not args.no_scale_workloads:
+        del dp, t, step
+        torch.cuda.empty_cache()
+        line["scale_workloads"] = {}
+        for other in sorted(WORKLOADS):
+            if other == args.workload:
+                continue
+            try:
+                r2, dp2, t2 = measure_workload(args, torch, dist, ups_b200, other, WORKLOADS[other]["B"], dev, rank, world,
+                                               reducer, max(5, min(args.steps, 20)), 3, detailed=False)
+                line["scale_workloads"][other] = {
+                    "value": r2["value"], "unit": "images/s", "ms_per_step": r2["ms_per_step"], "steps": r2["steps"],
+                    "per_gpu_batch": r2["per_gpu_batch"], "global_batch": r2["per_gpu_batch"] * world,
+                    "workload": r2["workload"], "step_roofline_frac": r2["step_roofline"]["frac"],
+                    "step_roofline_frac_of_nominal_8TBs": r2["step_roofline"]["frac_of_nominal_8TBs"]}
+                del dp2, t2
+            except Exception as e:  # noqa: BLE001 - a secondary workload must never cost the headline line
+                line["scale_workloads"][other] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, med, cores, sample = cpu_port_rate(wl, steps=5, warmup=1)
-        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        rate, med, ncores, sample = cpu_port_rate(wl, steps=5, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": ncores, "kind": "port", "sample": sample}
     # ---- SURVEY.md 8f N4 (next row): the first decoder / encoder convolutions on the part assignment, per C-ABI
     # call with CUDA events, L2 flushed between calls; the library (cuDNN) legs on the materialised tensors beside them
     if rank == 0 and world == 1 and args.workload == "cub" and not args.no_n4:
@@ -398,7 +467,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
             b = bufs[i % 2]
             main_s.wait_event(ready[i % 2])
             dp.forward(b["views"], b["coord"], b["tv"], t["l0"], t["l1"], t["feat"])
-            dp.backward(t["g_inj"], t["g_parts"], t["g_pooled"], t["g_m0"], t["g_m1"], t["g_warped"])
+            dp.backward(t["g_inj"], t["g_parts"], t["g_pooled"], t["g_m0"], t["g_m1"], t["g_warped"], g_recon=t["g_recon"])
             freed[i % 2].record(main_s)
             # results -> a device staging copy (35 MB device-to-device, ~12 us), read back from there on
             # its own stream: the D2H of step i overlaps the kernels of step i+1
@@ -413,6 +482,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
                 pooled_h.copy_(pooled_d, non_blocking=True)
                 dfeat_h.copy_(dfeat_d, non_blocking=True)
                 drained.record(out_s)
+        dp.wait_grads()
         main_s.wait_event(drained)
 
     def barrier():
@@ -436,6 +506,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
     assert int(lab_h.max()) < dp.step.K
     return {"value": world * B * n / (ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": n, "ms_per_step": ms / n,
+            "h2d_GBs_per_rank": h2d / (ms / n * 1e-3) / 1e9, "d2h_GBs_per_rank": d2h / (ms / n * 1e-3) / 1e9,
             "boundary": ("host: %s views + TPS params in, int64 labels + pooled + dfeat out; "
                          "logits/features/cotangents device-resident (CNN outputs in the real model)")
                         % ("uint8 (normalised on the device as cub/code/data/data.py:134 does on the host)" if u8
@@ -463,7 +534,11 @@ def main():
     ap.add_argument("--grad-mb", type=float, default=133.2,
                     help="size of the stand-in encoder/decoder gradient buffer all-reduced per step when N>1 "
                          "(33.3 M fp32 parameters of the reference's CNNs, SURVEY.md section 2)")
-    ap.add_argument("--bucket-mb", type=int, default=256, help="all-reduce bucket size; the stand-in buffer is ready at once, so one bucket")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],
+                    help="gradient mean when N>1: ups_dp_allreduce over symmetric memory (multicast / peer) or ncclAllReduce")
+    ap.add_argument("--allreduce-ctas", type=int, default=16, help="CTAs of the all-reduce kernel")
+    ap.add_argument("--no-scale-workloads", action="store_true", help="skip the DeepFashion / PennAction legs")
+    ap.add_argument("--no-affinity", action="store_true", help="do not give each rank its own slice of the host cores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-n4", action="store_true", help="skip the N4 first-convolution microbenchmark leg")

@@ -32,8 +32,11 @@ extern "C" {
 
 const char* ups_version(void);
 const char* ups_last_error_string(void);
-/* number of kernels this library has launched on the calling thread since the last reset
- * (bench.py's `gpu_launches`) */
+/* ups_version(): "ups_b200 <version> (sm_100a, src=<hash>)"; <hash> = first 12 hex digits of the SHA-256 over the sources
+ * and headers the binary was built from (unsupervised-part-segmentation_b200/build.py::source_hash), so that a binary
+ * that does not correspond to the sources beside it is detected and rebuilt.
+ * ups_launch_count(): number of kernels this library has launched on the calling thread since the last reset
+ * (thread-local diagnostics counter, bench.py's `gpu_launches`). */
 long long ups_launch_count(void);
 void ups_launch_count_reset(void);
 
@@ -96,6 +99,14 @@ int ups_part_softmax_fwd(const float* logits, float* probs, long long* labels, f
                          int K, void* stream);
 /* dx = p*(g - sum_j g_j p_j)  (TF SoftmaxGrad) */
 int ups_part_softmax_bwd(const float* probs, const float* g, float* dlogits, long long n_pix, int K, void* stream);
+/* same with up to three cotangents summed inside the kernel ((g + g2) + g3; g2, g3 may be NULL) */
+int ups_part_softmax_bwd2(const float* probs, const float* g, const float* g2, const float* g3, float* dlogits,
+                          long long n_pix, int K, void* stream);
+/* elementwise sums of the unfused step: y += a*x ; out[v] = (g_views ? g_views[v] : 0) + (v == idx ? extra : 0)
+ * for V views of n_per_view floats (the cotangent of the warped views: model.py:282-311 differentiated) */
+int ups_axpy(const float* x, float* y, long long n, float a, void* stream);
+int ups_views_cotangent(const float* g_views, const float* extra, float* out, int V, int idx, long long n_per_view,
+                        void* stream);
 /* nn.spatial_softmax — cub/code/nn.py:65-71: softmax over the P axis for every (n, c); x [N,P,C]. */
 int ups_spatial_softmax_fwd(const float* x, float* probs, int N, int P, int C, void* stream);
 int ups_spatial_softmax_bwd(const float* probs, const float* g, float* dx, int N, int P, int C, void* stream);
@@ -281,6 +292,39 @@ int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mas
                        const float* g_extra, float* dmask, float* dV, float* db, int B, int H, int W, int K, int C, int Co,
                        void* ws, size_t ws_bytes, void* stream);
 size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
+
+/* ---- data-parallel step wrapper (SURVEY.md 8d "DP step", 8e) ------------------------------------------------
+ * The reference trains on one GPU; the only multi-GPU analogue in its tree is the IMM baseline's host-side tower
+ * averaging (baselines/imm/imm/train/cnn_train_multi.py:75-118, `average_gradients`).  ups_dp_allreduce is that mean
+ * over ranks as ONE kernel over NVLink peer memory, in place on a bucket of the flat gradient buffer:
+ *   peer_bufs    HOST array [world] of this process's device mappings of every rank's bucket (entry `rank` = own)
+ *   mc_buf       device mapping of the multicast object bound to all buckets (NVSwitch in-switch reduction), or NULL:
+ *                then the kernel reads and writes the peers' buckets through peer_bufs
+ *   peer_signals HOST array [world] of mappings of every rank's signal pad: ups_dp_allreduce_signal_bytes(world, n_ctas)
+ *                bytes, zero-initialised once by its owner before the first call (the barriers reset it themselves)
+ *   scale        applied to the sum (1/world for the mean); n_floats % 4 == 0; n_ctas CTAs of 512 threads
+ * All ranks must enqueue the call with the same n_floats/n_ctas; the kernel waits (device side, no host sync) until
+ * every rank's call has started, i.e. until the producers of every rank's bucket have finished in stream order. */
+int ups_dp_allreduce(void* const* peer_bufs, void* mc_buf, void* const* peer_signals, int rank, int world,
+                     long long n_floats, float scale, int n_ctas, void* stream);
+size_t ups_dp_allreduce_signal_bytes(int world, int n_ctas);
+
+/* Stand-in parameterised modules that produce the gradients the wrapper all-reduces (csrc/standin.cu).
+ * encoder tail: feat[b,k,:] = pooled[b,k,:] . Wlin[C,F] + blin[F]         cub/code/SB_model48i/model.py:50-52
+ *   bwd: out = [dWlin (C*F), dblin (F)] from pooled [B,K,C] (C == 3) and dfeat [B,K,F]
+ * decoder head: recon[b,p,:] = concat(feat[b,label,:], one_hot(label)) . Whead[F+K,3] + bhead[3]
+ *   (1x1 conv on nn.unpool_features_gathered's injection, cub/code/nn.py:2469-2487; labels int64 [B,P])
+ *   bwd: out = [dWhead ((F+K)*3), dbhead (3)] from g_recon [B,P,3], labels, feat [B,K,F]
+ * Fixed-order sums (deterministic).  ws from ups_standin_workspace_bytes. */
+int ups_standin_tail_fwd(const float* pooled, const float* Wlin, const float* blin, float* feat, int B, int K, int C,
+                         int F, void* stream);
+int ups_standin_tail_bwd(const float* pooled, const float* dfeat, float* dWlin_dblin, int B, int K, int C, int F,
+                         void* ws, size_t ws_bytes, void* stream);
+int ups_standin_head_fwd(const long long* labels, const float* feat, const float* Whead, const float* bhead,
+                         float* recon, int B, int P, int K, int F, void* stream);
+int ups_standin_head_bwd(const float* g_recon, const long long* labels, const float* feat, float* dWhead_dbhead, int B,
+                         int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+size_t ups_standin_workspace_bytes(int B, int P, int K, int F);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,8 @@ def test_every_declared_symbol_is_exported(ups):
         assert hasattr(lib, n), f"{n} declared in include/ups_b200.h but not exported"
     bound = set(ups._cabi._SIGS) | {"ups_version", "ups_last_error_string", "ups_launch_count",
                                     "ups_launch_count_reset", "ups_workspace_bytes",
-                                    "ups_inject_conv_workspace_bytes", "ups_parts_conv_bwd_workspace_bytes"}
+                                    "ups_inject_conv_workspace_bytes", "ups_parts_conv_bwd_workspace_bytes",
+                                    "ups_standin_workspace_bytes", "ups_dp_allreduce_signal_bytes"}
     assert set(names) == bound, set(names) ^ bound
     assert "sm_100a" in ups._cabi.version()
 

@@ -27,7 +27,8 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(rank_seed(7, rank))
     grads = torch.randn(10_000, generator=g)
     mine = grads.clone()
-    red = GradAllReducer(grads, bucket_bytes=4096 * 4, world_size=world)
+    red = GradAllReducer(flat_grads=grads, bucket_bytes=4096 * 4, world_size=world)
+    assert red.impl == "gloo" and red.transport == "gloo" and red.grad_scale == 1.0
     assert len(red.buckets) == 3
     red.launch()
     red.wait()
@@ -62,3 +63,14 @@ def test_shard_bounds_cover_batch():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
     assert len({rank_seed(0, r) for r in range(8)}) == 8
+
+
+def test_bucket_split_is_16_byte_aligned_and_covers():
+    from ups_b200.dp import _split, DECODER_SHARE
+    for n in (4, 1000, 33_300_000, 33_300_004):
+        for parts in (1, 2, 3, 7):
+            b = _split(n, parts)
+            assert b[0][0] == 0 and b[-1][0] + b[-1][1] == n
+            assert all(o % 4 == 0 for o, _ in b)
+            assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(parts - 1))
+    assert 0.3 < DECODER_SHARE < 0.6

@@ -4,7 +4,8 @@ path of CompVis/unsupervised-part-segmentation, behind the reference's helper si
     from ups_b200 import nn, model, tps, pooling       # reference-named helpers
     from ups_b200.step import PartStep                 # the fused forward+backward step
 """
-from . import _cabi, ops, nn, tps, model, pooling  # noqa: F401
+from . import _cabi, ops, nn, tps, model, pooling, configs  # noqa: F401
+from .configs import PathConfig  # noqa: F401
 from .nn import (softmax, spatial_softmax, hard_max, straight_through_estimator,  # noqa: F401
                  hard_max_straight_through, apply_partwise, mask2hotmask, unpool_features_gathered,
                  probs_to_mu_sigma, mumford_shah, mumford_shah_sums, edge_set, MeanFieldDistribution, mask2rgb)

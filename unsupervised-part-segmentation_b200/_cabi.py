@@ -21,6 +21,9 @@ _SIGS = {
     "ups_tps_warp_pair_bwd": [c_f] * 6 + [c_i] * 7 + [c_f],
     "ups_part_softmax_fwd": [c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
     "ups_part_softmax_bwd": [c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_part_softmax_bwd2": [c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "ups_axpy": [c_f, c_f, c_ll, c_fl, c_f],
+    "ups_views_cotangent": [c_f, c_f, c_f, c_i, c_i, c_ll, c_f],
     "ups_spatial_softmax_fwd": [c_f, c_f, c_i, c_i, c_i, c_f],
     "ups_spatial_softmax_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
     "ups_hard_max_fwd": [c_f, c_f, c_ll, c_i, c_f],
@@ -63,6 +66,11 @@ _SIGS = {
     "ups_parts_conv_bwd": [c_f] * 9 + [c_i] * 6 + [c_f, c_sz, c_f],
     "ups_inject_conv_bwd_plan": [c_i] * 5 + [c_f],
     "ups_inject_conv_bwd": [c_f] * 8 + [c_i] * 5 + [c_f, c_sz, c_f],
+    "ups_dp_allreduce": [c_f, c_f, c_f, c_i, c_i, c_ll, c_fl, c_i, c_f],
+    "ups_standin_tail_fwd": [c_f] * 4 + [c_i] * 4 + [c_f],
+    "ups_standin_tail_bwd": [c_f] * 3 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_standin_head_fwd": [c_f] * 5 + [c_i] * 4 + [c_f],
+    "ups_standin_head_bwd": [c_f] * 4 + [c_i] * 4 + [c_f, c_sz, c_f],
 }
 
 OP_TPS_SOLVE, OP_POOL, OP_INJECT_BWD, OP_POOL_BWD, OP_STEP, OP_MOMENTS, OP_KL = 0, 1, 2, 3, 4, 5, 6
@@ -94,14 +102,39 @@ def _load():
     lib.ups_inject_conv_workspace_bytes.restype = c_sz
     lib.ups_parts_conv_bwd_workspace_bytes.argtypes = [c_i] * 5
     lib.ups_parts_conv_bwd_workspace_bytes.restype = c_sz
+    lib.ups_standin_workspace_bytes.argtypes = [c_i] * 4
+    lib.ups_standin_workspace_bytes.restype = c_sz
+    lib.ups_dp_allreduce_signal_bytes.argtypes = [c_i] * 2
+    lib.ups_dp_allreduce_signal_bytes.restype = c_sz
     return lib, path
 
 
 lib, LIB_PATH = _load()
 
 
+class StreamHandle(int):
+    """A cudaStream_t (as an integer) that remembers the index of the device it belongs to."""
+
+    def __new__(cls, stream, device_index):
+        self = super().__new__(cls, stream)
+        self.device_index = device_index
+        return self
+
+
 def call(name, *args):
-    rc = getattr(lib, name)(*args)
+    """Invoke one C-ABI entry point.  The stream is the last argument of every entry point; when it is a
+    StreamHandle of a device other than the calling thread's current one, that device is made current for
+    the call (the library launches on the current device and never calls cudaSetDevice itself)."""
+    st = args[-1] if args else None
+    if isinstance(st, StreamHandle) and st.device_index is not None:
+        import torch
+        if torch.cuda.current_device() != st.device_index:
+            with torch.cuda.device(st.device_index):
+                rc = getattr(lib, name)(*args)
+        else:
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise UpsError(f"{name} -> {rc}: {lib.ups_last_error_string().decode()}")
 

@@ -23,7 +23,10 @@ int after_launch(const char* what) {
 }
 }  // namespace ups
 
-extern "C" const char* ups_version(void) { return "ups_b200 0.1.0 (sm_100a)"; }
+#ifndef UPS_SRC_HASH
+#define UPS_SRC_HASH "unknown"
+#endif
+extern "C" const char* ups_version(void) { return "ups_b200 0.2.0 (sm_100a, src=" UPS_SRC_HASH ")"; }
 extern "C" const char* ups_last_error_string(void) { return ups::g_err; }
 extern "C" long long ups_launch_count(void) { return ups::g_launches; }
 extern "C" void ups_launch_count_reset(void) { ups::g_launches = 0; }

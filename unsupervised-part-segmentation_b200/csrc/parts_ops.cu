@@ -77,23 +77,49 @@ __global__ void __launch_bounds__(128) part_softmax_fwd_generic_kernel(const flo
 template <int LPP>
 __global__ void __launch_bounds__(TPB) part_softmax_bwd_kernel(const float* __restrict__ probs,
                                                                const float* __restrict__ g,
+                                                               const float* __restrict__ g2,
+                                                               const float* __restrict__ g3,
                                                                float* __restrict__ dlogits, long long n4) {
     const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
     const long long ii = i < n4 ? i : n4 - 1;
     const float4 p = ld4_stream(probs + 4 * ii);
-    const float4 gg = ld4_stream(g + 4 * ii);
+    float4 gg = ld4_stream(g + 4 * ii);
+    if (g2) { const float4 t = ld4_stream(g2 + 4 * ii); gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w; }
+    if (g3) { const float4 t = ld4_stream(g3 + 4 * ii); gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w; }
     float dot = p.x * gg.x + p.y * gg.y + p.z * gg.z + p.w * gg.w;
     dot = group_sum<LPP>(dot);
     if (i < n4) st4(dlogits + 4 * i, make_float4(p.x * (gg.x - dot), p.y * (gg.y - dot), p.z * (gg.z - dot), p.w * (gg.w - dot)));
 }
 
 __global__ void part_softmax_bwd_generic_kernel(const float* __restrict__ probs, const float* __restrict__ g,
+                                                const float* __restrict__ g2, const float* __restrict__ g3,
                                                 float* __restrict__ dlogits, long long n_pix, int K) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pix) return;
+    auto gsum = [&](long long j) {
+        float v = g[j];
+        if (g2) v += g2[j];
+        if (g3) v += g3[j];
+        return v;
+    };
     float dot = 0.f;
-    for (int k = 0; k < K; ++k) dot += probs[i * K + k] * g[i * K + k];
-    for (int k = 0; k < K; ++k) dlogits[i * K + k] = probs[i * K + k] * (g[i * K + k] - dot);
+    for (int k = 0; k < K; ++k) dot += probs[i * K + k] * gsum(i * K + k);
+    for (int k = 0; k < K; ++k) dlogits[i * K + k] = probs[i * K + k] * (gsum(i * K + k) - dot);
+}
+
+// y += a*x  and  out[v] = g[v] (or 0) + (v == idx ? extra : 0): the two elementwise sums of the unfused step
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+__global__ void views_cotangent_kernel(const float* __restrict__ g, const float* __restrict__ extra,
+                                       float* __restrict__ out, int idx, long long n_per_view, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long v = i / n_per_view;
+    float r = g ? g[i] : 0.f;
+    if (v == idx && extra) r += extra[i - v * n_per_view];
+    out[i] = r;
 }
 
 // =================================================================== spatial softmax (nn.py:65-71)
@@ -425,16 +451,39 @@ extern "C" int ups_part_softmax_sampled_fwd(const float* mean, const float* eps,
 
 extern "C" int ups_part_softmax_bwd(const float* probs, const float* g, float* dlogits, long long n_pix, int K,
                                     void* stream) {
+    return ups_part_softmax_bwd2(probs, g, nullptr, nullptr, dlogits, n_pix, K, stream);
+}
+
+extern "C" int ups_axpy(const float* x, float* y, long long n, float a, void* stream) {
+    UPS_REQUIRE(x && y && n >= 0, "axpy: null pointer");
+    if (n == 0) return UPS_OK;
+    UPS_GRID_OK(n, TPB);
+    axpy_kernel<<<nblk(n, TPB), TPB, 0, as_stream(stream)>>>(x, y, n, a);
+    return after_launch("axpy_kernel");
+}
+
+extern "C" int ups_views_cotangent(const float* g_views, const float* extra, float* out, int V, int idx,
+                                   long long n_per_view, void* stream) {
+    UPS_REQUIRE(out && V >= 1 && n_per_view >= 0 && idx >= 0 && idx < V, "views_cotangent: bad arguments");
+    const long long n = (long long)V * n_per_view;
+    if (n == 0) return UPS_OK;
+    UPS_GRID_OK(n, TPB);
+    views_cotangent_kernel<<<nblk(n, TPB), TPB, 0, as_stream(stream)>>>(g_views, extra, out, idx, n_per_view, n);
+    return after_launch("views_cotangent_kernel");
+}
+
+extern "C" int ups_part_softmax_bwd2(const float* probs, const float* g, const float* g2, const float* g3,
+                                     float* dlogits, long long n_pix, int K, void* stream) {
     UPS_REQUIRE(probs && g && dlogits, "part_softmax_bwd: null pointer");
     UPS_REQUIRE(n_pix >= 0 && K >= 1, "part_softmax_bwd: n_pix=%lld K=%d", n_pix, K);
     if (n_pix == 0) return UPS_OK;
     cudaStream_t s = as_stream(stream);
-    const bool vec = aligned16(probs) && aligned16(g) && aligned16(dlogits);
+    const bool vec = aligned16(probs) && aligned16(g) && aligned16(dlogits) && (!g2 || aligned16(g2)) && (!g3 || aligned16(g3));
 #define UPS_SM_BWD(LPP)                                                                              \
     {                                                                                                \
         const long long n4 = n_pix * LPP;                                                            \
         UPS_GRID_OK(n4, TPB);                                                                        \
-        part_softmax_bwd_kernel<LPP><<<nblk(n4, TPB), TPB, 0, s>>>(probs, g, dlogits, n4);           \
+        part_softmax_bwd_kernel<LPP><<<nblk(n4, TPB), TPB, 0, s>>>(probs, g, g2, g3, dlogits, n4);   \
         return after_launch("part_softmax_bwd_kernel");                                              \
     }
     if (vec && K == 4) UPS_SM_BWD(1)
@@ -443,7 +492,7 @@ extern "C" int ups_part_softmax_bwd(const float* probs, const float* g, float* d
     if (vec && K == 32) UPS_SM_BWD(8)
 #undef UPS_SM_BWD
     UPS_GRID_OK(n_pix, TPB);
-    part_softmax_bwd_generic_kernel<<<nblk(n_pix, TPB), TPB, 0, s>>>(probs, g, dlogits, n_pix, K);
+    part_softmax_bwd_generic_kernel<<<nblk(n_pix, TPB), TPB, 0, s>>>(probs, g, g2, g3, dlogits, n_pix, K);
     return after_launch("part_softmax_bwd_generic_kernel");
 }
 

@@ -2,16 +2,44 @@
 
 The path itself has no cross-sample dependency (TPS parameters, softmax, masks, pooling and
 unpooling are all indexed by the sample), so ranks exchange nothing on the data path.  The
-only collective of a training step is the gradient all-reduce of the encoder/decoder
+only collective of a training step is the mean of the gradients of the encoder/decoder
 parameters that surround the path (the reference trains on one GPU and has none; its IMM
-baseline averages tower gradients on the CPU, baselines/imm/imm/train/cnn_train_multi.py:
-75-118).  Here that all-reduce is NCCL over NVLink, bucketed, issued on a side stream so that
-it overlaps the path's backward kernels.
+baseline averages tower gradients on the host, baselines/imm/imm/train/cnn_train_multi.py:
+75-118).
+
+How the collective is done here
+-------------------------------
+* The flat gradient buffer lives in symmetric memory (torch.distributed._symmetric_memory:
+  every rank maps every other rank's buffer over NVLink and, on NVSwitch, a multicast address
+  bound to all of them).  PyTorch is plumbing: allocation and the handle exchange.
+* `ups_dp_allreduce` (csrc/dp_allreduce.cu) is ONE kernel per bucket: a flag barrier over peer
+  memory, an in-switch reduction of the rank's slice (`multimem.ld_reduce`), the 1/world of the
+  mean applied in registers, a multicast store into every rank's buffer, a second flag barrier.
+  No separate scale pass, and 16 small CTAs instead of NCCL's channel CTAs, so that the kernel
+  co-resides with the persistent K4 grid.  Without a multicast object the same kernel reads and
+  writes the peers' buffers directly.  If symmetric memory is not available at all the wrapper
+  falls back to `ncclAllReduce(SUM)` and hands the consumer the scale (`grad_scale`).
+* Two buckets, launched where their producers finish:
+    decoder bucket (the stand-in decoder head's gradient + the padding that stands for dd, dv and
+    the discriminators) at the top of backward, overlapped with K4;
+    encoder bucket (the stand-in encoder tail's gradient, which needs K4's dfeat, + the padding for
+    e_pi and e_alpha) after K4, overlapped with K5/K6 and with the next step's K1: the TPS warp
+    depends on the input batch only, not on the updated parameters, so `forward` waits for the
+    gradients between K1 and K2 (`wait_grads()` for whoever consumes them earlier).
+* The stand-in gradients are computed on the reducer's side stream: they feed the collective,
+  not the path.
 """
+import ctypes
 import os
 
 import torch
 import torch.distributed as dist
+
+from . import _cabi as C
+
+# parameter counts of the reference's CNNs (SURVEY.md section 2: e_pi 13.6 M, e_alpha 5.0 M | dv 6 M, three
+# discriminators 8.4 M, dd 0.2 M): share of the flat buffer whose gradients exist before the path's backward starts
+DECODER_SHARE = 14.6 / 33.2
 
 
 def shard_bounds(global_batch, rank, world_size):
@@ -45,68 +73,247 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def _split(n, parts):
+    """[(offset, length)] of `parts` contiguous pieces of n floats, every piece a multiple of 4 floats."""
+    out, off = [], 0
+    for i in range(parts):
+        end = n if i == parts - 1 else min(n, ((n * (i + 1) // parts) + 3) // 4 * 4)
+        out.append((off, end - off))
+        off = end
+    return out
+
+
 class GradAllReducer:
-    """Bucketed mean all-reduce of a flat gradient buffer on a side stream (NCCL) or inline (gloo)."""
+    """In-place mean all-reduce of the buckets of a flat fp32 gradient buffer, on a side stream.
 
-    def __init__(self, flat_grads, bucket_bytes=32 << 20, world_size=None):
-        self.flat = flat_grads
+    impl: "peer"  — ups_dp_allreduce over symmetric memory (multicast when the fabric offers it);
+          "nccl"  — ncclAllReduce(SUM); the buffer then holds the SUM and `grad_scale` = 1/world
+                    is the factor the consumer applies (no extra pass over HBM);
+          "gloo"  — CPU tensors (tests): all_reduce + scale inline;
+          "auto"  — "peer" on CUDA when symmetric memory can be set up, else "nccl" / "gloo".
+    `buckets`: [(offset, n_floats)] or an int (that many equal pieces); default one bucket.
+    """
+
+    def __init__(self, n_floats=None, device=None, buckets=None, impl="auto", n_ctas=16, flat_grads=None,
+                 bucket_bytes=None, world_size=None, group=None):
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        n = max(1, int(bucket_bytes) // flat_grads.element_size())
-        self.buckets = [flat_grads[i:i + n] for i in range(0, flat_grads.numel(), n)]
-        self.cuda = flat_grads.is_cuda
-        self.stream = torch.cuda.Stream(device=flat_grads.device) if self.cuda else None
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.group = group
+        self.n_ctas = int(n_ctas)
+        self.grad_scale = 1.0
+        self.fallback_reason = None
+        self._hdl = self._sig_hdl = None
+        if flat_grads is not None:      # caller-owned buffer (CPU tests, or NCCL on an ordinary CUDA tensor)
+            self.flat = flat_grads
+            n_floats = flat_grads.numel()
+            impl = ("nccl" if flat_grads.is_cuda else "gloo") if impl == "auto" else impl
+            assert impl in ("nccl", "gloo"), "a caller-owned buffer is not symmetric memory: impl must be nccl or gloo"
+        else:
+            device = torch.device(device if device is not None else "cuda")
+            n_floats = (int(n_floats) + 3) // 4 * 4
+            if device.type != "cuda":
+                impl = "gloo" if impl == "auto" else impl
+                self.flat = torch.zeros(n_floats, dtype=torch.float32, device=device)
+            elif self.world > 1 and impl in ("auto", "peer"):
+                try:
+                    self._setup_symmetric(n_floats, device)
+                    impl = "peer"
+                except Exception as e:  # noqa: BLE001 - any failure of the optional fast path selects NCCL
+                    if impl == "peer":
+                        raise
+                    self.fallback_reason = f"{type(e).__name__}: {e}"[:300]
+                    impl = "nccl"
+                    self.flat = torch.zeros(n_floats, dtype=torch.float32, device=device)
+            else:
+                impl = "nccl" if impl == "auto" else impl
+                self.flat = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.impl = impl
+        if bucket_bytes is not None and buckets is None:
+            per = max(4, int(bucket_bytes) // 4 // 4 * 4)
+            buckets = [(o, min(per, n_floats - o)) for o in range(0, n_floats, per)]
+        if buckets is None:
+            buckets = 1
+        if isinstance(buckets, int):
+            buckets = _split(n_floats, buckets)
+        self.bounds = [(int(o), int(n)) for o, n in buckets]
+        assert all(o % 4 == 0 for o, _ in self.bounds), "bucket offsets must be multiples of 4 floats"
+        self.buckets = [self.flat[o:o + n] for o, n in self.bounds]
+        self.cuda = self.flat.is_cuda
+        self.stream = torch.cuda.Stream(device=self.flat.device, priority=-1) if self.cuda else None
         self._done = None
+        if self.impl == "nccl" and self.world > 1:
+            self.grad_scale = 1.0 / self.world
+        if self.impl == "peer":
+            self._tables = []
+            for o, n in self.bounds:
+                assert n % 4 == 0 or o + n == n_floats, "peer buckets are multiples of 4 floats"
+                bufs = (ctypes.c_void_p * self.world)(*[p + 4 * o for p in self._buf_ptrs])
+                sigs = (ctypes.c_void_p * self.world)(*self._sig_ptrs)
+                mc = (self._mc_ptr + 4 * o) if self._mc_ptr else None
+                self._tables.append((bufs, sigs, mc, (n + 3) // 4 * 4))
 
-    def launch(self):
-        """Enqueue the all-reduce behind everything already queued on the current stream."""
+    def _setup_symmetric(self, n_floats, device):
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        name = group.group_name
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(name)
+            except Exception:  # noqa: BLE001 - newer torch enables it implicitly
+                pass
+        with torch.cuda.device(device):
+            buf = symm.empty(n_floats, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, name)
+            nsig = C.lib.ups_dp_allreduce_signal_bytes(self.world, max(self.n_ctas, 1)) // 4
+            sig = symm.empty(max(int(nsig), 64), dtype=torch.int32, device=device)
+            sig_hdl = symm.rendezvous(sig, name)
+            buf.zero_()
+            sig.zero_()
+            torch.cuda.synchronize(device)
+        dist.barrier(group=group)       # every pad is zero before anyone's first kernel signals into it
+        self.flat, self._sig = buf, sig
+        self._hdl, self._sig_hdl = hdl, sig_hdl
+        self._buf_ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._sig_ptrs = [int(p) for p in sig_hdl.buffer_ptrs]
+        use_mc = os.environ.get("UPS_DP_MULTICAST", "1") != "0"
+        self._mc_ptr = int(hdl.multicast_ptr) if (use_mc and getattr(hdl, "has_multicast_support", lambda *a: True) and
+                                                  int(hdl.multicast_ptr or 0)) else 0
+
+    @property
+    def transport(self):
+        """What carries the gradients: 'nvls-multicast', 'nvlink-peer', 'nccl', 'gloo' or 'none'."""
         if self.world == 1:
-            return
-        if self.cuda:
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
-                for b in self.buckets:
-                    # SUM (not AVG): NCCL's in-switch NVLS algorithms exist for sum only, and on NVSwitch they
-                    # need far fewer SM-resident channels than the 32-channel ring AVG falls back to
-                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
-                    b.mul_(1.0 / self.world)
+            return "none"
+        if self.impl == "peer":
+            return "nvls-multicast" if self._mc_ptr else "nvlink-peer"
+        return self.impl
+
+    def launch(self, bucket=None, after=None):
+        """Enqueue the all-reduce of one bucket (default: all) on the side stream, behind everything already
+        queued on the current stream (or behind the event `after`)."""
+        if self.world == 1:
+            if self.cuda:   # nothing to exchange, but whatever the caller queued on the side stream is still waited for
+                if after is not None:
+                    self.stream.wait_event(after)
                 self._done = torch.cuda.Event()
                 self._done.record(self.stream)
+            return
+        idx = range(len(self.buckets)) if bucket is None else [bucket]
+        if not self.cuda:
+            for i in idx:
+                dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group)
+                self.buckets[i].mul_(1.0 / self.world)
+            return
+        dev = self.flat.device
+        if after is not None:
+            self.stream.wait_event(after)
         else:
-            for b in self.buckets:
-                dist.all_reduce(b, op=dist.ReduceOp.SUM)
-                b.mul_(1.0 / self.world)
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            for i in idx:
+                if self.impl == "peer":
+                    bufs, sigs, mc, n = self._tables[i]
+                    C.call("ups_dp_allreduce", ctypes.cast(bufs, ctypes.c_void_p), mc, ctypes.cast(sigs, ctypes.c_void_p),
+                           self.rank, self.world, n, 1.0 / self.world, self.n_ctas, self.stream.cuda_stream)
+                else:
+                    # SUM (not AVG): NCCL's in-switch algorithms exist for sum only; the consumer applies grad_scale
+                    dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group)
+            self._done = torch.cuda.Event()
+            self._done.record(self.stream)
 
     def wait(self):
-        """Make the current stream wait for the reduction (no host synchronisation)."""
+        """Make the current stream wait for every launched reduction (no host synchronisation)."""
         if self.cuda and self._done is not None:
-            torch.cuda.current_stream().wait_event(self._done)
+            torch.cuda.current_stream(self.flat.device).wait_event(self._done)
             self._done = None
 
 
-class DataParallelPartStep:
-    """PartStep on this rank's shard + overlapped all-reduce of the surrounding modules' gradients.
+class StandInModules:
+    """The two tiny parameterised modules whose gradients the wrapper all-reduces (csrc/standin.cu):
+    encoder tail `feat = pooled . Wlin + blin` (model.py:50-52) and decoder head, a 1x1 conv F+K -> 3 on
+    concat(feat[label], one_hot(label)) (nn.unpool_features_gathered, nn.py:2469-2487).  Same seed on every rank:
+    replicas of one model."""
 
-    `n_grad_params` sizes the stand-in gradient buffer (default 33.3 M fp32 = the reference's
-    e_pi + e_alpha + dv + dd + discriminators)."""
+    def __init__(self, K, F, device, seed=0):
+        g = torch.Generator().manual_seed(10_007 + int(seed))
+        self.K, self.F = K, F
+        self.Wlin = ((torch.rand(3, F, generator=g) * 2 - 1) / 3 ** 0.5).to(device)
+        self.blin = torch.zeros(F, device=device)
+        self.Whead = ((torch.rand(F + K, 3, generator=g) * 2 - 1) / (F + K) ** 0.5).to(device)
+        self.bhead = torch.zeros(3, device=device)
+        self.n_tail = 3 * F + F
+        self.n_head = (F + K) * 3 + 3
+
+
+class DataParallelPartStep:
+    """PartStep on this rank's shard + the overlapped mean all-reduce of the surrounding modules' gradients.
+
+    `n_grad_params` sizes the flat gradient buffer (default 33.3 M fp32 = the reference's e_pi + e_alpha + dv + dd +
+    discriminators).  Its two buckets start with the stand-in modules' real gradients
+    (`grads_head`, `grads_tail`); the rest is padding that stands for the CNNs this repo does not contain."""
 
     def __init__(self, per_gpu_batch, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, n_grad_params=33_300_000, bucket_bytes=256 << 20, device="cuda",
-                 decode_bwd="auto"):
+                 views_grad=False, n_grad_params=33_300_000, device="cuda", decode_bwd="auto", allreduce="auto",
+                 allreduce_ctas=16, seed=0, reducer=None):
         from .step import PartStep
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device,
                              decode_bwd=decode_bwd)
-        self.grads = torch.zeros(int(n_grad_params), dtype=torch.float32, device=device)
-        self.reducer = GradAllReducer(self.grads, bucket_bytes, self.world)
+        dev = self.step.device
+        K, F = self.step.K, self.step.F
+        self.mod = StandInModules(K, F, dev, seed)
+        if reducer is None:     # `reducer`: an existing two-bucket GradAllReducer (one symmetric allocation per process)
+            n = max(int(n_grad_params), 4 * (self.mod.n_head + self.mod.n_tail + 8))
+            n = (n + 3) // 4 * 4
+            n_dec = max((int(n * DECODER_SHARE) + 3) // 4 * 4, (self.mod.n_head + 3) // 4 * 4)
+            reducer = GradAllReducer(n, dev, buckets=[(0, n_dec), (n_dec, n - n_dec)], impl=allreduce, n_ctas=allreduce_ctas)
+        assert len(reducer.bounds) == 2 and reducer.bounds[0][1] >= self.mod.n_head and reducer.bounds[1][1] >= self.mod.n_tail
+        n_dec = reducer.bounds[1][0]
+        self.reducer = reducer
+        self.grads = self.reducer.flat
+        self.grads_head = self.grads[:self.mod.n_head]                     # [dWhead ((F+K)*3), dbhead (3)]
+        self.grads_tail = self.grads[n_dec:n_dec + self.mod.n_tail]        # [dWlin (3*F), dblin (F)]
+        B, P = self.step.B, self.step.P
+        self._ws = torch.empty(max(int(C.lib.ups_standin_workspace_bytes(B, P, K, F)), 16), dtype=torch.uint8, device=dev)
+        self._ev = torch.cuda.Event()
 
-    def forward(self, *a, **k):
-        return self.step.forward(*a, **k)
-
-    def backward(self, *a, **k):
-        # the surrounding CNNs' gradients exist once their backward has run; the path's own
-        # backward kernels (K4-K6) then overlap with the collective
-        self.reducer.launch()
-        out = self.step.backward(*a, **k)
+    # ---------------------------------------------------------------- forward
+    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None):
+        # K1 needs the batch only; the parameters (hence the averaged gradients) are needed from K2/K3 on
+        self.step.forward_warp(views, coord, t_vector)
         self.reducer.wait()
+        return self.step.forward_parts(l0, l1, feat, conv_V, conv_b)
+
+    def wait_grads(self):
+        """The current stream waits until both buckets hold the mean over ranks (times 1/grad_scale for NCCL)."""
+        self.reducer.wait()
+
+    # ---------------------------------------------------------------- backward
+    def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None, g_recon=None):
+        """PartStep.backward plus the two gradient buckets.  g_recon [B,S,S,3]: cotangent of the stand-in decoder
+        head's output (None: the head contributes no gradient this step; the buckets are reduced all the same)."""
+        st, red, mod = self.step, self.reducer, self.mod
+        dev = st.device
+        B, P, K, F = st.B, st.P, st.K, st.F
+        side = red.stream
+        main = torch.cuda.current_stream(dev)
+        # decoder side: its gradients exist before the path's backward starts
+        side.wait_stream(main)
+        if g_recon is not None:
+            with torch.cuda.device(dev):
+                C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
+                       self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), side.cuda_stream)
+        self._ev.record(side)
+        red.launch(0, after=self._ev)
+        out = st.backward_decode(g_inj, g_m0)
+        # encoder side: the tail's gradient needs dfeat (K4)
+        self._ev.record(main)
+        side.wait_event(self._ev)
+        with torch.cuda.device(dev):
+            C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
+                   self._ws.data_ptr(), self._ws.numel(), side.cuda_stream)
+        self._ev.record(side)
+        red.launch(1, after=self._ev)
+        out.update(st.backward_encode(g_parts, g_pooled, g_m1, g_warped))
         return out

@@ -12,8 +12,10 @@ from torch import Tensor
 from . import _cabi as C
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: Tensor):
+    """The current stream of the device that owns `t`, tagged with that device: C.call makes the device current
+    for the duration of the call (the C ABI launches on the calling thread's current device)."""
+    return C.StreamHandle(torch.cuda.current_stream(t.device).cuda_stream, t.device.index)
 
 
 def _f32(t: Tensor, name="tensor") -> Tensor:
@@ -48,7 +50,7 @@ def _views_u8_to_f32(images: Tensor) -> Tensor:
         raise C.UpsError(f"ups_b200: images must be uint8, got {images.dtype}")
     images = images.contiguous()
     out = torch.empty(images.shape, dtype=torch.float32, device=images.device)
-    C.call("ups_views_u8_to_f32", images.data_ptr(), out.data_ptr(), images.numel(), _stream())
+    C.call("ups_views_u8_to_f32", images.data_ptr(), out.data_ptr(), images.numel(), _stream(images))
     return out
 
 
@@ -62,7 +64,7 @@ def _tps_input_param(coord: Tensor, vector: Tensor, offset: Tensor, offset_2: Te
     a = [_f32(t) for t in (coord, vector, offset, offset_2, t_scal, rot_mat)]
     N = a[0].shape[0]
     out = torch.empty_like(a[0])
-    C.call("ups_tps_input_param", *[t.data_ptr() for t in a], out.data_ptr(), N, _stream())
+    C.call("ups_tps_input_param", *[t.data_ptr() for t in a], out.data_ptr(), N, _stream(out))
     return out
 
 
@@ -73,7 +75,7 @@ def _tps_solve(coord: Tensor, vector: Tensor) -> Tensor:
     coord, vector = _f32(coord), _f32(vector)
     N = coord.shape[0]
     T = torch.empty(N, 2, 11, dtype=torch.float32, device=coord.device)
-    C.call("ups_tps_solve", coord.data_ptr(), vector.data_ptr(), T.data_ptr(), N, _stream())
+    C.call("ups_tps_solve", coord.data_ptr(), vector.data_ptr(), T.data_ptr(), N, _stream(coord))
     return T
 
 
@@ -89,7 +91,7 @@ def _tps_warp(U: Tensor, coord: Tensor, T: Tensor, out_size: int, move: Optional
     out = torch.empty(N, out_size, out_size, Cc, dtype=torch.float32, device=U.device)
     mesh = torch.empty(N, out_size, out_size, 2, dtype=torch.float32, device=U.device)
     C.call("ups_tps_warp_fwd", U.data_ptr(), coord.data_ptr(), T.data_ptr(), _ptr(move), _ptr(scal),
-           out.data_ptr(), mesh.data_ptr(), N, H, W, Cc, out_size, out_size, _stream())
+           out.data_ptr(), mesh.data_ptr(), N, H, W, Cc, out_size, out_size, _stream(U))
     return out, mesh
 
 
@@ -120,7 +122,7 @@ def _tps_warp_grad(g_out: Tensor, coord: Tensor, T: Tensor, shape: list[int], ou
     N, H, W, Cc = shape
     dU = torch.empty(N, H, W, Cc, dtype=torch.float32, device=g_out.device)
     C.call("ups_tps_warp_bwd", g_out.data_ptr(), coord.data_ptr(), T.data_ptr(), _ptr(move), _ptr(scal),
-           dU.data_ptr(), N, H, W, Cc, out_size, out_size, _stream())
+           dU.data_ptr(), N, H, W, Cc, out_size, out_size, _stream(g_out))
     return dU
 
 
@@ -138,7 +140,7 @@ def _part_softmax_full(logits: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     hard = torch.empty_like(x)
     labels = torch.empty(x.shape[:-1], dtype=torch.int64, device=x.device)
     C.call("ups_part_softmax_fwd", x.data_ptr(), probs.data_ptr(), labels.data_ptr(), hard.data_ptr(), n_pix, K,
-           _stream())
+           _stream(x))
     return probs, labels, hard
 
 
@@ -146,7 +148,7 @@ def _part_softmax(logits: Tensor) -> Tensor:
     x = _f32(logits, "logits")
     K = x.shape[-1]
     probs = torch.empty_like(x)
-    C.call("ups_part_softmax_fwd", x.data_ptr(), probs.data_ptr(), None, None, x.numel() // K, K, _stream())
+    C.call("ups_part_softmax_fwd", x.data_ptr(), probs.data_ptr(), None, None, x.numel() // K, K, _stream(x))
     return probs
 
 
@@ -154,7 +156,7 @@ def _part_softmax_grad(probs: Tensor, g: Tensor) -> Tensor:
     probs, g = _f32(probs), _f32(g)
     K = probs.shape[-1]
     dx = torch.empty_like(probs)
-    C.call("ups_part_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), probs.numel() // K, K, _stream())
+    C.call("ups_part_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), probs.numel() // K, K, _stream(probs))
     return dx
 
 
@@ -181,7 +183,7 @@ def _spatial_softmax(x: Tensor) -> Tensor:
     x = _f32(x)
     N, H, W, Cc = x.shape
     out = torch.empty_like(x)
-    C.call("ups_spatial_softmax_fwd", x.data_ptr(), out.data_ptr(), N, H * W, Cc, _stream())
+    C.call("ups_spatial_softmax_fwd", x.data_ptr(), out.data_ptr(), N, H * W, Cc, _stream(x))
     return out
 
 
@@ -189,7 +191,7 @@ def _spatial_softmax_grad(probs: Tensor, g: Tensor) -> Tensor:
     probs, g = _f32(probs), _f32(g)
     N, H, W, Cc = probs.shape
     dx = torch.empty_like(probs)
-    C.call("ups_spatial_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), N, H * W, Cc, _stream())
+    C.call("ups_spatial_softmax_bwd", probs.data_ptr(), g.data_ptr(), dx.data_ptr(), N, H * W, Cc, _stream(probs))
     return dx
 
 
@@ -203,7 +205,7 @@ def _hard_max(y: Tensor) -> Tensor:
     y = _f32(y)
     K = y.shape[-1]
     out = torch.empty_like(y)
-    C.call("ups_hard_max_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream())
+    C.call("ups_hard_max_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream(y))
     return out
 
 
@@ -213,7 +215,7 @@ hard_max = _op("hard_max", _hard_max, lambda y: torch.empty_like(y))   # tf.equa
 def _straight_through(y_hard: Tensor, y: Tensor) -> Tensor:
     y_hard, y = _f32(y_hard), _f32(y)
     out = torch.empty_like(y)
-    C.call("ups_straight_through_fwd", y_hard.data_ptr(), y.data_ptr(), out.data_ptr(), y.numel(), _stream())
+    C.call("ups_straight_through_fwd", y_hard.data_ptr(), y.data_ptr(), out.data_ptr(), y.numel(), _stream(y_hard))
     return out
 
 
@@ -225,7 +227,7 @@ def _argmax(y: Tensor) -> Tensor:
     y = _f32(y)
     K = y.shape[-1]
     out = torch.empty(y.shape[:-1], dtype=torch.int64, device=y.device)
-    C.call("ups_argmax_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream())
+    C.call("ups_argmax_fwd", y.data_ptr(), out.data_ptr(), y.numel() // K, K, _stream(y))
     return out
 
 
@@ -235,7 +237,7 @@ argmax = _op("argmax", _argmax, lambda y: y.new_empty(y.shape[:-1], dtype=torch.
 def _one_hot(labels: Tensor, depth: int) -> Tensor:
     labels = labels.contiguous()
     out = torch.empty(*labels.shape, depth, dtype=torch.float32, device=labels.device)
-    C.call("ups_one_hot_fwd", labels.data_ptr(), out.data_ptr(), labels.numel(), depth, _stream())
+    C.call("ups_one_hot_fwd", labels.data_ptr(), out.data_ptr(), labels.numel(), depth, _stream(labels))
     return out
 
 
@@ -255,7 +257,7 @@ def _mask_parts(image: Tensor, mask: Tensor, part_major: bool) -> Tensor:
     sp = image.shape[1:-1]
     out = torch.empty((K * B, *sp, Cc) if part_major else (B, *sp, K, Cc), dtype=torch.float32, device=image.device)
     C.call("ups_mask_parts_fwd", image.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, Cc, int(part_major),
-           _stream())
+           _stream(image))
     return out
 
 
@@ -270,7 +272,7 @@ def _mask_parts_grad(g: Tensor, image: Tensor, mask: Tensor, part_major: bool) -
     B, P, K, Cc = _dims_bpk(image, mask)
     dimage, dmask = torch.empty_like(image), torch.empty_like(mask)
     C.call("ups_mask_parts_bwd", g.data_ptr(), image.data_ptr(), mask.data_ptr(), dimage.data_ptr(), dmask.data_ptr(),
-           B, P, K, Cc, int(part_major), _stream())
+           B, P, K, Cc, int(part_major), _stream(g))
     return dimage, dmask
 
 
@@ -298,7 +300,7 @@ def _partwise_fold(x: Tensor) -> Tensor:
     sp = x.shape[1:-2]
     P = x.numel() // (B * K * Cc) if B else 0
     y = torch.empty(K * B, *sp, Cc, dtype=torch.float32, device=x.device)
-    C.call("ups_partwise_fold", x.data_ptr(), y.data_ptr(), B, P, K, Cc, _stream())
+    C.call("ups_partwise_fold", x.data_ptr(), y.data_ptr(), B, P, K, Cc, _stream(x))
     return y
 
 
@@ -309,7 +311,7 @@ def _partwise_unfold(y: Tensor, parts: int) -> Tensor:
     sp = y.shape[1:-1]
     P = y.numel() // (KB * Cc) if KB else 0
     x = torch.empty(B, *sp, parts, Cc, dtype=torch.float32, device=y.device)
-    C.call("ups_partwise_unfold", y.data_ptr(), x.data_ptr(), B, P, parts, Cc, _stream())
+    C.call("ups_partwise_unfold", y.data_ptr(), x.data_ptr(), B, P, parts, Cc, _stream(y))
     return x
 
 
@@ -331,7 +333,7 @@ def _part_pool(fmap: Tensor, mask: Tensor, grouped: bool, scale: float) -> Tenso
     out = torch.empty(B, K, Fg, dtype=torch.float32, device=fmap.device)
     ws = _ws(C.workspace_bytes(C.OP_POOL, B, P, K, Fg), fmap)
     C.call("ups_part_pool_fwd", fmap.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, Fg, int(grouped), scale,
-           ws.data_ptr(), ws.numel(), _stream())
+           ws.data_ptr(), ws.numel(), _stream(fmap))
     return out
 
 
@@ -347,7 +349,7 @@ def _part_pool_grad(g: Tensor, fmap: Tensor, mask: Tensor, grouped: bool, scale:
     Fg = nf // K if grouped else nf
     dfmap, dmask = torch.empty_like(fmap), torch.empty_like(mask)
     C.call("ups_part_pool_bwd", g.data_ptr(), fmap.data_ptr(), mask.data_ptr(), dfmap.data_ptr(), dmask.data_ptr(),
-           B, P, K, Fg, int(grouped), scale, _stream())
+           B, P, K, Fg, int(grouped), scale, _stream(g))
     return dfmap, dmask
 
 
@@ -380,7 +382,7 @@ def _part_unpool(feat: Tensor, mask: Tensor) -> Tensor:
     feat, mask = _f32(feat, "feature_vectors"), _f32(mask, "mask")
     B, P, K, F = _bpkf(feat, mask)
     out = torch.empty(*mask.shape, F, dtype=torch.float32, device=feat.device)
-    C.call("ups_part_unpool_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    C.call("ups_part_unpool_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream(feat))
     return out
 
 
@@ -390,7 +392,7 @@ def _part_unpool_grad(g: Tensor, feat: Tensor, mask: Tensor) -> Tuple[Tensor, Te
     dfeat, dmask = torch.empty_like(feat), torch.empty_like(mask)
     ws = _ws(C.workspace_bytes(C.OP_POOL, B, P, K, F), feat)
     C.call("ups_part_unpool_bwd", g.data_ptr(), feat.data_ptr(), mask.data_ptr(), dfeat.data_ptr(), dmask.data_ptr(),
-           B, P, K, F, ws.data_ptr(), ws.numel(), _stream())
+           B, P, K, F, ws.data_ptr(), ws.numel(), _stream(g))
     return dfeat, dmask
 
 
@@ -405,7 +407,7 @@ def _part_inject(feat: Tensor, mask: Tensor) -> Tensor:
     feat, mask = _f32(feat, "feature_vectors"), _f32(mask, "mask")
     B, P, K, F = _bpkf(feat, mask)
     out = torch.empty(*mask.shape[:-1], F + K, dtype=torch.float32, device=feat.device)
-    C.call("ups_part_inject_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    C.call("ups_part_inject_fwd", feat.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, K, F, _stream(feat))
     return out
 
 
@@ -415,7 +417,7 @@ def _part_inject_grad(g: Tensor, feat: Tensor, mask: Tensor) -> Tuple[Tensor, Te
     dfeat, dmask = torch.empty_like(feat), torch.empty_like(mask)
     ws = _ws(C.workspace_bytes(C.OP_INJECT_BWD, B, P, K, F), feat)
     C.call("ups_part_inject_bwd", g.data_ptr(), feat.data_ptr(), mask.data_ptr(), dfeat.data_ptr(), dmask.data_ptr(),
-           B, P, K, F, ws.data_ptr(), ws.numel(), _stream())
+           B, P, K, F, ws.data_ptr(), ws.numel(), _stream(g))
     return dfeat, dmask
 
 
@@ -433,7 +435,7 @@ def _part_gather(feat: Tensor, labels: Tensor) -> Tensor:
     B, K, F = feat.shape
     P = labels.numel() // B if B else 0
     out = torch.empty(*labels.shape, F, dtype=torch.float32, device=feat.device)
-    C.call("ups_part_gather_fwd", feat.data_ptr(), labels.data_ptr(), out.data_ptr(), B, P, K, F, _stream())
+    C.call("ups_part_gather_fwd", feat.data_ptr(), labels.data_ptr(), out.data_ptr(), B, P, K, F, _stream(feat))
     return out
 
 
@@ -449,7 +451,7 @@ def _mask_moments(probs: Tensor, scaling: Tensor) -> Tuple[Tensor, Tensor, Tenso
     moments = torch.empty(B, K, 5, dtype=torch.float32, device=probs.device)
     ws = _ws(C.workspace_bytes(C.OP_MOMENTS, B, H * W, K, 0), probs)
     C.call("ups_mask_moments_fwd", probs.data_ptr(), scaling.data_ptr(), mu.data_ptr(), sigma.data_ptr(),
-           moments.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream())
+           moments.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream(probs))
     return mu, sigma, moments
 
 
@@ -463,7 +465,7 @@ def _mask_moments_grad(g_mu: Tensor, g_sigma: Tensor, scaling: Tensor, moments: 
     B, H, W, K = shape
     dprobs = torch.empty(B, H, W, K, dtype=torch.float32, device=moments.device)
     C.call("ups_mask_moments_bwd", g_mu.data_ptr(), g_sigma.data_ptr(), scaling.data_ptr(), moments.data_ptr(),
-           dprobs.data_ptr(), B, H, W, K, _stream())
+           dprobs.data_ptr(), B, H, W, K, _stream(g_mu))
     return dprobs
 
 
@@ -492,7 +494,7 @@ def _categorical_kl(probs: Tensor) -> Tensor:
     n_pix = probs.numel() // K
     out = torch.empty((), dtype=torch.float32, device=probs.device)
     ws = _ws(C.workspace_bytes(C.OP_KL, 0, 0, K, 0), probs)
-    C.call("ups_categorical_kl_fwd", probs.data_ptr(), out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream())
+    C.call("ups_categorical_kl_fwd", probs.data_ptr(), out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream(probs))
     return out
 
 
@@ -500,7 +502,7 @@ def _categorical_kl_grad(probs: Tensor, g: Tensor) -> Tensor:
     probs, g = _f32(probs), _f32(g)
     K = probs.shape[-1]
     d = torch.empty_like(probs)
-    C.call("ups_categorical_kl_bwd", probs.data_ptr(), g.data_ptr(), d.data_ptr(), probs.numel() // K, K, _stream())
+    C.call("ups_categorical_kl_bwd", probs.data_ptr(), g.data_ptr(), d.data_ptr(), probs.numel() // K, K, _stream(probs))
     return d
 
 
@@ -516,7 +518,7 @@ def _mumford_shah(x: Tensor, alpha: float, lambda_: float) -> Tuple[Tensor, Tens
     B, H, W, K = x.shape
     r, s, c = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, r.data_ptr(), s.data_ptr(), c.data_ptr(), None, None,
-           B, H, W, K, None, 0, _stream())
+           B, H, W, K, None, 0, _stream(x))
     return r, s, c
 
 
@@ -527,7 +529,7 @@ def _mumford_shah_grad(x: Tensor, alpha: float, lambda_: float, g_r: Optional[Te
     gs = [None if g is None else _f32(g) for g in (g_r, g_s, g_c, g_sums)]
     dx = torch.empty_like(x)
     C.call("ups_mumford_shah_bwd", x.data_ptr(), alpha, lambda_, *[_ptr(g) for g in gs], dx.data_ptr(), B, H, W, K,
-           _stream())
+           _stream(x))
     return dx
 
 
@@ -552,7 +554,7 @@ def _mumford_shah_sums(x: Tensor, alpha: float, lambda_: float) -> Tensor:
     sums = torch.empty(B, 4, K, dtype=torch.float32, device=x.device)
     ws = _ws(C.workspace_bytes(C.OP_MUMFORD_SHAH, B, H * W, K, 0), x)
     C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, None, None, None, None, sums.data_ptr(), B, H, W, K,
-           ws.data_ptr(), ws.numel(), _stream())
+           ws.data_ptr(), ws.numel(), _stream(x))
     return sums
 
 
@@ -568,7 +570,7 @@ def _edge_set(x: Tensor, alpha: float, lambda_: float) -> Tensor:
     B, H, W, K = x.shape
     e = torch.empty_like(x)
     C.call("ups_mumford_shah_fwd", x.data_ptr(), alpha, lambda_, None, None, None, e.data_ptr(), None, B, H, W, K,
-           None, 0, _stream())
+           None, 0, _stream(x))
     return e
 
 
@@ -580,7 +582,7 @@ def _logit_priors(mean: Tensor) -> Tensor:
     B, H, W, K = mean.shape
     out = torch.empty(3, dtype=torch.float32, device=mean.device)
     ws = _ws(C.workspace_bytes(C.OP_LOGIT_PRIORS, B, H * W, K, 0), mean)
-    C.call("ups_logit_priors_fwd", mean.data_ptr(), out.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream())
+    C.call("ups_logit_priors_fwd", mean.data_ptr(), out.data_ptr(), B, H, W, K, ws.data_ptr(), ws.numel(), _stream(mean))
     return out
 
 
@@ -588,7 +590,7 @@ def _logit_priors_grad(mean: Tensor, g: Tensor) -> Tensor:
     mean, g = _f32(mean), _f32(g)
     B, H, W, K = mean.shape
     d = torch.empty_like(mean)
-    C.call("ups_logit_priors_bwd", mean.data_ptr(), g.data_ptr(), d.data_ptr(), B, H, W, K, _stream())
+    C.call("ups_logit_priors_bwd", mean.data_ptr(), g.data_ptr(), d.data_ptr(), B, H, W, K, _stream(mean))
     return d
 
 
@@ -603,7 +605,7 @@ def _mean_field_sample(mean: Tensor, eps: Tensor, noise_level: float) -> Tensor:
     assert mean.shape == eps.shape, (list(mean.shape), list(eps.shape))
     out = torch.empty_like(mean)
     C.call("ups_mean_field_sample_fwd", mean.data_ptr(), eps.data_ptr(), noise_level, out.data_ptr(), mean.numel(),
-           _stream())
+           _stream(mean))
     return out
 
 
@@ -618,7 +620,7 @@ def _part_softmax_sampled(mean: Tensor, eps: Tensor, noise_level: float) -> Tupl
     logits, probs, hard = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
     labels = torch.empty(mean.shape[:-1], dtype=torch.int64, device=mean.device)
     C.call("ups_part_softmax_sampled_fwd", mean.data_ptr(), eps.data_ptr(), noise_level, logits.data_ptr(),
-           probs.data_ptr(), labels.data_ptr(), hard.data_ptr(), mean.numel() // K, K, _stream())
+           probs.data_ptr(), labels.data_ptr(), hard.data_ptr(), mean.numel() // K, K, _stream(mean))
     return logits, probs, labels, hard
 
 
@@ -644,7 +646,7 @@ def _weak_xent(logits: Tensor, mode: int) -> Tensor:
     n_pix = x.numel() // K
     out = torch.empty((), dtype=torch.float32, device=x.device)
     ws = _ws(C.workspace_bytes(C.OP_WEAK_XENT, 1, n_pix, K, 0), x)
-    C.call("ups_weak_xent_fwd", x.data_ptr(), mode, out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream())
+    C.call("ups_weak_xent_fwd", x.data_ptr(), mode, out.data_ptr(), n_pix, K, ws.data_ptr(), ws.numel(), _stream(x))
     return out
 
 
@@ -652,7 +654,7 @@ def _weak_xent_grad(logits: Tensor, mode: int, g: Tensor) -> Tensor:
     x, g = _f32(logits), _f32(g)
     K = x.shape[-1]
     d = torch.empty_like(x)
-    C.call("ups_weak_xent_bwd", x.data_ptr(), mode, g.data_ptr(), d.data_ptr(), x.numel() // K, K, _stream())
+    C.call("ups_weak_xent_bwd", x.data_ptr(), mode, g.data_ptr(), d.data_ptr(), x.numel() // K, K, _stream(x))
     return d
 
 
@@ -672,7 +674,7 @@ def _mask2rgb(mask: Tensor, table: Tensor, make_hot: bool) -> Tensor:
     assert list(table.shape) == [K, 3], list(table.shape)
     out = torch.empty(*mask.shape[:-1], 3, dtype=torch.float32, device=mask.device)
     C.call("ups_mask2rgb_fwd", mask.data_ptr(), table.data_ptr(), int(make_hot), out.data_ptr(), mask.numel() // K, K,
-           _stream())
+           _stream(mask))
     return out
 
 
@@ -685,7 +687,7 @@ def _inject_conv_table(feat: Tensor, V: Tensor) -> Tensor:
     B, K, F = feat.shape
     Co = V.shape[-1]
     G = torch.empty(B, 9, K, Co, dtype=torch.float32, device=feat.device)
-    C.call("ups_inject_conv_table_fwd", feat.data_ptr(), V.data_ptr(), G.data_ptr(), B, K, F, Co, _stream())
+    C.call("ups_inject_conv_table_fwd", feat.data_ptr(), V.data_ptr(), G.data_ptr(), B, K, F, Co, _stream(feat))
     return G
 
 
@@ -695,7 +697,7 @@ def _inject_conv_table_grad(dG: Tensor, feat: Tensor, V: Tensor) -> Tuple[Tensor
     Co = V.shape[-1]
     dfeat, dV = torch.empty_like(feat), torch.empty_like(V)
     C.call("ups_inject_conv_table_bwd", dG.data_ptr(), feat.data_ptr(), V.data_ptr(), dfeat.data_ptr(), dV.data_ptr(),
-           B, K, F, Co, _stream())
+           B, K, F, Co, _stream(dG))
     return dfeat, dV
 
 
@@ -713,7 +715,7 @@ def _inject_conv_apply(mask: Tensor, G: Tensor, bias: Tensor) -> Tensor:
     Co = G.shape[-1]
     out = torch.empty(B, H, W, Co, dtype=torch.float32, device=mask.device)
     C.call("ups_inject_conv_fwd", mask.data_ptr(), G.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, K, Co,
-           _stream())
+           _stream(mask))
     return out
 
 
@@ -728,7 +730,7 @@ def _inject_conv_apply_grad(g_out: Tensor, mask: Tensor, G: Tensor, probs: Optio
     db = torch.empty(Co, dtype=torch.float32, device=mask.device)
     ws = _ws(C.inject_conv_workspace_bytes(B, H, W, K, Co), mask)
     C.call("ups_inject_conv_bwd", g_out.data_ptr(), mask.data_ptr(), G.data_ptr(), _ptr(probs), _ptr(g_extra),
-           dmask.data_ptr(), dG.data_ptr(), db.data_ptr(), B, H, W, K, Co, ws.data_ptr(), ws.numel(), _stream())
+           dmask.data_ptr(), dG.data_ptr(), db.data_ptr(), B, H, W, K, Co, ws.data_ptr(), ws.numel(), _stream(g_out))
     return dmask, dG, db
 
 
@@ -770,7 +772,7 @@ def _parts_conv(image: Tensor, mask: Tensor, V: Tensor, bias: Tensor) -> Tensor:
     Cin, Co = image.shape[-1], V.shape[-1]
     out = torch.empty(K * B, H, W, Co, dtype=torch.float32, device=image.device)
     C.call("ups_parts_conv_fwd", image.data_ptr(), mask.data_ptr(), V.data_ptr(), bias.data_ptr(), out.data_ptr(),
-           B, H, W, K, Cin, Co, _stream())
+           B, H, W, K, Cin, Co, _stream(image))
     return out
 
 
@@ -782,7 +784,7 @@ def _parts_conv_grad(g_out: Tensor, image: Tensor, mask: Tensor, V: Tensor) -> T
     db = torch.empty(Co, dtype=torch.float32, device=mask.device)
     ws = _ws(C.parts_conv_bwd_workspace_bytes(B, H, W, K, Co), mask)
     C.call("ups_parts_conv_bwd", g_out.data_ptr(), image.data_ptr(), mask.data_ptr(), V.data_ptr(), None, None,
-           dmask.data_ptr(), dV.data_ptr(), db.data_ptr(), B, H, W, K, Cin, Co, ws.data_ptr(), ws.numel(), _stream())
+           dmask.data_ptr(), dV.data_ptr(), db.data_ptr(), B, H, W, K, Cin, Co, ws.data_ptr(), ws.numel(), _stream(g_out))
     return dmask, dV, db
 
 

@@ -25,8 +25,16 @@ import torch
 from . import _cabi as C
 
 
-def _cur_stream():
-    return torch.cuda.current_stream().cuda_stream
+def _on_device(fn):
+    """Run a PartStep method with the step's device current: the C ABI launches on the device that is current on
+    the calling thread, on the stream it is given, so both must be the device that owns the step's buffers."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class PartStep:
@@ -40,6 +48,8 @@ class PartStep:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise C.UpsError("PartStep needs a CUDA device: there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.fused = K in (8, 16, 32) and F in (16, 32, 64) and self.P % 32 == 0
         # K4 variant: "tc" = persistent TMA + tcgen05/TMEM pipeline, "simt" = CUDA-core kernel
         tc_ok = self.fused and K in (16, 32) and F == 64 and self.P % 128 == 0
@@ -83,14 +93,12 @@ class PartStep:
             self.dfm = e(B, S, S, 3, **f32)
         self._views_f32 = None   # allocated on first use: fp32 copy of uint8 views (data.py:134 on the device)
         self._img1 = None
+        self._warped = None
         self._feat = None
         self._coord = None
-        # K3 (decode side: l0, feat only) does not depend on the warp: it runs on a side stream beside
-        # K1 (issue-bound canonical TPS math, ~12 % DRAM) and K2
-        self.overlap_fwd = self.fused and self.use_tps and os.environ.get("UPS_OVERLAP_FWD", "1") != "0"
-        if self.overlap_fwd:
-            self._side = torch.cuda.Stream(device=self.device, priority=-1)
-            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------ forward
     def _decode_fwd(self, l0, feat, conv_V, conv_b, st):
@@ -110,30 +118,25 @@ class PartStep:
         """views [V,B,S,S,3] (view0, view1[, view0_target]), fp32 in [-1, 1] or the dataset's uint8
         (normalised on the device exactly as cub/code/data/data.py:134 does on the host); coord,
         t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
-        of views into the step's persistent output buffers."""
-        B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
-        st = _cur_stream()
+        of views into the step's persistent output buffers.
+
+        = forward_warp (K1: needs only the input batch and the TPS parameters) followed by forward_parts
+        (K2, K3: need the encoders' outputs); the data-parallel wrapper puts its gradient wait between the two."""
+        self.forward_warp(views, coord, t_vector)
+        return self.forward_parts(l0, l1, feat, conv_V, conv_b)
+
+    @_on_device
+    def forward_warp(self, views, coord, t_vector):
+        """K1: the TPS equivariance warp of the views (model.py:282-311).  Returns the warped views [V,B,S,S,3]."""
+        B, S, V = self.B, self.S, self.V
+        st = self._stream()
         if views.dtype == torch.uint8:
             assert views.is_contiguous() and tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
             if self._views_f32 is None:
                 self._views_f32 = torch.empty(V, B, S, S, 3, dtype=torch.float32, device=self.device)
             C.call("ups_views_u8_to_f32", views.data_ptr(), self._views_f32.data_ptr(), views.numel(), st)
             views = self._views_f32
-        assert views.is_contiguous() and l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
-        assert tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
-        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
-        if self.Co:
-            assert conv_V is not None and conv_b is not None, "first_conv: pass conv_V [3,3,F+K,Co] and conv_b [Co]"
-            assert tuple(conv_V.shape) == (3, 3, F + K, self.Co) and tuple(conv_b.shape) == (self.Co,)
-            assert conv_V.is_contiguous() and conv_b.is_contiguous()
-            self._conv_V = conv_V
-        if self.overlap_fwd:
-            main = torch.cuda.current_stream()
-            self._fork.record(main)
-            self._side.wait_event(self._fork)
-            with torch.cuda.stream(self._side):
-                self._decode_fwd(l0, feat, conv_V, conv_b, self._side.cuda_stream)
-                self._join.record(self._side)
+        assert views.is_contiguous() and tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
         if self.use_tps:
             assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
             C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
@@ -143,30 +146,38 @@ class PartStep:
             else:
                 C.call("ups_tps_warp_fwd", views.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
                        self.warped.data_ptr(), None, 2 * B, S, S, 3, S, S, st)
-            warped = self.warped
+            self._warped = self.warped
             self._coord = coord
         else:
-            warped = views
+            self._warped = views
+        return self._warped
+
+    @_on_device
+    def forward_parts(self, l0, l1, feat, conv_V=None, conv_b=None):
+        """K2 (encode side: l1, warped view 1) and K3 (decode side: l0, feat) on the current stream."""
+        B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
+        st = self._stream()
+        assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
+        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        if self.Co:
+            assert conv_V is not None and conv_b is not None, "first_conv: pass conv_V [3,3,F+K,Co] and conv_b [Co]"
+            assert tuple(conv_V.shape) == (3, 3, F + K, self.Co) and tuple(conv_b.shape) == (self.Co,)
+            assert conv_V.is_contiguous() and conv_b.is_contiguous()
+            self._conv_V = conv_V
+        warped = self._warped
         img1 = warped[1]
         self._img1, self._feat = img1, feat
         if self.fused:
             C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
                    self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
-            if self.overlap_fwd:
-                torch.cuda.current_stream().wait_event(self._join)
-            else:
-                self._decode_fwd(l0, feat, conv_V, conv_b, st)
-        elif self.Co:
-            C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
-            C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
-            C.call("ups_part_pool_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.pooled.data_ptr(), B, P, K, 3, 0,
-                   1.0 / P, self.ws.data_ptr(), self.ws.numel(), st)
-            self._decode_fwd(l0, feat, conv_V, conv_b, st)
         else:
             C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
             C.call("ups_part_pool_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.pooled.data_ptr(), B, P, K, 3, 0,
                    1.0 / P, self.ws.data_ptr(), self.ws.numel(), st)
+        if self.fused or self.Co:
+            self._decode_fwd(l0, feat, conv_V, conv_b, st)
+        else:
             C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
                    self.mh0.data_ptr(), B * P, K, st)
             C.call("ups_part_inject_fwd", feat.data_ptr(), self.mh0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
@@ -181,12 +192,21 @@ class PartStep:
     def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None):
         """Cotangents: g_inj [B,S,S,F+K] (with first_conv: g_h0 [B,S,S,Co] in its place), g_parts [K*B,S,S,3]
         (part-major), g_pooled [B,K,3], g_m0/g_m1 [B,S,S,K] (from the mask losses), g_warped [V,B,S,S,3]
-        (views_grad only).  Returns dict(dl0, dl1, dfeat[, dV, db][, dviews])."""
-        B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
-        st = _cur_stream()
-        img1, feat = self._img1, self._feat
+        (views_grad only).  Returns dict(dl0, dl1, dfeat[, dV, db][, dviews]).
+
+        = backward_decode (K4: dl0, dfeat — what the appearance encoder's backward needs) followed by
+        backward_encode (K5 [, K6]: dl1 [, dviews])."""
+        out = self.backward_decode(g_inj, g_m0)
+        out.update(self.backward_encode(g_parts, g_pooled, g_m1, g_warped))
+        return out
+
+    @_on_device
+    def backward_decode(self, g_inj, g_m0=None):
+        """K4: autodiff of the decode side.  g_inj, g_m0 -> dl0 [B,S,S,K], dfeat [B,K,F] [, dV, db]."""
+        B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
+        st = self._stream()
+        feat = self._feat
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-        want_dimg = self.views_grad
         if self.Co:
             assert tuple(g_inj.shape) == (B, S, S, self.Co), list(g_inj.shape)
             C.call("ups_inject_conv_bwd", g_inj.data_ptr(), self.mh0c.data_ptr(), self.G.data_ptr(), self.m0.data_ptr(),
@@ -194,42 +214,49 @@ class PartStep:
                    self.ws_ic.data_ptr(), self.ws_ic.numel(), st)
             C.call("ups_inject_conv_table_bwd", self.dG.data_ptr(), feat.data_ptr(), self._conv_V.data_ptr(),
                    self.dfeat.data_ptr(), self.dV.data_ptr(), B, K, F, self.Co, st)
-        if self.fused and self.Co:
-            C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
-                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
         elif self.fused:
             C.call("ups_step_decode_bwd_tc" if self.decode_bwd == "tc" else "ups_step_decode_bwd",
                    g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
                    self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
+        else:
+            # dm0 = inject-bwd (+ g_m0, accumulated by the kernel) -> softmax-bwd
+            C.call("ups_part_inject_bwd", g_inj.data_ptr(), feat.data_ptr(), self.mh0.data_ptr(),
+                   self.dfeat.data_ptr(), self.dm.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
+            C.call("ups_part_softmax_bwd2", self.m0.data_ptr(), self.dm.data_ptr(), p(g_m0), None, self.dl0.data_ptr(),
+                   B * P, K, st)
+        out = dict(dl0=self.dl0, dfeat=self.dfeat)
+        if self.Co:
+            out["dV"], out["db"] = self.dV, self.db
+        return out
+
+    @_on_device
+    def backward_encode(self, g_parts, g_pooled=None, g_m1=None, g_warped=None):
+        """K5 (autodiff of the encode side: dl1 [, dimg1]) and, with views_grad, K6 (TPS backward: dviews)."""
+        B, S, K, P, V = self.B, self.S, self.K, self.P, self.V
+        st = self._stream()
+        img1 = self._img1
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        want_dimg = self.views_grad
+        if self.fused:
             C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
                    p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
         else:
-            if not self.Co:
-                C.call("ups_part_inject_bwd", g_inj.data_ptr(), feat.data_ptr(), self.mh0.data_ptr(),
-                       self.dfeat.data_ptr(), self.dm.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
-                g0 = self.dm if g_m0 is None else self.dm.add_(g_m0)
-                C.call("ups_part_softmax_bwd", self.m0.data_ptr(), g0.data_ptr(), self.dl0.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
                    self.dimg1.data_ptr() if want_dimg else None, self.dm.data_ptr(), B, P, K, 3, 1, st)
             if g_pooled is not None:
                 C.call("ups_part_pool_bwd", g_pooled.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
                        self.dfm.data_ptr() if want_dimg else None, self.dm2.data_ptr(), B, P, K, 3, 0, 1.0 / P, st)
-                self.dm.add_(self.dm2)
                 if want_dimg:
-                    self.dimg1.add_(self.dfm)
-            if g_m1 is not None:
-                self.dm.add_(g_m1)
-            C.call("ups_part_softmax_bwd", self.m1.data_ptr(), self.dm.data_ptr(), self.dl1.data_ptr(), B * P, K, st)
-        out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
-        if self.Co:
-            out["dV"], out["db"] = self.dV, self.db
+                    C.call("ups_axpy", self.dfm.data_ptr(), self.dimg1.data_ptr(), self.dimg1.numel(), 1.0, st)
+            # dl1 = softmax-bwd(m1, dm + dm2 + g_m1): the three cotangents are summed inside the kernel
+            C.call("ups_part_softmax_bwd2", self.m1.data_ptr(), self.dm.data_ptr(),
+                   self.dm2.data_ptr() if g_pooled is not None else None, p(g_m1), self.dl1.data_ptr(), B * P, K, st)
+        out = dict(dl1=self.dl1)
         if self.views_grad:
             if self.use_tps:
-                if g_warped is None:
-                    self.gw.zero_()
-                else:
-                    self.gw.copy_(g_warped)
-                self.gw[1].add_(self.dimg1)
+                # cotangent of the warped views: g_warped (+ dimg1 on view 1), summed by the library
+                C.call("ups_views_cotangent", p(g_warped), self.dimg1.data_ptr(), self.gw.data_ptr(), max(V, 2), 1,
+                       B * P * 3, st)
                 coord = self._coord
                 if V > 2:
                     C.call("ups_tps_warp_pair_bwd", self.gw.data_ptr(), self.gw[2].data_ptr(), coord.data_ptr(),
@@ -237,13 +264,10 @@ class PartStep:
                 else:
                     C.call("ups_tps_warp_bwd", self.gw.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
                            self.dviews.data_ptr(), 2 * B, S, S, 3, S, S, st)
-                out["dviews"] = self.dviews
             else:
-                self.dviews.zero_()
-                if g_warped is not None:
-                    self.dviews.copy_(g_warped)
-                self.dviews[1].add_(self.dimg1)
-                out["dviews"] = self.dviews
+                C.call("ups_views_cotangent", p(g_warped), self.dimg1.data_ptr(), self.dviews.data_ptr(), max(V, 2), 1,
+                       B * P * 3, st)
+            out["dviews"] = self.dviews
         return out
 
     # kernels enqueued by one forward+backward (bench.py's gpu_launches is counted, not assumed)
