@@ -16,16 +16,21 @@
 //
 // Ranks synchronise with two flag barriers on a caller-owned, zero-initialised signal pad in peer memory
 // (slot [cta][src rank] on the destination rank, compare-and-swap 0->1 by the sender with release, 1->0 by
-// the receiver with acquire: self-resetting, no epoch counter, no host involvement).  The kernel uses a
-// handful of small CTAs (default 16 x 512 threads, 0 bytes of shared memory) so that it co-resides with the
-// persistent K4 grid instead of taking SMs away from it.
+// the receiver with acquire: self-resetting, no epoch counter, no host involvement).
+//
+// Co-residency is the design constraint: the kernel runs BESIDE the path's backward.  K4 is a persistent grid of one
+// 448-thread CTA per SM holding 120 registers per thread (53 760 of the SM's 65 536) and ~200 KB of shared memory; a
+// CTA of this kernel is 256 threads x <= 40 registers (10 240) and no shared memory, so it fits into what K4 leaves
+// free on every SM and starts at once instead of waiting for K4's CTAs to retire (a 512-thread CTA did not fit:
+// measured at N=2, its first bucket only started once K4 had drained and 0.2 ms of the reduction was exposed).
 #include "common.cuh"
 
 namespace ups {
 namespace dp {
 
 constexpr int MAX_WORLD = 16;
-constexpr int TPB = 512;
+constexpr int TPB = 256;
+constexpr int MIN_CTAS_PER_SM = 6;   // caps ptxas at 65536 / (256*6) = 42 registers per thread
 constexpr int UNROLL = 4;
 constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // a dead peer must not hang the GPU
 
@@ -95,7 +100,7 @@ __device__ __forceinline__ void st_peer(float* p, float4 v) {
 }
 
 template <bool MC>
-__global__ void __launch_bounds__(TPB) dp_allreduce_kernel(const Peers pr, float* __restrict__ mc, int rank, int world,
+__global__ void __launch_bounds__(TPB, MIN_CTAS_PER_SM) dp_allreduce_kernel(const Peers pr, float* __restrict__ mc, int rank, int world,
                                                             long long n4, float scale) {
     rank_barrier(pr, rank, world);   // every rank's bucket is complete (its producers precede this kernel in stream order)
     const long long per = (n4 + world - 1) / world;
