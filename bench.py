@@ -147,18 +147,24 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-KERNEL_BYTES_PER_PX = {
-    # algorithmic (compulsory) bytes per pixel of each C-ABI call, fp32, K parts, F features, C=3
-    "ups_tps_warp_fwd": lambda K, F: 4 * (3 + 3),
-    "ups_tps_warp_pair_fwd": lambda K, F: 4 * (3 + 3),
-    "ups_tps_warp_pair_bwd": lambda K, F: 4 * (3 + 3),
-    "ups_step_encode_fwd": lambda K, F: 4 * (K + 3 + K + 3 * K),
-    "ups_step_decode_fwd": lambda K, F: 4 * (K + K + 2 + F + K),
-    "ups_step_decode_bwd": lambda K, F: 4 * ((F + K) + K + K + K),
-    "ups_step_decode_bwd_tc": lambda K, F: 4 * ((F + K) + K + K + K),
-    "ups_step_encode_bwd": lambda K, F: 4 * (3 * K + 3 + K + K + K),
-    "ups_tps_warp_bwd": lambda K, F: 4 * (3 + 3),
-}
+def call_bytes(name, K, F, V, B, P):
+    """Algorithmic (compulsory) bytes of one C-ABI call of the step, fp32, K parts, F features, 3 channels; None if the
+    call is not one of the path kernels.  Per decode/encode pixel there are B*P pixels, per warped pixel V*B*P."""
+    warp_px, px = V * B * P, B * P
+    per = {
+        "ups_tps_warp_fwd": (4 * (3 + 3), warp_px), "ups_tps_warp_pair_fwd": (4 * (3 + 3), warp_px),
+        "ups_tps_warp_bwd": (4 * (3 + 3), warp_px), "ups_tps_warp_pair_bwd": (4 * (3 + 3), warp_px),
+        "ups_step_encode_fwd": (4 * (K + 3 + K + 3 * K), px),
+        "ups_step_decode_fwd": (4 * (K + K + 2 + F + K), px),
+        "ups_step_decode_bwd": (4 * ((F + K) + K + K + K), px), "ups_step_decode_bwd_tc": (4 * ((F + K) + K + K + K), px),
+        "ups_step_encode_bwd": (4 * (3 * K + 3 + K + K + K), px),
+        # K1 + K3 in one launch: the decode side's bytes per pixel plus V warped pixels of 24 bytes
+        "ups_step_warp_decode_fwd": (4 * (K + K + 2 + F + K) + V * 4 * (3 + 3), px),
+    }
+    if name not in per:
+        return None
+    b, n = per[name]
+    return b * n
 
 
 CALL_KERNEL = {  # C-ABI call -> the kernel that dominates it (profiles/ncu_traffic.json keys)
@@ -291,8 +297,7 @@ def measure_workload(args, torch, dist, ups_b200, name, B, dev, rank, world, red
             per_call.setdefault(cname, []).append(e0.elapsed_time(e1))
         call_ms = {n: sum(v) / steps for n, v in per_call.items()}
         dom = max(call_ms, key=call_ms.get)
-        px = V * B * P if dom.startswith("ups_tps_warp") else B * P
-        dom_bytes = KERNEL_BYTES_PER_PX[dom](K, F) * px if dom in KERNEL_BYTES_PER_PX else None
+        dom_bytes = call_bytes(dom, K, F, V, B, P)
         n_dom = len(per_call[dom]) / steps
         dom_launch_ms = call_ms[dom] / n_dom
         achieved = (dom_bytes / n_dom) / (dom_launch_ms * 1e-3) / 1e9 if dom_bytes else None
@@ -303,10 +308,8 @@ def measure_workload(args, torch, dist, ups_b200, name, B, dev, rank, world, red
                            "algorithmic_bytes_per_launch": dom_bytes / n_dom if dom_bytes else None,
                            "launch_ms": dom_launch_ms}
         rec["per_call_ms"] = {k: round(v, 4) for k, v in sorted(call_ms.items())}
-        rec["per_call_frac_of_hbm"] = {
-            k: round(KERNEL_BYTES_PER_PX[k](K, F) * (V * B * P if k.startswith("ups_tps_warp") else B * P)
-                     / (v * 1e-3) / 1e9 / peak, 4)
-            for k, v in sorted(call_ms.items()) if k in KERNEL_BYTES_PER_PX and v > 0}
+        rec["per_call_frac_of_hbm"] = {k: round(call_bytes(k, K, F, V, B, P) / (v * 1e-3) / 1e9 / peak, 4)
+                                       for k, v in sorted(call_ms.items()) if call_bytes(k, K, F, V, B, P) and v > 0}
     return rec, dp, t
 
 
@@ -314,7 +317,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import ups_b200
-    from ups_b200.dp import GradAllReducer, DECODER_SHARE, init_from_env
+    from ups_b200.dp import GradAllReducer, init_from_env, two_buckets
 
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
     cores = set_rank_affinity(int(os.environ.get("LOCAL_RANK", "0")), local_world) if not args.no_affinity else None
@@ -328,9 +331,7 @@ def run_gpu(args):
     S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
     # one flat gradient buffer (symmetric memory when N>1) shared by every workload measured in this process
     n_grad = (int(args.grad_mb * 1e6 / 4) + 3) // 4 * 4
-    n_dec = (int(n_grad * DECODER_SHARE) + 3) // 4 * 4
-    reducer = GradAllReducer(n_grad, dev, buckets=[(0, n_dec), (n_dec, n_grad - n_dec)], impl=args.allreduce,
-                             n_ctas=args.allreduce_ctas)
+    reducer = GradAllReducer(n_grad, dev, buckets=two_buckets(n_grad), impl=args.allreduce, n_ctas=args.allreduce_ctas)
     warm = max(args.warmup, 3)
     rec, dp, t = measure_workload(args, torch, dist, ups_b200, args.workload, B, dev, rank, world, reducer, args.steps, warm,
                                   detailed=True)

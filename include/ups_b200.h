@@ -293,6 +293,15 @@ int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mas
                        void* ws, size_t ws_bytes, void* stream);
 size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
 
+/* K1 + K3 of the fused step in ONE launch (csrc/step_fwd_fused.cu): the TPS warp of the views (ups_tps_warp_pair_fwd's
+ * arguments: U [N,S,S,3], optional second image set U2 [N2,S,S,3] sharing the first N2 warps, coord, T -> out, out2) and
+ * the decode-side forward (ups_step_decode_fwd's arguments) are independent (model.py:282-311 vs :426-447,482-484);
+ * their CTAs are interleaved in one grid so that the warp's arithmetic hides under the decode side's memory stream.
+ * Results are bit-identical to the two separate calls.  K in {8,16,32}, F in {16,32,64}, S*S % 32 == 0. */
+int ups_step_warp_decode_fwd(const float* U, const float* U2, const float* coord, const float* T, float* out, float* out2,
+                             int N, int N2, int S, const float* l0, const float* feat, float* m0, long long* labels0,
+                             float* inj, int B, int K, int F, void* stream);
+
 /* ---- data-parallel step wrapper (SURVEY.md 8d "DP step", 8e) ------------------------------------------------
  * The reference trains on one GPU; the only multi-GPU analogue in its tree is the IMM baseline's host-side tower
  * averaging (baselines/imm/imm/train/cnn_train_multi.py:75-118, `average_gradients`).  ups_dp_allreduce is that mean

@@ -66,11 +66,12 @@ def test_shard_bounds_cover_batch():
 
 
 def test_bucket_split_is_16_byte_aligned_and_covers():
-    from ups_b200.dp import _split, DECODER_SHARE
+    from ups_b200.dp import _split, two_buckets, TAIL_BUCKET_FLOATS
     for n in (4, 1000, 33_300_000, 33_300_004):
         for parts in (1, 2, 3, 7):
             b = _split(n, parts)
             assert b[0][0] == 0 and b[-1][0] + b[-1][1] == n
             assert all(o % 4 == 0 for o, _ in b)
             assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(parts - 1))
-    assert 0.3 < DECODER_SHARE < 0.6
+    b = two_buckets(33_300_002)
+    assert b[0][0] == 0 and b[0][1] + b[1][1] == 33_300_004 and b[1][1] == TAIL_BUCKET_FLOATS and b[1][0] % 4 == 0

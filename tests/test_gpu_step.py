@@ -244,3 +244,19 @@ def test_first_conv_step(ups, B, S, K, F, Co):
     assert_close(grad["dfeat"], dfeat_o, "dfeat", atol=4 * reduce_atol(S * S * 9))
     assert_close(grad["dV"], dV_o, "dV", atol=4 * reduce_atol(B * S * S))
     assert_close(grad["db"], db_o, "db", atol=4 * reduce_atol(B * S * S))
+
+
+@pytest.mark.parametrize("B,S,K,F,V", [(4, 128, 16, 64, 3), (3, 96, 8, 16, 2), (2, 64, 32, 64, 3)])
+def test_fused_forward_launch_equals_two_kernels(ups, B, S, K, F, V):
+    """K1 + K3 in one launch (ups_step_warp_decode_fwd) is bit-identical to K1 and K3 as two kernels."""
+    from ups_b200.step import PartStep
+    d = cuda(make_inputs(B, S, K, F, V, seed=5, ties=True))
+    one = PartStep(B, S, K, F, n_views=V)
+    assert one.fuse_fwd
+    a = one.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    two = PartStep(B, S, K, F, n_views=V)
+    two.forward_warp(d["views"], d["coord"], d["t_vector"])
+    b = two.forward_parts(d["l0"], d["l1"], d["feat"])
+    torch.cuda.synchronize()
+    for k in ("warped", "m0", "m1", "labels0", "parts", "pooled", "inj"):
+        assert torch.equal(a[k], b[k]), k

@@ -15,13 +15,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "step_decode_fwd.cuh"
 
 namespace ups {
 
-constexpr int FW = 4;           // warps per CTA
-constexpr int FTPB = FW * 32;
 constexpr int MS = 34;          // row stride of the per-warp [K][32] mask stash (conflict-free)
-constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -31,33 +29,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// ============================================================================ K3 decode fwd
-// general rows (tied maxima somewhere in these PW pixels): sum over parts in ascending k
-template <int LPP>
-__device__ __noinline__ void inject_rows_general(float4 mh, const float4* fs4, float* rows, int NF4, int FK, int lane) {
-    constexpr int K = 4 * LPP, PW = 32 / LPP;
-    const int nf_it = (NF4 + 31) >> 5;
-    for (int pix_l = 0; pix_l < PW; ++pix_l) {
-        for (int it = 0; it < nf_it; ++it) {
-            const int f4 = it * 32 + lane;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int src = pix_l * LPP + (k >> 2);
-                const float comp = ((k & 3) == 0) ? mh.x : ((k & 3) == 1) ? mh.y : ((k & 3) == 2) ? mh.z : mh.w;
-                const float mk = __shfl_sync(FULL, comp, src);
-                if (mk != 0.f && f4 < NF4) {
-                    const float4 fv = fs4[k * NF4 + f4];
-                    acc.x = fmaf(mk, fv.x, acc.x); acc.y = fmaf(mk, fv.y, acc.y);
-                    acc.z = fmaf(mk, fv.z, acc.z); acc.w = fmaf(mk, fv.w, acc.w);
-                }
-            }
-            if (f4 < NF4) st4_stream(rows + (size_t)pix_l * FK + 4 * f4, acc);
-        }
-    }
-}
-
-// FT = compile-time F (0: run-time F) so that the row/column split of the inject store is shifts
+// ============================================================================ K3 decode fwd (body: step_decode_fwd.cuh)
 template <int LPP, int FT>
 __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __restrict__ l0,
                                                                const float* __restrict__ feat,
@@ -65,54 +37,8 @@ __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __re
                                                                long long* __restrict__ labels0,
                                                                float* __restrict__ inj, int P, int Frt,
                                                                int pix_per_cta) {
-    constexpr int K = 4 * LPP, PW = 32 / LPP;
     extern __shared__ float4 fs4[];  // feat[b] as [K][F/4] float4
-    const int b = blockIdx.y;
-    const int F = FT > 0 ? FT : Frt;
-    const int NF4 = F >> 2, FK = F + K;
-    for (int i = threadIdx.x; i < K * NF4; i += FTPB) fs4[i] = ld4(feat + (size_t)b * K * F + 4 * i);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = lane & (LPP - 1), plq = lane / LPP;
-    const int p_begin = blockIdx.x * pix_per_cta, p_end = min(P, p_begin + pix_per_cta);
-    const int n_items = PW * NF4, n_it = (n_items + 31) >> 5;
-    for (int pg = p_begin + warp * 32; pg < p_end; pg += FW * 32) {
-        float4 v[LPP];
-#pragma unroll
-        for (int s = 0; s < LPP; ++s)
-            v[s] = ld4_stream(l0 + (((size_t)b * P + pg + s * PW + plq) * LPP + c) * 4);
-#pragma unroll
-        for (int s = 0; s < LPP; ++s) {
-            const size_t pix = (size_t)b * P + pg + s * PW + plq;
-            float pmax; int arg, nmax;
-            const float4 p4 = softmax4<LPP>(v[s], c, pmax, arg, nmax);
-            st4(m0 + (pix * LPP + c) * 4, p4);
-            if (c == 0) labels0[pix] = arg;
-            const float4 mh = hard_st4(p4, pmax);
-            st4_stream(inj + pix * FK + F + 4 * c, mh);
-            const float mon = st_value(1.0f, pmax);
-            float* rows = inj + ((size_t)b * P + pg + s * PW) * FK;
-            if (!__any_sync(FULL, nmax > 1)) {
-                // one-hot fast path: row = mon * feat[arg, :]
-#pragma unroll 4
-                for (int it = 0; it < n_it; ++it) {
-                    const int idx = it * 32 + lane;
-                    const bool valid = idx < n_items;
-                    const int pix_l = valid ? idx / NF4 : 0;
-                    const int f4 = idx - pix_l * NF4;
-                    const int k = __shfl_sync(FULL, arg, pix_l * LPP);
-                    const float mv = __shfl_sync(FULL, mon, pix_l * LPP);
-                    if (valid) {
-                        const float4 fv = fs4[k * NF4 + f4];
-                        st4_stream(rows + (size_t)pix_l * FK + 4 * f4,
-                                   make_float4(fv.x * mv, fv.y * mv, fv.z * mv, fv.w * mv));
-                    }
-                }
-            } else {
-                inject_rows_general<LPP>(mh, fs4, rows, NF4, FK, lane);
-            }
-        }
-    }
+    step_decode_fwd_body<LPP, FT>(l0, feat, m0, labels0, inj, P, Frt, pix_per_cta, blockIdx.x, blockIdx.y, fs4);
 }
 
 // ============================================================================ K2 encode fwd

@@ -19,13 +19,12 @@ How the collective is done here
   co-resides with the persistent K4 grid.  Without a multicast object the same kernel reads and
   writes the peers' buffers directly.  If symmetric memory is not available at all the wrapper
   falls back to `ncclAllReduce(SUM)` and hands the consumer the scale (`grad_scale`).
-* Two buckets, launched where their producers finish:
-    decoder bucket (the stand-in decoder head's gradient + the padding that stands for dd, dv and
-    the discriminators) at the top of backward, overlapped with K4;
-    encoder bucket (the stand-in encoder tail's gradient, which needs K4's dfeat, + the padding for
-    e_pi and e_alpha) after K4, overlapped with K5/K6 and with the next step's K1: the TPS warp
-    depends on the input batch only, not on the updated parameters, so `forward` waits for the
-    gradients between K1 and K2 (`wait_grads()` for whoever consumes them earlier).
+* Two buckets, launched where their producers finish (the reduction overlaps K4-K6):
+    main bucket — the stand-in decoder head's gradient and all the padding — at the top of backward (everything a
+    decoder-side module contributes exists before the path's backward starts), overlapped with K4 and K5;
+    tail bucket — the stand-in encoder tail's gradient (1024 floats), which needs K4's dfeat — after K4,
+    overlapped with K5/K6.
+  The next forward (`forward`) waits for both before its first kernel; `wait_grads()` for whoever consumes them earlier.
 * The stand-in gradients are computed on the reducer's side stream: they feed the collective,
   not the path.
 """
@@ -37,9 +36,14 @@ import torch.distributed as dist
 
 from . import _cabi as C
 
-# parameter counts of the reference's CNNs (e_pi 13.6 M, e_alpha 5.0 M | dv 6 M, three
-# discriminators 8.4 M, dd 0.2 M): share of the flat buffer whose gradients exist before the path's backward starts
-DECODER_SHARE = 14.6 / 33.2
+TAIL_BUCKET_FLOATS = 1024     # the stand-in encoder tail's gradient (4*F floats) lives at the head of the last 1024 floats
+
+
+def two_buckets(n_floats):
+    """[(0, n - 1024), (n - 1024, 1024)]: main bucket (top of backward) and tail bucket (after K4)."""
+    n = (int(n_floats) + 3) // 4 * 4
+    assert n >= 2 * TAIL_BUCKET_FLOATS, n
+    return [(0, n - TAIL_BUCKET_FLOATS), (n - TAIL_BUCKET_FLOATS, TAIL_BUCKET_FLOATS)]
 
 
 def shard_bounds(global_batch, rank, world_size):
@@ -266,10 +270,8 @@ class DataParallelPartStep:
         K, F = self.step.K, self.step.F
         self.mod = StandInModules(K, F, dev, seed)
         if reducer is None:     # `reducer`: an existing two-bucket GradAllReducer (one symmetric allocation per process)
-            n = max(int(n_grad_params), 4 * (self.mod.n_head + self.mod.n_tail + 8))
-            n = (n + 3) // 4 * 4
-            n_dec = max((int(n * DECODER_SHARE) + 3) // 4 * 4, (self.mod.n_head + 3) // 4 * 4)
-            reducer = GradAllReducer(n, dev, buckets=[(0, n_dec), (n_dec, n - n_dec)], impl=allreduce, n_ctas=allreduce_ctas)
+            n = (max(int(n_grad_params), 4 * TAIL_BUCKET_FLOATS) + 3) // 4 * 4
+            reducer = GradAllReducer(n, dev, buckets=two_buckets(n), impl=allreduce, n_ctas=allreduce_ctas)
         assert len(reducer.bounds) == 2 and reducer.bounds[0][1] >= self.mod.n_head and reducer.bounds[1][1] >= self.mod.n_tail
         n_dec = reducer.bounds[1][0]
         self.reducer = reducer
@@ -282,10 +284,9 @@ class DataParallelPartStep:
 
     # ---------------------------------------------------------------- forward
     def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None):
-        # K1 needs the batch only; the parameters (hence the averaged gradients) are needed from K2/K3 on
-        self.step.forward_warp(views, coord, t_vector)
+        # the parameters (hence the averaged gradients of the previous step) are needed from the first kernel on
         self.reducer.wait()
-        return self.step.forward_parts(l0, l1, feat, conv_V, conv_b)
+        return self.step.forward(views, coord, t_vector, l0, l1, feat, conv_V, conv_b)
 
     def wait_grads(self):
         """The current stream waits until both buckets hold the mean over ranks (times 1/grad_scale for NCCL)."""
@@ -300,7 +301,7 @@ class DataParallelPartStep:
         B, P, K, F = st.B, st.P, st.K, st.F
         side = red.stream
         main = torch.cuda.current_stream(dev)
-        # decoder side: its gradients exist before the path's backward starts
+        # main bucket: everything a decoder-side module contributes exists before the path's backward starts
         side.wait_stream(main)
         if g_recon is not None:
             with torch.cuda.device(dev):
@@ -309,7 +310,7 @@ class DataParallelPartStep:
         self._ev.record(side)
         red.launch(0, after=self._ev)
         out = st.backward_decode(g_inj, g_m0)
-        # encoder side: the tail's gradient needs dfeat (K4)
+        # tail bucket: the encoder tail's gradient needs dfeat (K4)
         self._ev.record(main)
         side.wait_event(self._ev)
         with torch.cuda.device(dev):

@@ -91,6 +91,9 @@ class PartStep:
             self.dm = e(B, S, S, K, **f32)
             self.dm2 = e(B, S, S, K, **f32)
             self.dfm = e(B, S, S, 3, **f32)
+        # K1 and K3 in one launch (csrc/step_fwd_fused.cu); UPS_FUSE_FWD=0 keeps them as two kernels
+        self.fuse_fwd = (self.fused and self.use_tps and not self.Co and K in (8, 16, 32) and F in (16, 32, 64)
+                         and os.environ.get("UPS_FUSE_FWD", "1") != "0")
         self._views_f32 = None   # allocated on first use: fp32 copy of uint8 views (data.py:134 on the device)
         self._img1 = None
         self._warped = None
@@ -120,16 +123,38 @@ class PartStep:
         t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
         of views into the step's persistent output buffers.
 
-        = forward_warp (K1: needs only the input batch and the TPS parameters) followed by forward_parts
-        (K2, K3: need the encoders' outputs); the data-parallel wrapper puts its gradient wait between the two."""
+        On the fused path K1 (TPS warp) and K3 (decode side) are independent and run as ONE launch with interleaved
+        CTAs (ups_step_warp_decode_fwd): the warp's arithmetic hides under the decode side's memory stream.
+        forward_warp / forward_parts are the same step as two calls (K1 | K2, K3) for callers that have the views
+        before the logits."""
+        if self.fuse_fwd:
+            return self._forward_fused(views, coord, t_vector, l0, l1, feat)
         self.forward_warp(views, coord, t_vector)
         return self.forward_parts(l0, l1, feat, conv_V, conv_b)
 
     @_on_device
-    def forward_warp(self, views, coord, t_vector):
-        """K1: the TPS equivariance warp of the views (model.py:282-311).  Returns the warped views [V,B,S,S,3]."""
-        B, S, V = self.B, self.S, self.V
+    def _forward_fused(self, views, coord, t_vector, l0, l1, feat):
+        B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
         st = self._stream()
+        views = self._ingest(views, st)
+        assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
+        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
+        C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
+        C.call("ups_step_warp_decode_fwd", views.data_ptr(), views[2].data_ptr() if V > 2 else None, coord.data_ptr(),
+               self.T.data_ptr(), self.warped.data_ptr(), self.warped[2].data_ptr() if V > 2 else None, 2 * B,
+               B if V > 2 else 0, S, l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
+               self.inj.data_ptr(), B, K, F, st)
+        self._warped, self._coord = self.warped, coord
+        img1 = self.warped[1]
+        self._img1, self._feat = img1, feat
+        C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+               self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
+        return dict(warped=self.warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
+                    pooled=self.pooled, inj=self.inj)
+
+    def _ingest(self, views, st):
+        B, S, V = self.B, self.S, self.V
         if views.dtype == torch.uint8:
             assert views.is_contiguous() and tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
             if self._views_f32 is None:
@@ -137,6 +162,14 @@ class PartStep:
             C.call("ups_views_u8_to_f32", views.data_ptr(), self._views_f32.data_ptr(), views.numel(), st)
             views = self._views_f32
         assert views.is_contiguous() and tuple(views.shape) == (V, B, S, S, 3), list(views.shape)
+        return views
+
+    @_on_device
+    def forward_warp(self, views, coord, t_vector):
+        """K1: the TPS equivariance warp of the views (model.py:282-311).  Returns the warped views [V,B,S,S,3]."""
+        B, S, V = self.B, self.S, self.V
+        st = self._stream()
+        views = self._ingest(views, st)
         if self.use_tps:
             assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
             C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
