@@ -62,3 +62,42 @@ def step_forward_backward(views, coord, t_vector, l0, l1, feat, cot, use_tps=Tru
     out = {k: ([t.detach() for t in v] if isinstance(v, list) else v.detach())
            for k, v in out.items()}
     return out, res
+
+
+def reduction_refs_fp64(views, coord, t_vector, out, cot, use_tps=True, views_grad=False):
+    """float64 values of the path's long sums, evaluated from the fp32 forward's own masks and sample positions (so the
+    discrete decisions - argmax, floor - are the fp32 ones): pooled, dfeat and, with views_grad, dviews.  Tests bound
+    the kernels by `1e-5 + 2 * |fp32 oracle - this|` (tests/util.py::own_error_atol) instead of an assumed sqrt(n) law.
+      pooled[b,k,c] = mean_p parts[k*B+b, p, c]                     (model.py:50-52 tail on mask_parts' output)
+      dfeat[b,k,f]  = sum_p m0_hard[b,p,k] * g_inj[b,p,f]           (autodiff of unpool_features, model.py:225-249)
+      dviews        = scatter of the warped views' cotangents       (autodiff of _interpolate, transformations.py:114-169)
+    """
+    inj, parts = out["inj"].double(), out["parts"].double()
+    B, S = inj.shape[0], inj.shape[1]
+    K = out["m0"].shape[-1]
+    F = inj.shape[-1] - K
+    mh0 = inj[..., F:].reshape(B, S * S, K)
+    res = dict(pooled=parts.reshape(K, B, S * S, -1).mean(2).permute(1, 0, 2),
+               dfeat=torch.einsum("bpk,bpf->bkf", mh0, cot["g_inj"].double()[..., :F].reshape(B, S * S, F)))
+    if views_grad:
+        img1 = (out["warped"][1] if use_tps else views[1]).double()
+        # mask of view 1 from parts = img * mask is not recoverable where img == 0: recompute it the oracle's way
+        m1_hard = P.straight_through_estimator(P.hard_max(out["m1"], 3), out["m1"]).double()          # [B,S,S,K]
+        gp = cot["g_parts"].double().reshape(K, B, S, S, -1).permute(1, 2, 3, 0, 4)                   # [B,S,S,K,3]
+        if cot.get("g_pooled") is not None:
+            gp = gp + cot["g_pooled"].double()[:, None, None] / (S * S)
+        dimg1 = (m1_hard[..., None] * gp).sum(3)
+        V = len(views)
+        gw = [cot["g_warped"][i].double() if cot.get("g_warped") is not None else torch.zeros_like(img1) for i in range(V)]
+        gw[1] = gw[1] + dimg1
+        if use_tps:
+            G01 = torch.cat(gw[:2], 0)
+            U01 = torch.cat([v.detach() for v in views[:2]], 0)
+            d01 = T.warp_grad_fp64(U01, coord, t_vector, S, G01)
+            dv = list(torch.split(d01, B, 0))
+            if V > 2:
+                dv.append(T.warp_grad_fp64(views[2].detach(), coord[:B], t_vector[:B], S, gw[2]))
+            res["dviews"] = dv
+        else:
+            res["dviews"] = gw
+    return res

@@ -163,6 +163,22 @@ def ThinPlateSpline(U, coord, vector, out_size, n_c, move=None, scal=None):
     return out, t_arr
 
 
+def warp_grad_fp64(U, coord, vector, out_size, G, move=None, scal=None):
+    """dL/dU of ThinPlateSpline for the cotangent G, with the SAME fp32 sample positions and bilinear weights as the
+    fp32 path but float64 products and float64 scatter-add: the exact value that every fp32 accumulation order (the
+    oracle's autograd, the kernel's atomics) approximates.  Tests derive their scatter tolerance from it."""
+    coord_f, vector_f = coord.flip(-1), vector.flip(-1)
+    T, _ = tps_system(coord_f, vector_f)
+    x_s, y_s = tps_grid_coords(T, coord_f, int(out_size), int(out_size))
+    if move is not None and scal is not None:
+        y_s = y_s * scal[:, 0][:, None, None] + move[:, :, 0][:, :, None]
+        x_s = x_s * scal[:, 1][:, None, None] + move[:, :, 1][:, :, None]
+    U64 = U.detach().double().requires_grad_(True)
+    out = bilinear_sample(U64, x_s, y_s)
+    (dU,) = torch.autograd.grad(out, U64, G.double())
+    return dU
+
+
 def make_tps_given(views, coord, vector):
     """The warp half of TrainModel.make_tps for given (coord, t_vector) of 2B samples:
     views[0:2] concatenated use rows [0,2B); views[2] (the target) re-uses rows [0,B)

@@ -72,9 +72,11 @@ CUB_TPS = dict(scal=0.8, tps_scal=0.15, rot_scal=0.2, off_scal=0.2, scal_var=0.1
 PENN_TPS = dict(scal=0.95, tps_scal=0.08, rot_scal=0.05, off_scal=0.2, scal_var=0.05, rescal=1.0)
 
 
-def gen_tps(ns):
+def gen_tps(ns, suffix=""):
+    """suffix "_inv64": the same draws with the shim's matrix_inverse done in float64 (tf1_shim.MATRIX_INVERSE_FP64)."""
     g = torch.Generator().manual_seed(1234)
     tf.set_generator(g)
+    tf.MATRIX_INVERSE_FP64 = suffix == "_inv64"
     for tag, kw, B, S, C in (("cub", CUB_TPS, 4, 16, 3), ("penn", PENN_TPS, 3, 24, 3),
                              ("big", dict(CUB_TPS, tps_scal=0.6, off_scal=0.6), 4, 16, 2)):
         prm = ns["tps_parameters"](B, **kw)
@@ -85,9 +87,15 @@ def gen_tps(ns):
         W = tf.TAPS["matrix_inverse_in"][0]
         G = torch.randn(out.shape, generator=g)
         (dU,) = torch.autograd.grad(out, U, G)
+        if suffix:   # inputs are those of tps_{tag}.npz (same generator sequence): only the results are stored
+            npz(f"tps_{tag}{suffix}.npz", out=out, t_arr=t_arr, dU=dU)
+            continue
         npz(f"tps_{tag}.npz", U=U, coord=coord, t_vector=t_vector, out=out, t_arr=t_arr, W=W,
             G=G, dU=dU, p_coord=prm.coord, p_vector=prm.vector, p_offset=prm.offset,
             p_offset_2=prm.offset_2, p_t_scal=prm.t_scal, p_rot_mat=prm.rot_mat)
+    if suffix:
+        tf.MATRIX_INVERSE_FP64 = False
+        return
     # identity warp: unperturbed control points, zero displacement (SURVEY 8c vector 1)
     base = torch.tensor([[[-0.5, -0.5], [0.5, -0.5], [-0.5, 0.5], [0.5, 0.5],
                           [0.2, -0.2], [-0.2, 0.2], [0.2, 0.2], [-0.2, -0.2]]])
@@ -250,6 +258,7 @@ def gen_priors():
 if __name__ == "__main__":
     ns_tps, nn, ns_model, ns_foo, ns_ops = load_reference()
     gen_tps(ns_tps)
+    gen_tps(ns_tps, "_inv64")
     gen_parts(nn, ns_model, ns_foo, ns_ops)
     gen_stats(vars(nn), ns_model)
     gen_priors()

@@ -41,24 +41,28 @@ def test_tps_system_matrix(golden):
 
 
 def test_tps_mesh_and_output(golden):
-    # The reference inverts W in fp32 (cond 15..460): its coordinates carry ~1e-5 noise
-    # (observed 1.1e-5 max).  Output is compared where the bilinear stencil is the same in
-    # both, i.e. the sample is not within 2e-3 px of a cell border (the identity warp lands
-    # ON cell borders in its first/last rows, where floor() legitimately flips).
-    for name in ("tps_cub.npz", "tps_penn.npz", "tps_big.npz", "tps_identity.npz"):
-        g = golden(name)
+    """Oracle vs the reference's own ThinPlateSpline executed under the shim.  For the shipped parameter ranges (CUB,
+    PennAction) every pixel is inside the north-star tolerance, with the reference's fp32 matrix inverse
+    (transformations.py:228) AND with the inverse done in float64 (tps_*_inv64.npz): the fp32 inverse costs at most
+    1.4e-6 in normalised coordinates there.  The 4x exaggerated `big` warp and the identity warp (samples exactly on cell
+    borders) are held to the bound their measured sample-position difference implies (util.check_tps_against_fixture)."""
+    from util import check_tps_against_fixture
+    for tag, strict in (("cub", True), ("penn", True), ("big", False), ("identity", False)):
+        g = golden(f"tps_{tag}.npz")
         U = t(g["U"])
-        out, mesh = T.ThinPlateSpline(U, t(g["coord"]), t(g["t_vector"]), U.shape[1], U.shape[3])
-        close(mesh, g["t_arr"], 0, 3e-5)
         S = U.shape[1]
-        pix = (t(g["t_arr"]) + 1) * S / 2
-        frac = pix - torch.floor(pix)
-        safe = ((frac > 2e-3) & (frac < 1 - 2e-3)).all(-1)
-        if "identity" not in name:
-            assert safe.float().mean() > 0.97
-        d = (out - t(g["out"])).abs()[safe]
-        assert d.max() < 3e-4, d.max()           # |dU/dpx| <= 2 per px  x  coordinate noise
-        assert d.mean() < 1e-5
+        out, mesh = T.ThinPlateSpline(U, t(g["coord"]), t(g["t_vector"]), S, U.shape[3])
+        refs = [("fp32 inverse", g)]
+        if tag != "identity":
+            refs.append(("fp64 inverse", golden(f"tps_{tag}_inv64.npz")))
+        for name, r in refs:
+            n_white, dmesh = check_tps_against_fixture(out, mesh, t(r["out"]), t(r["t_arr"]), S, strict, f"{tag} / {name}")
+            assert dmesh < (2e-6 if strict else 2e-5), (tag, name, dmesh)
+            if tag == "big":
+                assert n_white <= 4, n_white
+    # the inverse's precision is NOT what separates oracle and reference on `big`: both fixtures sit equally far
+    g, h = golden("tps_big.npz"), golden("tps_big_inv64.npz")
+    assert np.abs(g["t_arr"] - h["t_arr"]).max() < 2e-5
 
 
 def test_tps_move_scal_branch(golden):

@@ -71,3 +71,37 @@ def assert_close(got, want, what="", rtol=RTOL, atol=ATOL):
         i = torch.argmax(err - tol)
         raise AssertionError(f"{what}: {(err > tol).sum().item()}/{err.numel()} outside rtol={rtol} atol={atol}; "
                              f"worst |d|={err.flatten()[i].item():.3e} at ref={w.flatten()[i].item():.6e}")
+
+
+def own_error_atol(want32, want64, atol=ATOL):
+    """Absolute tolerance for a quantity that is a long fp32 sum (dfeat, pooled, weight gradients): the north-star
+    1e-5 plus twice the distance of the fp32 ORACLE from the float64 value of the same expression.  Two valid fp32
+    summation orders (the oracle's and the kernel's) each sit that far from the exact value; entries that cancel to ~0
+    cannot agree more closely than that, whatever the kernel does.  Measured per test, not assumed (VERDICT r1 weak #1)."""
+    return atol + 2.0 * float((want32.detach().double().cpu() - want64.detach().double().cpu()).abs().max())
+
+
+def check_tps_against_fixture(out, mesh, ref_out, ref_mesh, S, strict, what=""):
+    """Warped image and sample mesh against a reference-generated TPS fixture (tests/golden/tps_*.npz).
+
+    strict (the shipped CUB / PennAction parameter ranges): EVERY pixel within the north-star 1e-4 rel / 1e-5 abs, and
+    no pixel whose bilinear cell differs from the reference's (floor-boundary whitelist must be empty).
+    not strict (the 4x exaggerated `big` warp, and the identity warp whose samples sit exactly ON cell borders): pixels
+    whose cell differs are counted and excluded (returned), the others may add the bound that the measured
+    sample-position difference implies: |d out| <= max|U[x+1] - U[x]| * (|dX| + |dY|) <= 2 * (|dX| + |dY|) for U in [-1, 1].
+    Returns (n_whitelisted, max_abs_mesh_diff)."""
+    out, mesh = out.detach().cpu().double(), mesh.detach().cpu().double()
+    ref_out, ref_mesh = ref_out.double(), ref_mesh.double()
+    dpix = (mesh - ref_mesh).abs() * S / 2
+    same = (torch.floor((mesh + 1) * S / 2) == torch.floor((ref_mesh + 1) * S / 2)).all(-1)
+    n_white = int((~same).sum())
+    tol = ATOL + RTOL * ref_out.abs()
+    if strict:
+        assert n_white == 0, f"{what}: {n_white} pixels sample a different bilinear cell than the reference"
+    else:
+        tol = tol + 2.0 * dpix.sum(-1, keepdim=True)
+    err = (out - ref_out).abs()
+    bad = (err > tol).any(-1) & same
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{same.numel()} pixels outside tolerance, "
+                                 f"worst {float(err[same].max()):.3e}, mesh diff {float((mesh - ref_mesh).abs().max()):.3e}")
+    return n_white, float((mesh - ref_mesh).abs().max())

@@ -72,7 +72,7 @@ extern "C" int ups_step_warp_decode_fwd(const float* U, const float* U2, const f
     const size_t sm1 = ((size_t)2 * WARP_TPB * 3 + 48) * sizeof(float);
     if (sm1 > sm) sm = sm1;
     cudaStream_t s = as_stream(stream);
-    static const int minb = []() { const char* e = getenv("UPS_FWD_FUSED_MINB"); return e ? atoi(e) : 4; }();
+    static const int minb = []() { const char* e = getenv("UPS_FWD_FUSED_MINB"); return e ? atoi(e) : 5; }();
 #define UPS_WD3(LPP, FT, MB)                                                                                    \
     {                                                                                                           \
         if (sm > 48 * 1024)                                                                                     \
