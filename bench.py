@@ -431,10 +431,13 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
         views_h = t["views"].cpu().pin_memory()
     coord_h, tv_h = t["coord"].pin_memory(), t["tv"].pin_memory()
     step = dp.step
-    lab_h = torch.empty(step.labels0.shape, dtype=torch.int64).pin_memory()
+    # u8 leg: the label map is read back at one byte per pixel too (ups_labels_i64_to_u8; n_parts <= 255)
+    lab_dtype = torch.uint8 if u8 else torch.int64
+    lab_h = torch.empty(step.labels0.shape, dtype=lab_dtype).pin_memory()
     pooled_h = torch.empty(step.pooled.shape).pin_memory()
     dfeat_h = torch.empty(step.dfeat.shape).pin_memory()
-    lab_d, pooled_d, dfeat_d = (torch.empty_like(x) for x in (step.labels0, step.pooled, step.dfeat))
+    lab_d = torch.empty(step.labels0.shape, dtype=lab_dtype, device=dev)
+    pooled_d, dfeat_d = (torch.empty_like(x) for x in (step.pooled, step.dfeat))
     bufs = [dict(views=torch.empty(views_h.shape, dtype=views_h.dtype, device=dev),
                  coord=torch.empty(coord_h.shape, device=dev),
                  tv=torch.empty(tv_h.shape, device=dev)) for _ in range(2)]
@@ -446,7 +449,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
     done = torch.cuda.Event()
     drained = torch.cuda.Event()
     h2d = views_h.numel() * views_h.element_size() + coord_h.numel() * 4 + tv_h.numel() * 4
-    d2h = lab_h.numel() * 8 + pooled_h.numel() * 4 + dfeat_h.numel() * 4
+    d2h = lab_h.numel() * lab_h.element_size() + pooled_h.numel() * 4 + dfeat_h.numel() * 4
 
     def stage(i):
         b = bufs[i % 2]
@@ -473,7 +476,7 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
             # results -> a device staging copy (35 MB device-to-device, ~12 us), read back from there on
             # its own stream: the D2H of step i overlaps the kernels of step i+1
             main_s.wait_event(drained)          # the previous read-back has left the staging buffers
-            lab_d.copy_(step.labels0, non_blocking=True)
+            lab_d.copy_(step.labels_u8() if u8 else step.labels0, non_blocking=True)
             pooled_d.copy_(step.pooled, non_blocking=True)
             dfeat_d.copy_(step.dfeat, non_blocking=True)
             done.record(main_s)
@@ -508,10 +511,10 @@ def run_e2e(args, torch, dist, dp, dev, world, t, B, u8=False):
     return {"value": world * B * n / (ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": n, "ms_per_step": ms / n,
             "h2d_GBs_per_rank": h2d / (ms / n * 1e-3) / 1e9, "d2h_GBs_per_rank": d2h / (ms / n * 1e-3) / 1e9,
-            "boundary": ("host: %s views + TPS params in, int64 labels + pooled + dfeat out; "
+            "boundary": ("host: %s views + TPS params in, %s labels + pooled + dfeat out; "
                          "logits/features/cotangents device-resident (CNN outputs in the real model)")
-                        % ("uint8 (normalised on the device as cub/code/data/data.py:134 does on the host)" if u8
-                           else "fp32")}
+                        % (("uint8 (normalised on the device as cub/code/data/data.py:134 does on the host)", "uint8") if u8
+                           else ("fp32", "int64"))}
 
 
 def main():

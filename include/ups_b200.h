@@ -62,6 +62,10 @@ size_t ups_workspace_bytes(int op, int B, int P, int K, int F);
  * src: n uint8 values (any NHWC image batch), dst: n fp32 values; both 16-byte aligned device pointers.
  * Bit-identical to the numpy expression (fp32 multiply, correctly rounded divide, subtract). */
 int ups_views_u8_to_f32(const unsigned char* src, float* dst, long long n, void* stream);
+/* The other direction of the host boundary: int64 part labels (tf.argmax's dtype, cub/code/SB_model48i/model.py:447,470)
+ * narrowed to one byte per pixel for the read-back of the label map (n_parts <= 255; the evaluation code only uses the
+ * labels as an index map, cub/code/eval/eval_iclr_01/eval_01.py:237-239).  labels 16-byte aligned, out 4-byte aligned. */
+int ups_labels_i64_to_u8(const long long* labels, unsigned char* out, long long n, void* stream);
 
 /* ---- thin-plate-spline warp -------------------------------------------------------- */
 /* make_input_tps_param(tps_param) — baselines/unsupervised-disentangling/transformations.py:59-77

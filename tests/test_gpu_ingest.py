@@ -57,3 +57,12 @@ def test_step_accepts_uint8_views(ups):
         assert_bitexact(out["warped"][i], want["warped"][i].cpu(), f"warped[{i}]")
     assert_bitexact(out["parts"], want["parts"].cpu(), "parts")
     assert_bitexact(out["pooled"], want["pooled"].cpu(), "pooled")
+
+
+def test_labels_to_u8():
+    from ups_b200 import _cabi as C
+    for n in (1, 3, 4, 1000, 128 * 128 * 8 + 3):
+        lab = torch.randint(0, 25, (n,), dtype=torch.int64, device="cuda")
+        out = torch.full((n + 4,), 77, dtype=torch.uint8, device="cuda")
+        C.call("ups_labels_i64_to_u8", lab.data_ptr(), out.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        assert torch.equal(out[:n].cpu(), lab.cpu().to(torch.uint8)) and bool((out[n:] == 77).all())

@@ -242,3 +242,17 @@ def test_golden_chain_through_public_api(ups, golden):
 def test_cpu_tensors_are_rejected(ups):
     with pytest.raises(Exception):
         ups.softmax(torch.randn(1, 2, 2, 4))
+
+
+def test_unpool_features_gathered_backward(ups):
+    """tf.gather is differentiable in feature_vectors (cub/code/nn.py:2469-2487): dfeat = segment sum of the cotangent."""
+    B, S, K, F = 3, 24, 25, 16
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(B, K, F, generator=g)
+    labels = torch.randint(0, K, (B, S, S), generator=g)
+    G = torch.randn(B, S, S, F, generator=g)
+    fo = feat.clone().requires_grad_(True)
+    (d_o,) = torch.autograd.grad(OP.unpool_features_gathered(fo, labels), fo, G)
+    fc = feat.cuda().requires_grad_(True)
+    (d_c,) = torch.autograd.grad(ups.unpool_features_gathered(fc, labels.cuda()), fc, G.cuda())
+    assert_close(d_c, d_o, "dfeat of the gathered unpooling")

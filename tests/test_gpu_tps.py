@@ -140,3 +140,18 @@ def test_make_tps_three_and_two_views(ups):
     out_c2 = ups.make_tps([v.cuda() for v in views[:2]], kw, generator=torch.Generator().manual_seed(42))
     assert len(out_c2) == 2
     assert_bitexact(out_c2[1], out_o[1], "make_tps (2 views)")
+
+
+def test_warp_parameter_gradients_raise(ups):
+    """gradients with respect to the warp parameters or through the mesh are an error, not a silent zero."""
+    from ups_b200._cabi import UpsError
+    prm, U, g = _case(2, 16, 3, CUB_TPS, 1)
+    coord, tv = OT.make_input_tps_param(prm)
+    with pytest.raises(UpsError, match="must not require grad"):
+        ups.ThinPlateSpline(U.cuda(), coord.cuda().requires_grad_(True), tv.cuda(), 16, 3)
+    Uc = U.cuda().requires_grad_(True)
+    out, mesh = ups.ThinPlateSpline(Uc, coord.cuda(), tv.cuda(), 16, 3)
+    with pytest.raises(Exception, match="sampling mesh"):
+        torch.autograd.grad(mesh.sum() + out.sum(), Uc)
+    (dU,) = torch.autograd.grad(ups.ThinPlateSpline(Uc, coord.cuda(), tv.cuda(), 16, 3)[0].sum(), Uc)
+    assert dU.shape == Uc.shape

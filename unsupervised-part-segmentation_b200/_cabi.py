@@ -13,6 +13,7 @@ c_fl = ctypes.c_float
 
 _SIGS = {
     "ups_views_u8_to_f32": [c_f, c_f, c_ll, c_f],
+    "ups_labels_i64_to_u8": [c_f, c_f, c_ll, c_f],
     "ups_tps_input_param": [c_f] * 7 + [c_i, c_f],
     "ups_tps_solve": [c_f, c_f, c_f, c_i, c_f],
     "ups_tps_warp_fwd": [c_f] * 7 + [c_i] * 6 + [c_f],

@@ -117,6 +117,18 @@ __global__ void __launch_bounds__(WARP_TPB, MINB) tps_warp_fwd_kernel(const floa
                          sm_const, sm_out);
 }
 
+// three consecutive floats at a 4-byte aligned address p (p + even offset is 8-byte aligned when the base is):
+// one 8-byte vector reduction + one scalar reduction
+__device__ __forceinline__ void red_add3(float* p, const float (&v)[3]) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p + 2), "f"(v[2]) : "memory");
+    } else {
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p + 1), "f"(v[1]), "f"(v[2]) : "memory");
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __restrict__ g_out,
                                                                 const float* __restrict__ g_out2,
@@ -139,6 +151,7 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
     float* Ub = dU + (size_t)b * H * W * Cc;
     float* Ub2 = second ? dU2 + (size_t)b * H * W * Cc : nullptr;
     float* sm_g2 = sm_g + WARP_TPB * Cc;
+    const bool vec_red = ((reinterpret_cast<uintptr_t>(dU) | reinterpret_cast<uintptr_t>(dU2)) & 7u) == 0;
     const int tile0 = blockIdx.x * (WARP_TPB * WARP_PPT);
 #pragma unroll 1
     for (int it = 0; it < WARP_PPT; ++it) {
@@ -153,13 +166,58 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
         }
         __syncthreads();
         const int pix = base + threadIdx.x;
-        if (pix < OP) {
+        const bool live = pix < OP;
+        Bilinear s;
+        int oa = -1, ob = -1, oc = -1, od = -1;
+        if (live) {
             const int i = pix / ow, j = pix - i * ow;
             float x_s, y_s;
             sample_position(k, has_move, i, j, step_h, step_w, x_s, y_s);
-            const Bilinear s = bilinear_stencil(x_s, y_s, W, H);
-            const int oa = (s.y0 * W + s.x0) * Cc, ob = (s.y1 * W + s.x0) * Cc;
-            const int oc = (s.y0 * W + s.x1) * Cc, od = (s.y1 * W + s.x1) * Cc;
+            s = bilinear_stencil(x_s, y_s, W, H);
+            oa = (s.y0 * W + s.x0) * Cc; ob = (s.y1 * W + s.x0) * Cc;
+            oc = (s.y0 * W + s.x1) * Cc; od = (s.y1 * W + s.x1) * Cc;
+        }
+        if (C == 3 && vec_red) {
+            // Scatter with a quarter of the reduction traffic.  (1) Neighbouring output pixels of a row sample
+            // neighbouring source pixels: lane L's right corners (x1) are lane L+1's left corners (x0) whenever the
+            // addresses coincide (~80 % of the lanes at the shipped scales), so L adds its neighbour's left
+            // contributions to its own right ones in registers and the neighbour drops them.  The test is address
+            // equality, so the result is the same sum whatever the warp looks like.  (2) A corner's three channels
+            // go out as one 8-byte vector reduction + one scalar instead of three scalars.
+            // Out-of-range samples keep all four (cancelling) contributions, as autodiff of the forward does.
+            const unsigned FULLM = 0xffffffffu;
+            const int lane = threadIdx.x & 31;
+            const int n_oa = __shfl_down_sync(FULLM, oa, 1), n_ob = __shfl_down_sync(FULLM, ob, 1);
+            const int p_oc = __shfl_up_sync(FULLM, oc, 1), p_od = __shfl_up_sync(FULLM, od, 1);
+            const bool take_a = live && lane < 31 && n_oa == oc && n_oa >= 0;   // I absorb my right neighbour's a
+            const bool take_b = live && lane < 31 && n_ob == od && n_ob >= 0;
+            const bool gave_a = live && lane > 0 && p_oc == oa && p_oc >= 0;    // my a was absorbed by my left neighbour
+            const bool gave_b = live && lane > 0 && p_od == ob && p_od >= 0;
+            const int n_img = second ? 2 : 1;
+            for (int im = 0; im < n_img; ++im) {
+                const float* sg = (im ? sm_g2 : sm_g) + threadIdx.x * 3;
+                float* Ud = im ? Ub2 : Ub;
+                float ca[3], cb[3], cc[3], cd[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float g = live ? sg[c] : 0.f;
+                    ca[c] = live ? s.wa * g : 0.f; cb[c] = live ? s.wb * g : 0.f;
+                    cc[c] = live ? s.wc * g : 0.f; cd[c] = live ? s.wd * g : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float na = __shfl_down_sync(FULLM, ca[c], 1), nb = __shfl_down_sync(FULLM, cb[c], 1);
+                    if (take_a) cc[c] += na;
+                    if (take_b) cd[c] += nb;
+                }
+                if (live) {
+                    if (!gave_a) red_add3(Ud + oa, ca);
+                    if (!gave_b) red_add3(Ud + ob, cb);
+                    red_add3(Ud + oc, cc);
+                    red_add3(Ud + od, cd);
+                }
+            }
+        } else if (live) {
             for (int c = 0; c < Cc; ++c) {
                 // out-of-range samples have coinciding clipped corners whose weights cancel:
                 // keep all four adds so that the sum matches autodiff of the forward exactly.

@@ -102,6 +102,10 @@ def _tps_warp_fake(U, coord, T, out_size, move, scal):
 
 def _tps_warp_setup(ctx, inputs, output):
     U, coord, T, out_size, move, scal = inputs
+    # gradients reach the images only: the reference draws the TPS / crop parameters at random (model.py:298-300) and
+    # they are data, not variables.  Asking for more raises instead of silently returning nothing.
+    ctx.set_materialize_grads(False)
+    ctx.param_grad = any(t is not None and t.requires_grad for t in (coord, T, move, scal))
     ctx.save_for_backward(coord, T, *([move, scal] if move is not None else []))
     ctx.has_move = move is not None
     ctx.shape = tuple(U.shape)
@@ -109,7 +113,14 @@ def _tps_warp_setup(ctx, inputs, output):
 
 
 def _tps_warp_bwd(ctx, g_out, g_mesh):
+    if ctx.param_grad:
+        raise C.UpsError("ups_b200: ThinPlateSpline has no gradient with respect to coord / T / move / scal "
+                         "(the warp parameters are data in the reference, model.py:298-300); detach them")
+    if g_mesh is not None:
+        raise C.UpsError("ups_b200: no gradient flows through the sampling mesh (t_arr) of ThinPlateSpline")
     saved = ctx.saved_tensors
+    if g_out is None:
+        return None, None, None, None, None, None
     coord, T = saved[0], saved[1]
     move, scal = (saved[2], saved[3]) if ctx.has_move else (None, None)
     dU = tps_warp_grad(g_out, coord, T, list(ctx.shape), ctx.out_size, move, scal)
@@ -439,7 +450,21 @@ def _part_gather(feat: Tensor, labels: Tensor) -> Tensor:
     return out
 
 
-part_gather = _op("part_gather", _part_gather, lambda f, l: f.new_empty(*l.shape, f.shape[-1]))
+def _part_gather_setup(ctx, inputs, output):
+    feat, labels = inputs
+    ctx.save_for_backward(labels)
+    ctx.K = feat.shape[1]
+
+
+def _part_gather_bwd(ctx, g):
+    """tf.gather is differentiable in `feature_vectors` (cub/code/nn.py:2469-2487): dfeat[b,k,:] is the sum of g over
+    the pixels labelled k = the dense pooling of g with the one-hot mask (deterministic fixed-order sums)."""
+    (labels,) = ctx.saved_tensors
+    return part_pool(g.contiguous(), one_hot(labels, ctx.K), False, 1.0), None
+
+
+part_gather = _op("part_gather", _part_gather, lambda f, l: f.new_empty(*l.shape, f.shape[-1]),
+                  _part_gather_bwd, _part_gather_setup)
 
 
 # ------------------------------------------------------------------ mask statistics (SURVEY.md 8f N1/N2)

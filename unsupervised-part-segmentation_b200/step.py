@@ -94,6 +94,7 @@ class PartStep:
         # K1 and K3 in one launch (csrc/step_fwd_fused.cu); UPS_FUSE_FWD=0 keeps them as two kernels
         self.fuse_fwd = (self.fused and self.use_tps and not self.Co and K in (8, 16, 32) and F in (16, 32, 64)
                          and os.environ.get("UPS_FUSE_FWD", "1") != "0")
+        self._labels_u8 = None
         self._views_f32 = None   # allocated on first use: fp32 copy of uint8 views (data.py:134 on the device)
         self._img1 = None
         self._warped = None
@@ -152,6 +153,17 @@ class PartStep:
                self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
         return dict(warped=self.warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
                     pooled=self.pooled, inj=self.inj)
+
+    @_on_device
+    def labels_u8(self):
+        """labels0 narrowed to uint8 on the device (n_parts <= 255): the label map a host-side consumer reads back,
+        one byte per pixel instead of tf.argmax's eight."""
+        assert self.K <= 255
+        if self._labels_u8 is None:
+            self._labels_u8 = torch.empty(self.labels0.shape, dtype=torch.uint8, device=self.device)
+        C.call("ups_labels_i64_to_u8", self.labels0.data_ptr(), self._labels_u8.data_ptr(), self.labels0.numel(),
+               self._stream())
+        return self._labels_u8
 
     def _ingest(self, views, st):
         B, S, V = self.B, self.S, self.V

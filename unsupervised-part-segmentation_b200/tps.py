@@ -60,6 +60,12 @@ def ThinPlateSpline(U, coord, vector, out_size, n_c, move=None, scal=None):
     assert coord.shape == vector.shape and coord.shape[0] == U.shape[0] and tuple(coord.shape[1:]) == (8, 2), \
         list(coord.shape)
     assert (move is None) == (scal is None)
-    T = ops.tps_solve(coord.detach(), vector.detach())
-    out, mesh = ops.tps_warp(U, coord.detach(), T, int(out_size), move, scal)
+    # Gradients flow to the images U only.  The reference draws coord / vector / move / scal at random every step
+    # (cub/code/SB_model48i/model.py:298-300): they are data, never variables.  A caller that asks for their gradient
+    # gets an error here rather than a silently missing one (the TF graph would have propagated it).
+    if any(t is not None and t.requires_grad for t in (coord, vector, move, scal)):
+        raise ops.C.UpsError("ups_b200.ThinPlateSpline: coord / vector / move / scal must not require grad "
+                             "(no gradient with respect to the warp parameters is implemented); detach them")
+    T = ops.tps_solve(coord, vector)
+    out, mesh = ops.tps_warp(U, coord, T, int(out_size), move, scal)
     return out, mesh
