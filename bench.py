@@ -540,7 +540,7 @@ def main():
                          "(33.3 M fp32 parameters of the reference's CNNs, SURVEY.md section 2)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],
                     help="gradient mean when N>1: ups_dp_allreduce over symmetric memory (multicast / peer) or ncclAllReduce")
-    ap.add_argument("--allreduce-ctas", type=int, default=32, help="CTAs of the all-reduce kernel")
+    ap.add_argument("--allreduce-ctas", type=int, default=64, help="CTAs of the all-reduce kernel")
     ap.add_argument("--no-scale-workloads", action="store_true", help="skip the DeepFashion / PennAction legs")
     ap.add_argument("--no-affinity", action="store_true", help="do not give each rank its own slice of the host cores")
     ap.add_argument("--no-e2e", action="store_true")

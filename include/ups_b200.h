@@ -315,7 +315,7 @@ int ups_step_warp_decode_fwd(const float* U, const float* U2, const float* coord
  *                then the kernel reads and writes the peers' buckets through peer_bufs
  *   peer_signals HOST array [world] of mappings of every rank's signal pad: ups_dp_allreduce_signal_bytes(world, n_ctas)
  *                bytes, zero-initialised once by its owner before the first call (the barriers reset it themselves)
- *   scale        applied to the sum (1/world for the mean); n_floats % 4 == 0; n_ctas CTAs of 256 threads, <= 42 registers,
+ *   scale        applied to the sum (1/world for the mean); n_floats % 4 == 0; n_ctas CTAs of 128 threads, <= 42 registers,
  *                no shared memory (sized to co-reside with the persistent K4 grid)
  * All ranks must enqueue the call with the same n_floats/n_ctas; the kernel waits (device side, no host sync) until
  * every rank's call has started, i.e. until the producers of every rank's bucket have finished in stream order. */

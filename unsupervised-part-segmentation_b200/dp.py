@@ -100,7 +100,7 @@ class GradAllReducer:
 
     MAX_CTAS = 4 * 148      # the signal pad is sized for this many CTAs: `n_ctas` may be changed between launches
 
-    def __init__(self, n_floats=None, device=None, buckets=None, impl="auto", n_ctas=32, flat_grads=None,
+    def __init__(self, n_floats=None, device=None, buckets=None, impl="auto", n_ctas=64, flat_grads=None,
                  bucket_bytes=None, world_size=None, group=None):
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
@@ -260,7 +260,7 @@ class DataParallelPartStep:
 
     def __init__(self, per_gpu_batch, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
                  views_grad=False, n_grad_params=33_300_000, device="cuda", decode_bwd="auto", allreduce="auto",
-                 allreduce_ctas=32, seed=0, reducer=None):
+                 allreduce_ctas=64, seed=0, reducer=None):
         from .step import PartStep
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
