@@ -19,7 +19,7 @@
 // the receiver with acquire: self-resetting, no epoch counter, no host involvement).
 //
 // Co-residency is the design constraint: the kernel runs BESIDE the path's backward.  K4 is a persistent grid of one
-// 448-thread CTA per SM holding 128 registers per thread (57 344 of the SM's 65 536) and ~200 KB of shared memory; a
+// 448-thread CTA per SM holding 120 registers per thread (53 760 of the SM's 65 536) and ~200 KB of shared memory; a
 // CTA of this kernel is 128 threads x <= 40 registers (5 120) and no shared memory, so it fits into what K4 leaves
 // free on every SM and starts at once instead of waiting for K4's CTAs to retire (a 512-thread CTA did not fit:
 // measured at N=2, its first bucket only started once K4 had drained and 0.2 ms of the reduction was exposed).

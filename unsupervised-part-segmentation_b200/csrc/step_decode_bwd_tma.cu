@@ -337,14 +337,6 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             for (int i = 0; i < (K * F) / 128; ++i) sts4(accw + (i * 32 + lane) * 16, make_float4(0.f, 0.f, 0.f, 0.f));
         };
         zero_acc();
-        // K == 16: the warp's dfeat accumulators live in REGISTERS (lane = feature pair, 16 labels x float2); the
-        // row's label is warp-uniform, so the update is one FFMA2 behind a warp-uniform switch.  Shared memory only
-        // sees them once per chunk (the fixed-order sum over the splitter warps below).  K == 32 keeps the
-        // shared-memory read-modify-write form (64 more registers would not fit beside the other roles).
-        constexpr bool REG_ACC = (K == 16);
-        float2 racc[REG_ACC ? 16 : 1];
-#pragma unroll
-        for (int i = 0; i < (REG_ACC ? 16 : 1); ++i) racc[i] = make_float2(0.f, 0.f);
         ti.set_chunk(cr.take(true, lane), n_chunks, splits, tps);
         // this thread's slice of the B operand: part bn, 16-byte chunks [bc0, bc0 + BCH)
         constexpr int BCH = (K * 16) / (NSPL * 32);    // chunks per thread
@@ -369,8 +361,6 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             // per-row hard mask (bit k set where p_k == max) and the straight-through value of the maxima,
             // parked in a warp-private smem table so that the row loop below can stay rolled
             const uint32_t rinfo = sb + L::RINFO + sw * (ROWS * 8);
-            uint32_t mlocv[SPASS];
-            float monv[SPASS];
 #pragma unroll
             for (int p = 0; p < SPASS; ++p) {
                 const float4 v = pm[p];
@@ -379,9 +369,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 mloc <<= 4 * c;
 #pragma unroll
                 for (int o = 1; o < LPP; o <<= 1) mloc |= __shfl_xor_sync(FULLM, mloc, o);
-                mlocv[p] = mloc;                       // row p*PW + q of this warp: every lane of the pixel holds it
-                monv[p] = st_value(1.0f, pmax);
-                if (!REG_ACC && c == 0) sts2(rinfo + (p * PW + q) * 8, make_float2(__uint_as_float(mloc), monv[p]));
+                if (c == 0) sts2(rinfo + (p * PW + q) * 8, make_float2(__uint_as_float(mloc), st_value(1.0f, pmax)));
             }
             __syncwarp();
             mbar_wait(bar_lo_free + 8 * j, u ^ 1);      // MMA of tile it-2 has finished reading LO[j] (and older B buffers)
@@ -415,41 +403,6 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             const uint32_t lane_off = (lane >> 4) * L::BLK + (lane & 1) * 8;
             const int lch = (lane & 15) >> 1;
             const uint32_t acc_lane = accw + lane * 8;
-            if constexpr (REG_ACC) {
-                static_assert(!REG_ACC || (PW == 8 && SPASS * PW == ROWS), "row r8*8+i of the warp is (pass r8, pixel i)");
-#pragma unroll
-                for (int r8 = 0; r8 < ROWS / 8; ++r8) {
-                    float2 g[8];
-                    uint32_t off[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = sw * ROWS + r8 * 8 + i;         // r & 7 == i
-                        off[i] = r * 128 + ((lch ^ i) * 16) + lane_off;
-                        g[i] = lds2(hi_base + off[i]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        sts2(lo_base + off[i], make_float2(g[i].x - tf32_hi(g[i].x), g[i].y - tf32_hi(g[i].y)));
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint32_t mb = __shfl_sync(FULLM, mlocv[r8], i * LPP);     // warp-uniform
-                        const float mo = __shfl_sync(FULLM, monv[r8], i * LPP);
-                        const float2 gi = g[i];
-                        do {   // one pass for a one-hot row; tied maxima take one pass per maximum, ascending k
-                            const int kk = __ffs(mb) - 1;
-                            mb &= mb - 1;
-                            switch (kk) {
-#define UPS_ACC_CASE(k_) case k_: racc[k_].x = fmaf(mo, gi.x, racc[k_].x); racc[k_].y = fmaf(mo, gi.y, racc[k_].y); break;
-                                UPS_ACC_CASE(0) UPS_ACC_CASE(1) UPS_ACC_CASE(2) UPS_ACC_CASE(3) UPS_ACC_CASE(4) UPS_ACC_CASE(5)
-                                UPS_ACC_CASE(6) UPS_ACC_CASE(7) UPS_ACC_CASE(8) UPS_ACC_CASE(9) UPS_ACC_CASE(10) UPS_ACC_CASE(11)
-                                UPS_ACC_CASE(12) UPS_ACC_CASE(13) UPS_ACC_CASE(14) UPS_ACC_CASE(15)
-#undef UPS_ACC_CASE
-                                default: break;
-                            }
-                        } while (mb);
-                    }
-                }
-            } else {
 #pragma unroll 1
             for (int r8 = 0; r8 < ROWS / 8; ++r8) {
                 // (a) 8 rows of the tile: all loads first (the asm statements keep program order), then lo
@@ -514,16 +467,11 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                     }
                 }
             }
-            }   // !REG_ACC
             __syncwarp();                              // rinfo is rewritten by the next tile
             fence_proxy_async();
             mbar_arrive(bar_lo_ready + 8 * j);
             if (last) {
                 // dfeat partial of this chunk: fixed-order sum over the splitter warps -> workspace
-                if constexpr (REG_ACC) {
-#pragma unroll
-                    for (int k_ = 0; k_ < 16; ++k_) { sts2(acc_lane + k_ * (F * 4), racc[k_]); racc[k_] = make_float2(0.f, 0.f); }
-                }
                 asm volatile("bar.sync 1, %0;\n" ::"n"(NSPL * 32) : "memory");
                 float* dst = partial + (size_t)cur_chunk * (K * F);
                 const uint32_t acc0 = sb + L::ACC;
@@ -534,7 +482,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                     dst[i] = v;
                 }
                 asm volatile("bar.sync 1, %0;\n" ::"n"(NSPL * 32) : "memory");
-                if constexpr (!REG_ACC) zero_acc();
+                zero_acc();
             }
         }
     } else {
@@ -682,15 +630,17 @@ extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const
     const size_t counter_off = (((size_t)B * splits * K * F * sizeof(float)) + 255) & ~(size_t)255;
     unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + counter_off);
     UPS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-    if (K == 16) {
-        const size_t sm = tma::Cfg<16>::TOTAL + 1024;
-        UPS_CUDA(cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tma::step_decode_bwd_tma_kernel<16><<<grid, tma::Cfg<16>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, counter, n_chunks, splits, tps);
-    } else {
-        const size_t sm = tma::Cfg<32>::TOTAL + 1024;
-        UPS_CUDA(cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tma::step_decode_bwd_tma_kernel<32><<<grid, tma::Cfg<32>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial, counter, n_chunks, splits, tps);
+#define UPS_K4(KK)                                                                                                           \
+    {                                                                                                                        \
+        const size_t sm = tma::Cfg<KK>::TOTAL + 1024;                                                                        \
+        static const cudaError_t attr = cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<KK>,                            \
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);          \
+        UPS_CUDA(attr);   /* set once per process and kernel instance, not per call */                                       \
+        tma::step_decode_bwd_tma_kernel<KK><<<grid, tma::Cfg<KK>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial,    \
+                                                                              counter, n_chunks, splits, tps);              \
     }
+    if (K == 16) UPS_K4(16) else UPS_K4(32)
+#undef UPS_K4
     if (int rc = after_launch("step_decode_bwd_tma_kernel")) return rc;
     const long long n = (long long)B * K * F;
     tma::chunk_finalize_kernel<<<(unsigned)cdiv(n, 128), 128, 0, s>>>(partial, dfeat, K * F, splits, n);
