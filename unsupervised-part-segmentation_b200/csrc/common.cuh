@@ -42,6 +42,14 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
         }                                                                           \
     } while (0)
 
+// Kernels that run BESIDE the persistent K4 grid (the all-reduce, the stand-in gradient kernels): K4 configures its SM
+// for the largest shared-memory carve-out; a kernel that prefers another carve-out cannot become resident on that SM
+// until K4's CTA has left.  Asking for the same carve-out (once per kernel and process) removes that obstacle.
+template <typename Kern>
+inline void prefer_max_shared_carveout(Kern kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 

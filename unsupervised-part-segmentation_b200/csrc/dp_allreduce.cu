@@ -168,6 +168,12 @@ extern "C" int ups_dp_allreduce(void* const* peer_bufs, void* mc_buf, void* cons
     UPS_REQUIRE(!mc_buf || aligned16(mc_buf), "dp_allreduce: 16-byte alignment of the multicast mapping");
     if (n_floats == 0) return UPS_OK;
     cudaStream_t s = as_stream(stream);
+    static const bool carveout = []() {
+        prefer_max_shared_carveout(dp::dp_allreduce_kernel<true>);
+        prefer_max_shared_carveout(dp::dp_allreduce_kernel<false>);
+        return true;
+    }();
+    (void)carveout;
     if (mc_buf)
         dp::dp_allreduce_kernel<true><<<n_ctas, dp::TPB, 0, s>>>(pr, static_cast<float*>(mc_buf), rank, world, n_floats / 4, scale);
     else
