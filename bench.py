@@ -252,7 +252,7 @@ def measure_workload(args, torch, dist, ups_b200, name, B, dev, rank, world, red
     raw_call = C.call
 
     def timed_call(cname, *a):
-        if cname.startswith(("ups_standin", "ups_dp_")):     # enqueued on the reducer's side stream, not timed per call
+        if cname.startswith("ups_dp_"):     # enqueued on the reducer's side stream, not timed per call
             return raw_call(cname, *a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -25,8 +25,8 @@ How the collective is done here
     tail bucket — the stand-in encoder tail's gradient (1024 floats), which needs K4's dfeat — after K4,
     overlapped with K5/K6.
   The next forward (`forward`) waits for both before its first kernel; `wait_grads()` for whoever consumes them earlier.
-* The stand-in gradients are computed on the reducer's side stream: they feed the collective,
-  not the path.
+* The stand-in gradient kernels (~25 us) run on the main stream in front of K4 / K5; the all-reduce kernels run on the
+  reducer's high-priority side stream beside K4 and K5.
 """
 import ctypes
 import os
@@ -299,24 +299,20 @@ class DataParallelPartStep:
         st, red, mod = self.step, self.reducer, self.mod
         dev = st.device
         B, P, K, F = st.B, st.P, st.K, st.F
-        side = red.stream
         main = torch.cuda.current_stream(dev)
-        # main bucket: everything a decoder-side module contributes exists before the path's backward starts
-        side.wait_stream(main)
+        # main bucket: everything a decoder-side module contributes exists before the path's backward starts.  The
+        # stand-in gradient kernels run on the MAIN stream, in front of K4 (~25 us): on a side stream they shared the SMs
+        # with the persistent K4 grid, took ten times as long and held the all-reduce behind them (profiles/r02_tuning.md)
         if g_recon is not None:
             with torch.cuda.device(dev):
                 C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
-                       self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), side.cuda_stream)
-        self._ev.record(side)
-        red.launch(0, after=self._ev)
+                       self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
+        red.launch(0)                      # side stream, behind what is queued on the main stream so far
         out = st.backward_decode(g_inj, g_m0)
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
-        self._ev.record(main)
-        side.wait_event(self._ev)
         with torch.cuda.device(dev):
             C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
-                   self._ws.data_ptr(), self._ws.numel(), side.cuda_stream)
-        self._ev.record(side)
-        red.launch(1, after=self._ev)
+                   self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
+        red.launch(1)
         out.update(st.backward_encode(g_parts, g_pooled, g_m1, g_warped))
         return out
