@@ -78,50 +78,29 @@ __global__ void head_fwd_kernel(const long long* __restrict__ labels, const floa
     }
 }
 
-// R partial [b][split*warps + warp][k][c] = sum over the warp's pixels with label k of g_recon[b,p,c].
-// No shared memory and ~32 registers, so that the CTAs co-reside with the persistent K4 grid (which leaves 8 KB of
-// shared memory per SM): a 48 KB version of this kernel waited for K4 to drain and held the all-reduce behind it.
-// A lane owns the parts k = lane % KL (+ KL, ...) with KL = 16 when K <= 16 (two pixels per iteration, one per
-// half-warp) and 32 otherwise; all lanes of a (half-)warp read the same pixel (broadcast loads) and the owner of its
-// label adds the three channels.  Fixed pixel order per lane: deterministic.
-constexpr int POOL_WARPS = 4;
-template <int KL>
-__global__ void __launch_bounds__(POOL_WARPS * 32) head_pool_kernel(const float* __restrict__ g_recon,
-                                                                    const long long* __restrict__ labels,
-                                                                    float* __restrict__ partial, int P, int K,
-                                                                    int pix_per_cta) {
-    constexpr int PPI = 32 / KL;                 // pixels per warp iteration
-    constexpr int NK = (KL == 16) ? 1 : 2;       // parts per lane (K <= 64)
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kl = lane % KL, sub = lane / KL;
+// R partial [b][split][k][c] = sum over the CTA's pixels with label k of g_recon[b,p,c]; lane-private accumulators
+__global__ void __launch_bounds__(TPB) head_pool_kernel(const float* __restrict__ g_recon,
+                                                         const long long* __restrict__ labels,
+                                                         float* __restrict__ partial, int P, int K, int pix_per_cta) {
+    extern __shared__ float acc[];   // [warp][k*3+c][32 lanes]
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = TPB / 32;
+    float* a = acc + (size_t)warp * K * 3 * 32;
+    for (int i = lane; i < K * 3 * 32; i += 32) a[i] = 0.f;
+    __syncwarp();
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(P, p0 + pix_per_cta);
-    const int per_warp = (p1 - p0 + POOL_WARPS - 1) / POOL_WARPS;
-    const int w0 = p0 + warp * per_warp, w1 = min(p1, w0 + per_warp);
-    float acc[NK][3];
-#pragma unroll
-    for (int j = 0; j < NK; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
-    const long long* lb = labels + (size_t)b * P;
-    const float* gb = g_recon + (size_t)b * P * 3;
-#pragma unroll 4
-    for (int p = w0 + sub; p < w1; p += PPI) {
-        int k = (int)__ldg(lb + p);
+    for (int p = p0 + threadIdx.x; p < p1; p += TPB) {
+        int k = (int)__ldcs(labels + (size_t)b * P + p);
         k = k < 0 ? 0 : (k >= K ? K - 1 : k);
-        const float g0 = __ldg(gb + 3 * p), g1 = __ldg(gb + 3 * p + 1), g2 = __ldg(gb + 3 * p + 2);
-#pragma unroll
-        for (int j = 0; j < NK; ++j)
-            if (k == kl + j * KL) { acc[j][0] += g0; acc[j][1] += g1; acc[j][2] += g2; }
+        const float* g = g_recon + ((size_t)b * P + p) * 3;
+        float* q = a + (k * 3) * 32 + lane;
+        q[0] += __ldcs(g); q[32] += __ldcs(g + 1); q[64] += __ldcs(g + 2);
     }
-    if (PPI == 2) {   // the two half-warps hold disjoint pixels of the same parts: lower half + upper half, fixed order
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[0][c] += __shfl_down_sync(0xffffffffu, acc[0][c], 16);
-    }
-    float* out = partial + (((size_t)b * gridDim.x + blockIdx.x) * POOL_WARPS + warp) * (K * 3);
-    if (sub == 0) {
-#pragma unroll
-        for (int j = 0; j < NK; ++j) {
-            const int k = kl + j * KL;
-            if (k < K) { out[k * 3] = acc[j][0]; out[k * 3 + 1] = acc[j][1]; out[k * 3 + 2] = acc[j][2]; }
-        }
+    __syncthreads();
+    for (int t = threadIdx.x; t < K * 3; t += TPB) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w)
+            for (int l = 0; l < 32; ++l) s += acc[((size_t)w * K * 3 + t) * 32 + ((l + t) & 31)];
+        partial[((size_t)b * gridDim.x + blockIdx.x) * (K * 3) + t] = s;
     }
 }
 
@@ -170,7 +149,7 @@ __global__ void __launch_bounds__(TPB) head_grad_partial_kernel(const float* __r
 
 constexpr int TAIL_CTAS = 64;
 constexpr int HEAD_B_PER_CTA = 8;
-inline int head_splits(int P) { return (int)(cdiv(P, 2048) < 1 ? 1 : cdiv(P, 2048)); }
+inline int head_splits(int P) { return (int)(cdiv(P, 4096) < 1 ? 1 : cdiv(P, 4096)); }
 
 }  // namespace standin
 }  // namespace ups
@@ -179,8 +158,7 @@ using namespace ups;
 
 static void standin_carveouts() {
     static const bool once = []() {
-        prefer_max_shared_carveout(standin::head_pool_kernel<16>);
-        prefer_max_shared_carveout(standin::head_pool_kernel<32>);
+        prefer_max_shared_carveout(standin::head_pool_kernel);
         prefer_max_shared_carveout(standin::head_grad_partial_kernel);
         prefer_max_shared_carveout(standin::tail_bwd_partial_kernel);
         prefer_max_shared_carveout(standin::finish_kernel);
@@ -192,7 +170,7 @@ static void standin_carveouts() {
 extern "C" size_t ups_standin_workspace_bytes(int B, int P, int K, int F) {
     if (B <= 0 || P <= 0 || K <= 0 || F <= 0) return 0;
     const size_t tail = (size_t)standin::TAIL_CTAS * 4 * F * sizeof(float);
-    const size_t head = ((size_t)B * standin::head_splits(P) * standin::POOL_WARPS * K * 3 +
+    const size_t head = ((size_t)B * standin::head_splits(P) * K * 3 +
                          (size_t)cdiv(B, standin::HEAD_B_PER_CTA) * ((F + K) * 3 + 3)) * sizeof(float);
     return (tail > head ? tail : head) + 256;
 }
@@ -244,7 +222,7 @@ extern "C" int ups_standin_head_bwd(const float* g_recon, const long long* label
     const int n = (F + K) * 3 + 3;
     UPS_REQUIRE(n <= 4 * standin::TPB, "standin_head_bwd: (F+K)*3+3 = %d exceeds %d", n, 4 * standin::TPB);
     const int splits = standin::head_splits(P);
-    const int rparts = splits * standin::POOL_WARPS;     // partial sums of R per sample
+    const int rparts = splits;                             // partial sums of R per sample
     const int chunks = (int)cdiv(B, standin::HEAD_B_PER_CTA);
     const size_t need = ((size_t)B * rparts * K * 3 + (size_t)chunks * n) * sizeof(float);
     if (!ws || ws_bytes < need) { set_error("standin_head_bwd: workspace %zu < %zu bytes", ws_bytes, need); return UPS_E_WORKSPACE; }
@@ -253,10 +231,10 @@ extern "C" int ups_standin_head_bwd(const float* g_recon, const long long* label
     float* Rpart = static_cast<float*>(ws);
     float* partial = Rpart + (size_t)B * rparts * K * 3;
     const int ppc = (int)cdiv(P, splits);
-    if (K <= 16)
-        standin::head_pool_kernel<16><<<dim3(splits, B), standin::POOL_WARPS * 32, 0, s>>>(g_recon, labels, Rpart, P, K, ppc);
-    else
-        standin::head_pool_kernel<32><<<dim3(splits, B), standin::POOL_WARPS * 32, 0, s>>>(g_recon, labels, Rpart, P, K, ppc);
+    const size_t sm = (size_t)(standin::TPB / 32) * K * 3 * 32 * sizeof(float);
+    if (sm > 48 * 1024)
+        UPS_CUDA(cudaFuncSetAttribute(standin::head_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    standin::head_pool_kernel<<<dim3(splits, B), standin::TPB, sm, s>>>(g_recon, labels, Rpart, P, K, ppc);
     if (int rc = after_launch("standin::head_pool_kernel")) return rc;
     standin::head_grad_partial_kernel<<<chunks, standin::TPB, K * 3 * sizeof(float), s>>>(Rpart, feat, partial, B, K, F, rparts,
                                                                                         standin::HEAD_B_PER_CTA);

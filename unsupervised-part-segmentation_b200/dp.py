@@ -307,8 +307,12 @@ class DataParallelPartStep:
             with torch.cuda.device(dev):
                 C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
                        self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
-        red.launch(0)                      # side stream, behind what is queued on the main stream so far
+        after_k4 = os.environ.get("UPS_DP_MAIN_AFTER_K4", "0") == "1"     # experiment knob (profiles/r02_tuning.md)
+        if not after_k4:
+            red.launch(0)                  # side stream, behind what is queued on the main stream so far
         out = st.backward_decode(g_inj, g_m0)
+        if after_k4:
+            red.launch(0)
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
         with torch.cuda.device(dev):
             C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
