@@ -343,7 +343,7 @@ def run_gpu(args):
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "spatial": S, "n_parts": K,
                    "local_app_size": F, "views": V, "tps_backward": bool(args.tps_bwd), "decode_bwd": step.decode_bwd,
                    "parallelism": f"dp{world} (batch-sharded; no data-path collective; {reducer.flat.numel() * 4 / 1e6:.0f} MB fp32 "
-                                  f"gradient mean per step in two buckets when N>1; stand-in gradient kernels run at every N)",
+                                  f"gradient mean per step in two buckets, fed by the stand-in gradient kernels, when N>1)",
                    "allreduce": {"transport": reducer.transport, "impl": reducer.impl, "ctas": reducer.n_ctas,
                                  "fallback_reason": reducer.fallback_reason,
                                  "buckets_mb": [round(n * 4 / 1e6, 1) for _, n in reducer.bounds]},

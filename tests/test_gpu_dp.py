@@ -96,7 +96,7 @@ def test_dp_world1_equals_partstep_and_holds_standin_grads():
     ref = PartStep(B, S, K, F, n_views=V)
     o_ref = ref.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
     g_ref = ref.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
-    dp = DataParallelPartStep(B, S, K, F, n_views=V, n_grad_params=100_000)
+    dp = DataParallelPartStep(B, S, K, F, n_views=V, n_grad_params=100_000, standin=True)
     assert dp.step.fuse_fwd
     assert dp.world == 1 and dp.reducer.transport == "none"
     g_recon = torch.randn(B, S, S, 3, generator=torch.Generator().manual_seed(1)).cuda()

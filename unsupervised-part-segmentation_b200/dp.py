@@ -260,10 +260,13 @@ class DataParallelPartStep:
 
     def __init__(self, per_gpu_batch, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
                  views_grad=False, n_grad_params=33_300_000, device="cuda", decode_bwd="auto", allreduce="auto",
-                 allreduce_ctas=64, seed=0, reducer=None):
+                 allreduce_ctas=64, seed=0, reducer=None, standin="auto"):
         from .step import PartStep
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        # the stand-in modules exist to feed the collective: with one rank there is none and the step is the path alone
+        # ("no CNN or stand-in compute inside the clock"); standin=True forces them (tests)
+        self.standin = (self.world > 1) if standin == "auto" else bool(standin)
         self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device,
                              decode_bwd=decode_bwd)
         dev = self.step.device
@@ -303,7 +306,7 @@ class DataParallelPartStep:
         # main bucket: everything a decoder-side module contributes exists before the path's backward starts.  The
         # stand-in gradient kernels run on the MAIN stream, in front of K4 (~25 us): on a side stream they shared the SMs
         # with the persistent K4 grid, took ten times as long and held the all-reduce behind them (profiles/r02_tuning.md)
-        if g_recon is not None:
+        if g_recon is not None and self.standin:
             with torch.cuda.device(dev):
                 C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
                        self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
@@ -314,9 +317,10 @@ class DataParallelPartStep:
         if after_k4:
             red.launch(0)
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
-        with torch.cuda.device(dev):
-            C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
-                   self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
+        if self.standin:
+            with torch.cuda.device(dev):
+                C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
+                       self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
         red.launch(1)
         out.update(st.backward_encode(g_parts, g_pooled, g_m1, g_warped))
         return out
