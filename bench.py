@@ -331,7 +331,9 @@ def run_gpu(args):
     S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
     # one flat gradient buffer (symmetric memory when N>1) shared by every workload measured in this process
     n_grad = (int(args.grad_mb * 1e6 / 4) + 3) // 4 * 4
-    reducer = GradAllReducer(n_grad, dev, buckets=two_buckets(n_grad), impl=args.allreduce, n_ctas=args.allreduce_ctas)
+    from ups_b200.dp import default_allreduce_ctas
+    reducer = GradAllReducer(n_grad, dev, buckets=two_buckets(n_grad), impl=args.allreduce,
+                             n_ctas=args.allreduce_ctas or default_allreduce_ctas(world))
     warm = max(args.warmup, 3)
     rec, dp, t = measure_workload(args, torch, dist, ups_b200, args.workload, B, dev, rank, world, reducer, args.steps, warm,
                                   detailed=True)
@@ -540,7 +542,7 @@ def main():
                          "(33.3 M fp32 parameters of the reference's CNNs, SURVEY.md section 2)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],
                     help="gradient mean when N>1: ups_dp_allreduce over symmetric memory (multicast / peer) or ncclAllReduce")
-    ap.add_argument("--allreduce-ctas", type=int, default=64, help="CTAs of the all-reduce kernel")
+    ap.add_argument("--allreduce-ctas", type=int, default=0, help="CTAs of the all-reduce kernel (0: by world size)")
     ap.add_argument("--no-scale-workloads", action="store_true", help="skip the DeepFashion / PennAction legs")
     ap.add_argument("--no-affinity", action="store_true", help="do not give each rank its own slice of the host cores")
     ap.add_argument("--no-e2e", action="store_true")

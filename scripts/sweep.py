@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: part-count / resolution sweep K in {8,16,32} x S in {128,256,512}
 (F=64, V=2), timing the fused step with the CUDA-core K4 and, where it applies (K in {16,32}),
-the TMA + tcgen05 K4.  Prints one JSON line per cell and a markdown table.
+the TMA + tcgen05 K4; plus K=25 (the reference's shipped n_parts, train_cub_subset_tps.yaml:132), which is not a
+power of two and runs on the generic (unfused) kernels.  Prints one JSON line per cell and a markdown table.
 
     python scripts/sweep.py [--out gpurun_out/sweep.json]
 """
@@ -33,7 +34,7 @@ def main():
     rows = []
     for S, B in ((128, 64), (256, 16), (512, 4)):      # SURVEY.md 8d config 5 batch sizes ...
         B *= 4                                           # ... x4 so that one step exceeds the 126 MB L2
-        for K in (8, 16, 32):
+        for K in (8, 16, 25, 32):
             g = torch.Generator(device=dev).manual_seed(0)
             views = torch.rand(V, B, S, S, 3, device=dev, generator=g) * 2 - 1
             l0 = torch.randn(B, S, S, K, device=dev, generator=g)
@@ -46,10 +47,11 @@ def main():
             g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
             prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234), device=dev, **PENN_TPS)
             coord, tv = ups_b200.make_input_tps_param(prm)
-            for variant in ("simt", "tc"):
+            for variant in (("generic",) if K == 25 else ("simt", "tc")):
                 if variant == "tc" and K == 8:
                     continue
-                step = PartStep(B, S, K, F, n_views=V, decode_bwd=variant, device=dev)
+                step = PartStep(B, S, K, F, n_views=V, decode_bwd="auto" if variant == "generic" else variant, device=dev)
+                assert step.fused == (variant != "generic")
 
                 def one():
                     step.forward(views, coord, tv, l0, l1, feat)
@@ -73,7 +75,8 @@ def main():
                 torch.cuda.synchronize()
                 ups_b200.step.C.call = raw
                 ms = t0.elapsed_time(t1) / args.steps
-                k4 = [e0.elapsed_time(e1) for n, e0, e1 in marks if n.startswith("ups_step_decode_bwd")]
+                k4 = [e0.elapsed_time(e1) for n, e0, e1 in marks
+                      if n.startswith("ups_step_decode_bwd") or n in ("ups_part_inject_bwd",)]
                 bytes_img = step.algorithmic_bytes_per_image()
                 row = dict(S=S, K=K, B=B, k4=variant, ms_per_step=ms, images_per_s=B / (ms * 1e-3),
                            step_frac_of_measured_hbm=bytes_img * B / (ms * 1e-3) / 1e9 / peak,

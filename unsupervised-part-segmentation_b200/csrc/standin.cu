@@ -49,12 +49,17 @@ __global__ void __launch_bounds__(TPB) tail_bwd_partial_kernel(const float* __re
     }
 }
 
-__global__ void finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+// out[t] = sum_p partial[p][t]: one warp per output, lane l takes p = l, l+32, ... in ascending order, then a fixed
+// shuffle tree: deterministic, and the `parts` loads of an output are 32-way parallel instead of one dependent chain
+__global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
+                                                     int parts) {
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= n) return;   // warp-uniform
     float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += partial[(size_t)p * n + t];
-    out[t] = s;
+    for (int p = lane; p < parts; p += 32) s += partial[(size_t)p * n + t];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[t] = s;
 }
 
 // ---------------------------------------------------------------- decoder head
@@ -104,51 +109,35 @@ __global__ void __launch_bounds__(TPB) head_pool_kernel(const float* __restrict_
     }
 }
 
-// one CTA per sample chunk: dW partial over the chunk's samples; [chunk][(F+K)*3 + 3]
+// one CTA per sample: that sample's contribution to dW / db; [b][(F+K)*3 + 3] (summed over b by finish_kernel)
 __global__ void __launch_bounds__(TPB) head_grad_partial_kernel(const float* __restrict__ Rpart,
                                                                  const float* __restrict__ feat,
-                                                                 float* __restrict__ partial, int B, int K, int F,
-                                                                 int splits, int b_per_cta) {
-    extern __shared__ float R[];   // [K][3] of the current sample
+                                                                 float* __restrict__ partial, int K, int F, int splits) {
+    extern __shared__ float R[];   // [K][3] of this sample
     const int n = (F + K) * 3 + 3;
-    const int b0 = blockIdx.x * b_per_cta, b1 = min(B, b0 + b_per_cta);
-    float s[4] = {0.f, 0.f, 0.f, 0.f};   // outputs t = threadIdx.x + j*TPB  (n <= 4*TPB)
-    for (int b = b0; b < b1; ++b) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < K * 3; t += TPB) {
-            float r = 0.f;
-            for (int sp = 0; sp < splits; ++sp) r += Rpart[((size_t)b * splits + sp) * (K * 3) + t];
-            R[t] = r;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t = threadIdx.x + j * TPB;
-            if (t >= n) continue;
-            if (t < F * 3) {
-                const int f = t / 3, c = t - 3 * f;
-                float v = s[j];
-                for (int k = 0; k < K; ++k) v = fmaf(feat[((size_t)b * K + k) * F + f], R[k * 3 + c], v);
-                s[j] = v;
-            } else if (t < (F + K) * 3) {
-                s[j] += R[t - F * 3];
-            } else {
-                const int c = t - (F + K) * 3;
-                float v = s[j];
-                for (int k = 0; k < K; ++k) v += R[k * 3 + c];
-                s[j] = v;
-            }
-        }
+    const int b = blockIdx.x;
+    for (int t = threadIdx.x; t < K * 3; t += TPB) {
+        float r = 0.f;
+        for (int sp = 0; sp < splits; ++sp) r += Rpart[((size_t)b * splits + sp) * (K * 3) + t];
+        R[t] = r;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int t = threadIdx.x + j * TPB;
-        if (t < n) partial[(size_t)blockIdx.x * n + t] = s[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += TPB) {
+        float v = 0.f;
+        if (t < F * 3) {
+            const int f = t / 3, c = t - 3 * f;
+            for (int k = 0; k < K; ++k) v = fmaf(feat[((size_t)b * K + k) * F + f], R[k * 3 + c], v);
+        } else if (t < (F + K) * 3) {
+            v = R[t - F * 3];
+        } else {
+            const int c = t - (F + K) * 3;
+            for (int k = 0; k < K; ++k) v += R[k * 3 + c];
+        }
+        partial[(size_t)b * n + t] = v;
     }
 }
 
-constexpr int TAIL_CTAS = 64;
-constexpr int HEAD_B_PER_CTA = 8;
+constexpr int TAIL_CTAS = 256;
 inline int head_splits(int P) { return (int)(cdiv(P, 4096) < 1 ? 1 : cdiv(P, 4096)); }
 
 }  // namespace standin
@@ -171,7 +160,7 @@ extern "C" size_t ups_standin_workspace_bytes(int B, int P, int K, int F) {
     if (B <= 0 || P <= 0 || K <= 0 || F <= 0) return 0;
     const size_t tail = (size_t)standin::TAIL_CTAS * 4 * F * sizeof(float);
     const size_t head = ((size_t)B * standin::head_splits(P) * K * 3 +
-                         (size_t)cdiv(B, standin::HEAD_B_PER_CTA) * ((F + K) * 3 + 3)) * sizeof(float);
+                         (size_t)B * ((F + K) * 3 + 3)) * sizeof(float);
     return (tail > head ? tail : head) + 256;
 }
 
@@ -200,7 +189,7 @@ extern "C" int ups_standin_tail_bwd(const float* pooled, const float* dfeat, flo
     standin::tail_bwd_partial_kernel<<<ctas, standin::TPB, 0, s>>>(pooled, dfeat, partial, rows, C, F, rpc);
     if (int rc = after_launch("standin::tail_bwd_partial_kernel")) return rc;
     const int n = (C + 1) * F;
-    standin::finish_kernel<<<(unsigned)cdiv(n, 128), 128, 0, s>>>(partial, dWlin_dblin, n, ctas);
+    standin::finish_kernel<<<(unsigned)cdiv(n, 8), 256, 0, s>>>(partial, dWlin_dblin, n, ctas);
     return after_launch("standin::finish_kernel");
 }
 
@@ -220,10 +209,9 @@ extern "C" int ups_standin_head_bwd(const float* g_recon, const long long* label
     UPS_REQUIRE(g_recon && labels && feat && dWhead_dbhead, "standin_head_bwd: null pointer");
     UPS_REQUIRE(B > 0 && B <= 65535 && P > 0 && K > 0 && K <= 64 && F > 0, "standin_head_bwd: bad shape");
     const int n = (F + K) * 3 + 3;
-    UPS_REQUIRE(n <= 4 * standin::TPB, "standin_head_bwd: (F+K)*3+3 = %d exceeds %d", n, 4 * standin::TPB);
     const int splits = standin::head_splits(P);
     const int rparts = splits;                             // partial sums of R per sample
-    const int chunks = (int)cdiv(B, standin::HEAD_B_PER_CTA);
+    const int chunks = B;                                  // one CTA (and one partial dW) per sample
     const size_t need = ((size_t)B * rparts * K * 3 + (size_t)chunks * n) * sizeof(float);
     if (!ws || ws_bytes < need) { set_error("standin_head_bwd: workspace %zu < %zu bytes", ws_bytes, need); return UPS_E_WORKSPACE; }
     standin_carveouts();
@@ -236,9 +224,8 @@ extern "C" int ups_standin_head_bwd(const float* g_recon, const long long* label
         UPS_CUDA(cudaFuncSetAttribute(standin::head_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     standin::head_pool_kernel<<<dim3(splits, B), standin::TPB, sm, s>>>(g_recon, labels, Rpart, P, K, ppc);
     if (int rc = after_launch("standin::head_pool_kernel")) return rc;
-    standin::head_grad_partial_kernel<<<chunks, standin::TPB, K * 3 * sizeof(float), s>>>(Rpart, feat, partial, B, K, F, rparts,
-                                                                                        standin::HEAD_B_PER_CTA);
+    standin::head_grad_partial_kernel<<<chunks, standin::TPB, K * 3 * sizeof(float), s>>>(Rpart, feat, partial, K, F, rparts);
     if (int rc = after_launch("standin::head_grad_partial_kernel")) return rc;
-    standin::finish_kernel<<<(unsigned)cdiv(n, 128), 128, 0, s>>>(partial, dWhead_dbhead, n, chunks);
+    standin::finish_kernel<<<(unsigned)cdiv(n, 8), 256, 0, s>>>(partial, dWhead_dbhead, n, chunks);
     return after_launch("standin::finish_kernel");
 }

@@ -46,6 +46,16 @@ def two_buckets(n_floats):
     return [(0, n - TAIL_BUCKET_FLOATS), (n - TAIL_BUCKET_FLOATS, TAIL_BUCKET_FLOATS)]
 
 
+def default_allreduce_ctas(world):
+    """CTAs (128 threads each) of the all-reduce kernel.  With the in-switch reduction of >= 4 ranks 16 CTAs already run
+    at the fabric's rate (profiles/r02d_allreduce_n8.json) and disturb K4 least; two ranks need more loads in flight."""
+    return 16 if world >= 4 else 64
+
+
+def default_main_bucket(world):
+    return "before_k4"
+
+
 def shard_bounds(global_batch, rank, world_size):
     """Contiguous batch shard [lo, hi) of `rank`; the first (global_batch % world) ranks get one extra."""
     base, rem = divmod(int(global_batch), int(world_size))
@@ -260,13 +270,22 @@ class DataParallelPartStep:
 
     def __init__(self, per_gpu_batch, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
                  views_grad=False, n_grad_params=33_300_000, device="cuda", decode_bwd="auto", allreduce="auto",
-                 allreduce_ctas=64, seed=0, reducer=None, standin="auto"):
+                 allreduce_ctas=0, seed=0, reducer=None, standin="auto", main_bucket="auto"):
         from .step import PartStep
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         # the stand-in modules exist to feed the collective: with one rank there is none and the step is the path alone
         # ("no CNN or stand-in compute inside the clock"); standin=True forces them (tests)
         self.standin = (self.world > 1) if standin == "auto" else bool(standin)
+        # where the main bucket's all-reduce starts: "before_k4" (beside K4 and K5) or "after_k4" (beside K5 only);
+        # measured per world size in profiles/r02_tuning.md
+        env = os.environ.get("UPS_DP_MAIN_AFTER_K4")
+        if env is not None:
+            main_bucket = "after_k4" if env == "1" else "before_k4"
+        if main_bucket == "auto":
+            main_bucket = default_main_bucket(self.world)
+        assert main_bucket in ("before_k4", "after_k4"), main_bucket
+        self.main_after_k4 = main_bucket == "after_k4"
         self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device,
                              decode_bwd=decode_bwd)
         dev = self.step.device
@@ -274,7 +293,8 @@ class DataParallelPartStep:
         self.mod = StandInModules(K, F, dev, seed)
         if reducer is None:     # `reducer`: an existing two-bucket GradAllReducer (one symmetric allocation per process)
             n = (max(int(n_grad_params), 4 * TAIL_BUCKET_FLOATS) + 3) // 4 * 4
-            reducer = GradAllReducer(n, dev, buckets=two_buckets(n), impl=allreduce, n_ctas=allreduce_ctas)
+            reducer = GradAllReducer(n, dev, buckets=two_buckets(n), impl=allreduce,
+                                     n_ctas=allreduce_ctas or default_allreduce_ctas(self.world))
         assert len(reducer.bounds) == 2 and reducer.bounds[0][1] >= self.mod.n_head and reducer.bounds[1][1] >= self.mod.n_tail
         n_dec = reducer.bounds[1][0]
         self.reducer = reducer
@@ -310,7 +330,7 @@ class DataParallelPartStep:
             with torch.cuda.device(dev):
                 C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
                        self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
-        after_k4 = os.environ.get("UPS_DP_MAIN_AFTER_K4", "0") == "1"     # experiment knob (profiles/r02_tuning.md)
+        after_k4 = self.main_after_k4
         if not after_k4:
             red.launch(0)                  # side stream, behind what is queued on the main stream so far
         out = st.backward_decode(g_inj, g_m0)
