@@ -297,6 +297,12 @@ int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const float* mas
                        void* ws, size_t ws_bytes, void* stream);
 size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
 
+/* tfutils.draw_rect(mu, patch_size, patch_size, [h, w, 1]) — cub/code/SB_model48i/model.py:442 (the patch masks around
+ * the part centres; `tfutils` is not vendored in the reference tree, so the convention is this library's and is stated
+ * here): centers [N,2] int32 = (row, column) in pixels; out [N,H,W] = 1 on rows [cy - ph/2, cy - ph/2 + ph) x columns
+ * [cx - pw/2, cx - pw/2 + pw) clipped to the image, 0 elsewhere.  No gradient (the call site stops it, model.py:441,449). */
+int ups_draw_rect_fwd(const int* centers, float* out, int N, int ph, int pw, int H, int W, void* stream);
+
 /* K1 + K3 of the fused step in ONE launch (csrc/step_fwd_fused.cu): the TPS warp of the views (ups_tps_warp_pair_fwd's
  * arguments: U [N,S,S,3], optional second image set U2 [N2,S,S,3] sharing the first N2 warps, coord, T -> out, out2) and
  * the decode-side forward (ups_step_decode_fwd's arguments) are independent (model.py:282-311 vs :426-447,482-484);

@@ -92,3 +92,26 @@ def test_categorical_kl(ups, shape):
     assert_close(kl, kl_o.detach(), "kl")
     (dp,) = torch.autograd.grad(kl, p_c, torch.tensor(cot).cuda())
     assert_close(dp, dp_o, "d kl")
+
+
+def test_draw_rect_and_patch_masks(ups=None):
+    """tfutils.draw_rect / the patch masks of model.py:437-445 (source un-vendored: the oracle restates
+    the library's documented convention; borders, zero-size and out-of-image centres included)."""
+    import ups_b200
+    from oracle import parts as OP
+    from oracle import stats as OS_
+    centers = torch.tensor([[0, 0], [5, 7], [15, 15], [-3, 4], [20, 2], [8, 8]], dtype=torch.int32)
+    for ph, pw in ((5, 5), (4, 6), (1, 1), (0, 3), (40, 40)):
+        got = ups_b200.nn.draw_rect(centers.cuda(), ph, pw, [16, 12, 1])
+        assert got.shape == (6, 16, 12, 1)
+        assert torch.equal(got[..., 0].cpu(), OS_.draw_rect(centers, ph, pw, 16, 12)), (ph, pw)
+    g = torch.Generator().manual_seed(0)
+    p = OP.softmax(torch.randn(3, 24, 24, 16, generator=g))
+    mh = OP.straight_through_estimator(OP.hard_max(p, 3), p)
+    got = ups_b200.nn.patch_masks(mh.cuda(), 7, gamma=3.0)
+    want = OS_.patch_masks(mh, 7, gamma=3.0)
+    assert got.shape == (3, 24, 24, 16)
+    # the centre of mass is a float reduction: a centre within rounding of an integer boundary may land one pixel off
+    same = (got.cpu() == want).all(1).all(1)          # [N, K]
+    assert same.float().mean() >= 0.9, same
+    assert torch.equal(got.cpu().sum((1, 2))[same], want.sum((1, 2))[same])

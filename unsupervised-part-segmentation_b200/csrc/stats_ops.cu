@@ -284,6 +284,32 @@ static int moments_checks(const char* what, int B, int H, int W, int K) {
     return UPS_OK;
 }
 
+// ---------------------------------------------------------------- patch masks (draw_rect)
+// out[n, i, j] = 1 inside the ph x pw rectangle centred on (cy, cx) = centers[n] (int32, pixels), 0 outside:
+// rows [cy - ph/2, cy - ph/2 + ph), columns [cx - pw/2, cx - pw/2 + pw), clipped to the image.
+namespace ups {
+__global__ void draw_rect_kernel(const int* __restrict__ centers, float* __restrict__ out, int ph, int pw, int H, int W,
+                                 long long n_total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const long long n = i / ((long long)H * W);
+    const int r = (int)(i - n * H * W);
+    const int y = r / W, x = r - y * W;
+    const int y0 = centers[2 * n] - ph / 2, x0 = centers[2 * n + 1] - pw / 2;
+    out[i] = (y >= y0 && y < y0 + ph && x >= x0 && x < x0 + pw) ? 1.0f : 0.0f;
+}
+}  // namespace ups
+
+extern "C" int ups_draw_rect_fwd(const int* centers, float* out, int N, int ph, int pw, int H, int W, void* stream) {
+    UPS_REQUIRE(N >= 0 && ph >= 0 && pw >= 0 && H > 0 && W > 0, "draw_rect: bad dims N=%d ph=%d pw=%d H=%d W=%d", N, ph, pw, H, W);
+    if (N == 0) return UPS_OK;
+    UPS_REQUIRE(centers && out, "draw_rect: null pointer");
+    const long long n_total = (long long)N * H * W;
+    UPS_REQUIRE(cdiv(n_total, 256) < (1ll << 31), "draw_rect: too large");
+    ups::draw_rect_kernel<<<(unsigned)cdiv(n_total, 256), 256, 0, as_stream(stream)>>>(centers, out, ph, pw, H, W, n_total);
+    return after_launch("draw_rect_kernel");
+}
+
 extern "C" int ups_mask_moments_fwd(const float* probs, const float* scaling, float* mu, float* sigma, float* moments,
                                     int B, int H, int W, int K, void* ws, size_t ws_bytes, void* stream) {
     UPS_REQUIRE(probs && scaling && mu && sigma && moments, "mask_moments_fwd: null pointer");

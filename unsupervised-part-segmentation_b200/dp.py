@@ -49,11 +49,14 @@ def two_buckets(n_floats):
 def default_allreduce_ctas(world):
     """CTAs (128 threads each) of the all-reduce kernel.  With the in-switch reduction of >= 4 ranks 16 CTAs already run
     at the fabric's rate (profiles/r02d_allreduce_n8.json) and disturb K4 least; two ranks need more loads in flight."""
-    return 16 if world >= 4 else 64
+    return 16 if world >= 4 else 128
 
 
 def default_main_bucket(world):
-    return "before_k4"
+    """>= 4 ranks: the main bucket's all-reduce starts before K4 and runs beside K4 and K5 (N=8: 1.600 vs 1.640 ms);
+    2 ranks need 128 CTAs to fill the link, which slows the persistent K4 by 0.16 ms when they share its SMs, so there
+    the all-reduce starts after K4, beside K5 (1.605 vs 1.666 ms).  profiles/r02_tuning.md."""
+    return "before_k4" if world >= 4 else "after_k4"
 
 
 def shard_bounds(global_batch, rank, world_size):

@@ -72,6 +72,28 @@ def unpool_features_gathered(feature_vectors, mask):
     return ops.part_gather(feature_vectors, mask)
 
 
+def draw_rect(center, height, width, shape):
+    """tfutils.draw_rect as called at cub/code/SB_model48i/model.py:442 — center [N,2] integer (row, column), rectangle
+    height x width, shape = [h, w, 1] -> [N,h,w,1] of 0/1.  `tfutils` is not vendored with the reference; the
+    convention (rows [cy - height//2, cy - height//2 + height), same for columns, clipped) is documented in
+    include/ups_b200.h."""
+    h, w = int(shape[0]), int(shape[1])
+    return ops.draw_rect(center, int(height), int(width), h, w)[..., None]
+
+
+def patch_masks(mask_hard, patch_size, gamma=3.0):
+    """cub/code/SB_model48i/model.py:437-445: the square patch around each part's centre of mass —
+    softmax(spatial=True) of gamma * mask, probs_to_mu_sigma, centres cast to int pixels (truncation, as tf.cast),
+    draw_rect, back to [N,h,w,P].  No gradient (tf.stop_gradient at the call site)."""
+    N, h, w, P = mask_hard.shape
+    with torch.no_grad():
+        corrected = softmax(mask_hard * gamma, spatial=True)
+        mu, _ = probs_to_mu_sigma(corrected, torch.ones(N, P, device=mask_hard.device))
+        centers = (mu.reshape(N * P, 2) * h / 2.0 + h / 2.0).to(torch.int32)
+        rect = draw_rect(centers, patch_size, patch_size, [h, w, 1])
+        return rect.reshape(N, P, h, w).permute(0, 2, 3, 1).contiguous()
+
+
 def probs_to_mu_sigma(probs, scaling_factor):
     """cub/code/nn.py:1541-1587 — per-part mean (y, x) and 2x2 covariance of the [b,h,w,k] densities on
     the linspace(-1, 1) grid; scaling_factor [b,k].  Returns (mu [b,k,2], sigma [b,k,2,2])."""

@@ -827,3 +827,17 @@ def _parts_conv_bwd(ctx, g):
 parts_conv = _op("parts_conv", _parts_conv,
                  lambda i, m, v, b: i.new_empty(m.shape[-1] * m.shape[0], m.shape[1], m.shape[2], v.shape[-1]),
                  _parts_conv_bwd, lambda ctx, inputs, output: ctx.save_for_backward(inputs[0], inputs[1], inputs[2]))
+
+
+# ------------------------------------------------------------------ patch masks (draw_rect)
+def _draw_rect(centers: Tensor, ph: int, pw: int, H: int, W: int) -> Tensor:
+    if not centers.is_cuda:
+        raise C.UpsError("ups_b200: centers must be a CUDA tensor (no CPU fallback exists)")
+    centers = centers.to(torch.int32).contiguous()
+    N = centers.shape[0]
+    out = torch.empty(N, H, W, dtype=torch.float32, device=centers.device)
+    C.call("ups_draw_rect_fwd", centers.data_ptr(), out.data_ptr(), N, int(ph), int(pw), int(H), int(W), _stream(centers))
+    return out
+
+
+draw_rect = _op("draw_rect", _draw_rect, lambda c, ph, pw, H, W: c.new_empty(c.shape[0], H, W, dtype=torch.float32))
