@@ -196,7 +196,10 @@ def test_parts_conv_reference_fixture(ups, tag):
 
 @pytest.mark.parametrize("B,H,W,K,Co,kind", [(2, 64, 64, 16, 32, "hard"), (1, 128, 128, 16, 32, "ties"),
                                              (3, 40, 50, 25, 32, "ties"), (2, 33, 31, 8, 64, "soft"),
-                                             (1, 16, 160, 4, 16, "hard"), (2, 9, 70, 5, 8, "soft"), (1, 1, 1, 16, 32, "hard")])
+                                             (1, 16, 160, 4, 16, "hard"), (2, 9, 70, 5, 8, "soft"), (1, 1, 1, 16, 32, "hard"),
+                                             # Co = 32 and W in {128, 256}: the tcgen05 kernel (parts_conv_bwd_tc.cu)
+                                             (3, 33, 128, 5, 32, "ties"), (1, 40, 256, 8, 32, "soft"), (2, 1, 128, 3, 32, "hard"),
+                                             (5, 7, 256, 32, 32, "hard")])
 def test_parts_conv2d_backward_vs_oracle(ups, B, H, W, K, Co, kind):
     from oracle import parts_conv as PC
     _, mask, _, _, _, _ = _case(B, H, W, K, 4, Co, kind, seed=B * 10 + K + 1)

@@ -17,8 +17,8 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libups_b200.so")
 HOST_LIB = os.path.join(CSRC, "libups_canon_host.so")
 CU_SOURCES = ["cabi.cu", "tps.cu", "parts_ops.cu", "step_fused.cu", "step_decode_bwd_tma.cu", "stats_ops.cu", "priors_ops.cu", "ingest.cu",
-              "inject_conv.cu", "parts_conv.cu", "dp_allreduce.cu", "standin.cu", "step_fwd_fused.cu"]
-HEADERS = ["common.cuh", "canon_math.cuh", "pk_math.cuh", "tps_warp_fwd.cuh", "step_decode_fwd.cuh", os.path.join("..", "..", "include", "ups_b200.h")]
+              "inject_conv.cu", "parts_conv.cu", "dp_allreduce.cu", "standin.cu", "step_fwd_fused.cu", "parts_conv_bwd_tc.cu"]
+HEADERS = ["common.cuh", "canon_math.cuh", "pk_math.cuh", "tps_warp_fwd.cuh", "step_decode_fwd.cuh", "tc_helpers.cuh", os.path.join("..", "..", "include", "ups_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -22,6 +22,9 @@ size_t decode_bwd_tma_ws_bytes(int B, int P, int K, int F);  // step_decode_bwd_
 size_t moments_ws_bytes(int B, int P, int K);  // stats_ops.cu
 size_t mumford_shah_ws_bytes(int B, int P, int K);  // priors_ops.cu
 size_t priors_scalar_ws_bytes();                    // priors_ops.cu
+bool parts_conv_bwd_tc_ok(int B, int H, int W, int K, int Co);   // parts_conv_bwd_tc.cu
+int parts_conv_bwd_tc_launch(const float* g_h, const float* img, const float* V, float* dm_planes, float* ws_db, int B,
+                             int H, int W, int K, cudaStream_t st);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

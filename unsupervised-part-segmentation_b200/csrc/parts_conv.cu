@@ -567,6 +567,10 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     float* ws_db = ws_dV + (size_t)B * runs_per_sample * 27 * Co;
     float* dm_planes = ws_db + (size_t)K * B * Co;
     cudaStream_t st = as_stream(stream);
+    const bool use_tc = parts_conv_bwd_tc_ok(B, H, W, K, Co);   // tcgen05 kernel (parts_conv_bwd_tc.cu): Co = 32, W in {128, 256}
+    if (use_tc) {
+        if (int rc = parts_conv_bwd_tc_launch(g_out_pm, img, V, dm_planes, ws_db, B, H, W, K, st)) return rc;
+    } else {
     const size_t smem = (size_t)(28 * Co + 4 * (W + 2) * 27 + (PCB_THREADS / 32) * Co + 4 + 2 * PCB_THREADS * (Co + 4)) * sizeof(float);
     UPS_REQUIRE(smem <= 200 * 1024, "parts_conv_bwd: W=%d Co=%d needs %zu bytes of shared memory", W, Co, smem);
 #define UPS_PCB(CO, MINB)                                                                                              \
@@ -586,6 +590,7 @@ extern "C" int ups_parts_conv_bwd(const float* g_out_pm, const float* img, const
     else UPS_PCB(64, 2);
 #undef UPS_PCB
     if (int rc = after_launch("parts_conv_bwd_data_kernel")) return rc;
+    }
     {
         const unsigned grid = (unsigned)cdiv((long long)B * P, 256);
         if (K <= 8) parts_conv_bwd_finish_kernel<8><<<grid, 256, 0, st>>>(dm_planes, probs, g_extra, dmask, B, P, K);
