@@ -13,10 +13,13 @@
 // the image run in the TMEM-drain epilogue through a 4-row shared-memory ring, as in the CUDA-core kernel.
 //
 // One persistent CTA per SM walks whole planes (rows top to bottom).  Warp roles:
-//   warps 0-3   epilogue: tcgen05.ld (thread = pixel) -> ring row y; barrier; R and dmask of row y-1 -> dm_planes
-//   warps 4-7   splitter: lo tile, and the column sums of g_h (db)
-//   warp 8      TMA producer (one lane): 128 x 32 fp32 boxes into a 4-stage ring
-//   warp 9      MMA issuer (one lane)
+//   warps 0-3   drain:  tcgen05.ld (thread = pixel) -> ring row y (27 floats per pixel)
+//   warps 4-7   reduce: R and dmask of row y-1 from ring rows y-2, y-1, y -> dm_planes.  Drain and reduce are
+//               two stages of a pipeline over the ring rows (mbarriers rowfull / rowfree per ring slot): as one
+//               warp group they ran one warp per scheduler, latency-bound at 2150 cycles per tile (measured 4.0 ms)
+//   warps 8-11  splitter: lo tile, and the column sums of g_h (db)
+//   warp 12     TMA producer (one lane): 128 x 32 fp32 boxes into a 4-stage ring
+//   warp 13     MMA issuer (one lane)
 // Every cross-role hand-off is an mbarrier with a bounded wait (a protocol bug traps instead of hanging the GPU).
 #include <stdlib.h>
 
@@ -34,7 +37,8 @@ constexpr int NTC = 32;     // (tap, channel) columns: 27 used
 constexpr int NST = 4;      // TMA stages
 constexpr int G_BYTES = TILE * 128;          // 16 KB per tile
 constexpr int B_BYTES = 2 * NTC * 128;       // [V_hi | V_lo] rows
-constexpr int TPB = 320;
+constexpr int TPB = 448;
+constexpr int W_SPLIT = 8, W_TMA = 12, W_MMA = 13;
 constexpr uint32_t TMEM_COLS = 128;          // 2 accumulator buffers of 64 columns
 constexpr unsigned FULLM = 0xffffffffu;
 
@@ -77,7 +81,9 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
     const uint32_t bar_lo_free = bar_lo_ready + 16;        // [2]
     const uint32_t bar_tm_full = bar_lo_free + 16;         // [2]
     const uint32_t bar_tm_empty = bar_tm_full + 16;        // [2]
-    const uint32_t slot = bar_tm_empty + 16;
+    const uint32_t bar_rowfull = bar_tm_empty + 16;        // [4] ring slots: drain -> reduce
+    const uint32_t bar_rowfree = bar_rowfull + 32;         // [4] reduce -> drain
+    const uint32_t slot = bar_rowfree + 32;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot), "r"(TMEM_COLS) : "memory");
@@ -91,9 +97,10 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             mbar_init(bar_tm_full + 8 * i, 1);
             mbar_init(bar_tm_empty + 8 * i, 128);
         }
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_rowfull + 8 * i, 128); mbar_init(bar_rowfree + 8 * i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid == 8 * 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmap_g)) : "memory");
+    if (tid == W_TMA * 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmap_g)) : "memory");
     // B operand, once per CTA: rows 0..31 = V_hi[tc][o], rows 32..63 = V_lo[tc][o] (rows 27..31 of each half zero),
     // K-major SWIZZLE_128B: 16-byte chunk cc of row r at r*128 + ((cc ^ (r & 7)) * 16)
     for (int i = tid; i < NTC * 8; i += TPB) {
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(tmem_base) : "r"(slot));
 
-    if (warp == 8) {
+    if (warp == W_TMA) {
         // ================================================================= TMA producer
         if (lane == 0) {
             uint32_t it = 0;
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                     }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             uint32_t it = 0;
@@ -152,9 +159,9 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                 }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= W_SPLIT) {
         // ================================================================= splitter (+ db)
-        const int st = tid - 128;                 // 0..127
+        const int st = tid - W_SPLIT * 32;        // 0..127
         const int cc = st & 7, rsub = st >> 3;    // 16-byte chunk of the row, row within a pass of 16 rows
         uint32_t it = 0;
         for (int n = blockIdx.x; n < n_planes; n += gridDim.x) {
@@ -186,27 +193,19 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             }
             asm volatile("bar.sync 2, 128;\n" ::: "memory");
         }
-    } else {
-        // ================================================================= epilogue (warps 0-3): thread = pixel of the tile
-        uint32_t it = 0;
-        for (int n = blockIdx.x; n < n_planes; n += gridDim.x) {
-            const int k = n / B, b = n - k * B;
-            const float* ib = img + (size_t)b * P * 3;
-            float* dm = dm_planes + ((size_t)b * K + k) * P;
-            // a new plane: row -1 (slot 3) is zero; the other slots are overwritten before they are read
-            for (int i = tid; i < Wr * 27; i += 128) sD[3 * Wr * 27 + i] = 0.f;
-            for (int y = 0; y <= H; ++y) {
-                const int sl = y & 3;
-                // image pixels of row y-1 (requested before the accumulators arrive)
-                float im[2][3];
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const bool ok = t < NT && y >= 1;
-                    const size_t q = ok ? (size_t)(y - 1) * W + t * TILE + tid : 0;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) im[t][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
-                }
-                if (y < H) {
+    } else if (warp < 4) {
+        // ================================================================= drain (warps 0-3): thread = pixel of the tile
+        // Ring rows are numbered globally: plane i writes rows base-1 (zeros), base .. base+H-1 (D), base+H (zeros) with
+        // base = i*(H+2) + 1; global row r lives in slot r & 3 and is the (r >> 2)-th occupant of that slot.
+        uint32_t it = 0, base = 1;
+        auto claim = [&](uint32_t r) { mbar_wait(bar_rowfree + 8 * (r & 3), ((r >> 2) & 1) ^ 1); };
+        auto publish = [&](uint32_t r) { mbar_arrive(bar_rowfull + 8 * (r & 3)); };
+        for (int n = blockIdx.x; n < n_planes; n += gridDim.x, base += H + 2) {
+            for (int y = -1; y <= H; ++y) {
+                const uint32_t r = base + y;
+                claim(r);
+                float* rowp = sD + ((r & 3) * Wr + 1 + tid) * 27;
+                if (y >= 0 && y < H) {
                     for (int t = 0; t < NT; ++t, ++it) {
                         const uint32_t j = it & 1, u = (it >> 1) & 1;
                         mbar_wait(bar_tm_full + 8 * j, u);
@@ -217,38 +216,61 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                         tmem_ld_wait();
                         tc_fence_before();
                         mbar_arrive(bar_tm_empty + 8 * j);
-                        float* dst = sD + (sl * Wr + t * TILE + tid + 1) * 27;
+                        float* dst = rowp + t * TILE * 27;
 #pragma unroll
                         for (int tc = 0; tc < 27; ++tc) dst[tc] = d0[tc] + d1[tc];
                     }
                 } else {
-                    for (int t = 0; t < NT; ++t) {   // the row below the image contributes nothing
-                        float* dst = sD + (sl * Wr + t * TILE + tid + 1) * 27;
+                    for (int t = 0; t < NT; ++t) {   // the rows above and below the image contribute nothing
+                        float* dst = rowp + t * TILE * 27;
 #pragma unroll
                         for (int tc = 0; tc < 27; ++tc) dst[tc] = 0.f;
                     }
                 }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                if (y >= 1) {
-                    // R of row y-1 needs D rows y-2 (tap dy = 2), y-1, y (dy = 0): slots (y-2)&3, (y-1)&3, y&3
-                    for (int t = 0; t < NT; ++t) {
-                        const int x = t * TILE + tid;
-                        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const int srow = (y - dy) & 3;      // D row (y-1) + 1 - dy
-                            const float* row = sD + (srow * Wr + x + 2) * 27 + 9 * dy;
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const float* dd = row + 3 * dx - dx * 27;   // column x + 1 - dx (+1 for the zero border)
-                                r0 += dd[0]; r1 += dd[1]; r2 += dd[2];
-                            }
-                        }
-                        dm[(size_t)(y - 1) * W + x] = fmaf(im[t][2], r2, fmaf(im[t][1], r1, im[t][0] * r0));
-                    }
-                }
+                publish(r);
             }
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");   // the last R row has been read before slot 3 is cleared
+        }
+    } else {
+        // ================================================================= reduce (warps 4-7): thread = column of the row
+        const int ct = tid - 128;
+        uint32_t base = 1;
+        for (int n = blockIdx.x; n < n_planes; n += gridDim.x, base += H + 2) {
+            const int k = n / B, b = n - k * B;
+            const float* ib = img + (size_t)b * P * 3;
+            float* dm = dm_planes + ((size_t)b * K + k) * P;
+            for (int yy = 0; yy < H; ++yy) {
+                float im[2][3];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const bool ok = t < NT;
+                    const size_t q = ok ? (size_t)yy * W + t * TILE + ct : 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) im[t][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
+                }
+                // R of row yy needs D rows yy+1 (tap dy = 0), yy, yy-1 (dy = 2); rows are published in order
+                const uint32_t r1 = base + yy + 1;
+                if (yy == 0) { mbar_wait(bar_rowfull + 8 * ((r1 - 2) & 3), (((r1 - 2) >> 2) & 1));
+                               mbar_wait(bar_rowfull + 8 * ((r1 - 1) & 3), (((r1 - 1) >> 2) & 1)); }
+                mbar_wait(bar_rowfull + 8 * (r1 & 3), (r1 >> 2) & 1);
+                for (int t = 0; t < NT; ++t) {
+                    const int x = t * TILE + ct;
+                    float r0 = 0.f, rr1 = 0.f, r2 = 0.f;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t srow = (r1 - dy) & 3;
+                        const float* row = sD + (srow * Wr + x + 2) * 27 + 9 * dy;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float* dd = row + 3 * dx - dx * 27;   // column x + 1 - dx (+1 for the zero border)
+                            r0 += dd[0]; rr1 += dd[1]; r2 += dd[2];
+                        }
+                    }
+                    dm[(size_t)yy * W + x] = fmaf(im[t][2], r2, fmaf(im[t][1], rr1, im[t][0] * r0));
+                }
+                // row yy-1 is not needed any more; after the last row of the plane neither are rows yy and yy+1
+                mbar_arrive(bar_rowfree + 8 * ((r1 - 2) & 3));
+                if (yy == H - 1) { mbar_arrive(bar_rowfree + 8 * ((r1 - 1) & 3)); mbar_arrive(bar_rowfree + 8 * (r1 & 3)); }
+            }
         }
     }
     tc_fence_before();
