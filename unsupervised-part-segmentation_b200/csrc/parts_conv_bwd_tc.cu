@@ -37,9 +37,9 @@ constexpr int NTC = 32;     // (tap, channel) columns: 27 used
 constexpr int NST = 4;      // TMA stages
 constexpr int G_BYTES = TILE * 128;          // 16 KB per tile
 constexpr int B_BYTES = 2 * NTC * 128;       // [V_hi | V_lo] rows
-constexpr int TPB = 448;
-constexpr int W_SPLIT = 8, W_TMA = 12, W_MMA = 13;
-constexpr uint32_t TMEM_COLS = 128;          // 2 accumulator buffers of 64 columns
+constexpr int TPB = 576;
+constexpr int W_RED = 8, W_SPLIT = 12, W_TMA = 16, W_MMA = 17;
+constexpr uint32_t TMEM_COLS = 64;           // 2 accumulator buffers of 32 columns
 constexpr unsigned FULLM = 0xffffffffu;
 
 struct Layout {
@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                                                                  float* __restrict__ dm_planes,
                                                                  float* __restrict__ ws_db, int B, int H, int W, int K,
                                                                  int n_planes) {
-    constexpr uint32_t IDESC_64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     constexpr uint32_t IDESC_32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -95,9 +94,9 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             mbar_init(bar_lo_ready + 8 * i, 128);
             mbar_init(bar_lo_free + 8 * i, 1);
             mbar_init(bar_tm_full + 8 * i, 1);
-            mbar_init(bar_tm_empty + 8 * i, 128);
+            mbar_init(bar_tm_empty + 8 * i, 256);
         }
-        for (int i = 0; i < 4; ++i) { mbar_init(bar_rowfull + 8 * i, 128); mbar_init(bar_rowfree + 8 * i, 128); }
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_rowfull + 8 * i, 256); mbar_init(bar_rowfree + 8 * i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid == W_TMA * 32) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmap_g)) : "memory");
@@ -145,13 +144,15 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                     mbar_wait(bar_lo_ready + 8 * j, u);
                     mbar_wait(bar_tm_empty + 8 * j, u ^ 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + j * 64;
+                    const uint32_t d = tmem_base + j * 32;
                     const uint32_t a_hi = sb + L.stage0 + s * G_BYTES, a_lo = sb + L.lo0 + j * G_BYTES, bb = sb + L.b0;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t bd = sw128_desc(bb + ks * 32);
-                        umma_tf32(d, sw128_desc(a_hi + ks * 32), bd, IDESC_64, ks > 0 ? 1u : 0u);   // hi.hi | hi.lo
-                        umma_tf32(d, sw128_desc(a_lo + ks * 32), bd, IDESC_32, 1u);                  // lo.hi
+                    for (int ks = 0; ks < 4; ++ks) {   // the three 3xTF32 terms accumulate into the same 32 columns
+                        const uint64_t b_hi = sw128_desc(bb + ks * 32), b_lo = sw128_desc(bb + NTC * 128 + ks * 32);
+                        const uint64_t ah = sw128_desc(a_hi + ks * 32);
+                        umma_tf32(d, ah, b_hi, IDESC_32, ks > 0 ? 1u : 0u);                    // hi.hi
+                        umma_tf32(d, ah, b_lo, IDESC_32, 1u);                                  // hi.lo
+                        umma_tf32(d, sw128_desc(a_lo + ks * 32), b_hi, IDESC_32, 1u);          // lo.hi
                     }
                     umma_commit(bar_empty + 8 * s);
                     umma_commit(bar_lo_free + 8 * j);
@@ -193,8 +194,10 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             }
             asm volatile("bar.sync 2, 128;\n" ::: "memory");
         }
-    } else if (warp < 4) {
-        // ================================================================= drain (warps 0-3): thread = pixel of the tile
+    } else if (warp < W_RED) {
+        // ================================================================= drain (warps 0-7): thread = pixel of the tile,
+        // warp w reads TMEM lane quadrant w & 3 and the column half w >> 2 (columns 0-15 or 16-31 of the 27 used)
+        const int px = (warp & 3) * 32 + lane, half = warp >> 2;
         // Ring rows are numbered globally: plane i writes rows base-1 (zeros), base .. base+H-1 (D), base+H (zeros) with
         // base = i*(H+2) + 1; global row r lives in slot r & 3 and is the (r >> 2)-th occupant of that slot.
         uint32_t it = 0, base = 1;
@@ -204,35 +207,36 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             for (int y = -1; y <= H; ++y) {
                 const uint32_t r = base + y;
                 claim(r);
-                float* rowp = sD + ((r & 3) * Wr + 1 + tid) * 27;
+                float* rowp = sD + ((r & 3) * Wr + 1 + px) * 27 + 16 * half;
                 if (y >= 0 && y < H) {
                     for (int t = 0; t < NT; ++t, ++it) {
                         const uint32_t j = it & 1, u = (it >> 1) & 1;
                         mbar_wait(bar_tm_full + 8 * j, u);
                         tc_fence_after();
-                        float d0[32], d1[32];
-                        tmem_ld32(tmem_base + j * 64 + ((uint32_t)(warp * 32) << 16), d0);
-                        tmem_ld32(tmem_base + j * 64 + 32 + ((uint32_t)(warp * 32) << 16), d1);
+                        float d0[16];
+                        tmem_ld16(tmem_base + j * 32 + 16 * half + ((uint32_t)((warp & 3) * 32) << 16), d0);
                         tmem_ld_wait();
                         tc_fence_before();
                         mbar_arrive(bar_tm_empty + 8 * j);
                         float* dst = rowp + t * TILE * 27;
 #pragma unroll
-                        for (int tc = 0; tc < 27; ++tc) dst[tc] = d0[tc] + d1[tc];
+                        for (int tc = 0; tc < 16; ++tc)
+                            if (16 * half + tc < 27) dst[tc] = d0[tc];
                     }
                 } else {
                     for (int t = 0; t < NT; ++t) {   // the rows above and below the image contribute nothing
                         float* dst = rowp + t * TILE * 27;
 #pragma unroll
-                        for (int tc = 0; tc < 27; ++tc) dst[tc] = 0.f;
+                        for (int tc = 0; tc < 16; ++tc)
+                            if (16 * half + tc < 27) dst[tc] = 0.f;
                     }
                 }
                 publish(r);
             }
         }
-    } else {
-        // ================================================================= reduce (warps 4-7): thread = column of the row
-        const int ct = tid - 128;
+    } else if (warp < W_SPLIT) {
+        // ================================================================= reduce (warps 8-11): thread = column of the row
+        const int ct = tid - W_RED * 32;
         uint32_t base = 1;
         for (int n = blockIdx.x; n < n_planes; n += gridDim.x, base += H + 2) {
             const int k = n / B, b = n - k * B;
