@@ -172,13 +172,19 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                 mbar_wait(bar_lo_free + 8 * j, u ^ 1);
                 mbar_wait(bar_full + 8 * s, ph & 1);
                 const uint32_t hi_base = sb + L.stage0 + s * G_BYTES, lo_base = sb + L.lo0 + j * G_BYTES;
+                float4 g[TILE / 16];
+                uint32_t off[TILE / 16];
+#pragma unroll
+                for (int p = 0; p < TILE / 16; ++p) {      // all loads first (the asm statements keep program order)
+                    const int r = p * 16 + rsub;
+                    off[p] = r * 128 + ((cc ^ (r & 7)) * 16);
+                    g[p] = lds4(hi_base + off[p]);
+                }
 #pragma unroll
                 for (int p = 0; p < TILE / 16; ++p) {
-                    const int r = p * 16 + rsub;
-                    const uint32_t off = r * 128 + ((cc ^ (r & 7)) * 16);
-                    const float4 g = lds4(hi_base + off);
-                    sts4(lo_base + off, make_float4(g.x - tf32_hi(g.x), g.y - tf32_hi(g.y), g.z - tf32_hi(g.z), g.w - tf32_hi(g.w)));
-                    dbacc.x += g.x; dbacc.y += g.y; dbacc.z += g.z; dbacc.w += g.w;
+                    sts4(lo_base + off[p], make_float4(g[p].x - tf32_hi(g[p].x), g[p].y - tf32_hi(g[p].y),
+                                                        g[p].z - tf32_hi(g[p].z), g[p].w - tf32_hi(g[p].w)));
+                    dbacc.x += g[p].x; dbacc.y += g[p].y; dbacc.z += g[p].z; dbacc.w += g[p].w;
                 }
                 fence_proxy_async();
                 mbar_arrive(bar_lo_ready + 8 * j);
@@ -242,21 +248,31 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
             const int k = n / B, b = n - k * B;
             const float* ib = img + (size_t)b * P * 3;
             float* dm = dm_planes + ((size_t)b * K + k) * P;
-            for (int yy = 0; yy < H; ++yy) {
-                float im[2][3];
+            // image pixels of the row, fetched one row ahead and kept in registers (static indices: a dynamically
+            // indexed array lands in local memory and the reduce warps then wait a DRAM latency per row)
+            float im[2][3], imn[2][3];
+            auto fetch = [&](int y, float (&dst)[2][3]) {
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const bool ok = t < NT;
-                    const size_t q = ok ? (size_t)yy * W + t * TILE + ct : 0;
+                    const bool ok = t < NT && y < H;
+                    const size_t q = ok ? (size_t)y * W + t * TILE + ct : 0;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) im[t][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
+                    for (int c = 0; c < 3; ++c) dst[t][c] = ok ? __ldg(ib + q * 3 + c) : 0.f;
                 }
+            };
+            fetch(0, imn);
+            for (int yy = 0; yy < H; ++yy) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) im[t][c] = imn[t][c];
+                fetch(yy + 1, imn);
                 // R of row yy needs D rows yy+1 (tap dy = 0), yy, yy-1 (dy = 2); rows are published in order
                 const uint32_t r1 = base + yy + 1;
-                if (yy == 0) { mbar_wait(bar_rowfull + 8 * ((r1 - 2) & 3), (((r1 - 2) >> 2) & 1));
-                               mbar_wait(bar_rowfull + 8 * ((r1 - 1) & 3), (((r1 - 1) >> 2) & 1)); }
                 mbar_wait(bar_rowfull + 8 * (r1 & 3), (r1 >> 2) & 1);
-                for (int t = 0; t < NT; ++t) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (t >= NT) continue;
                     const int x = t * TILE + ct;
                     float r0 = 0.f, rr1 = 0.f, r2 = 0.f;
 #pragma unroll
