@@ -35,6 +35,16 @@ def test_every_declared_symbol_is_exported(ups):
     assert "sm_100a" in ups._cabi.version()
 
 
+def test_library_records_the_hash_of_its_sources(ups):
+    """VERDICT r1 weak #7: the binary that travels to the GPU box must be the one built from the tree's sources."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b", os.path.join(ROOT, "unsupervised-part-segmentation_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.built_hash() == b.source_hash()
+    assert f"src={b.source_hash()}" in ups._cabi.version()
+
+
 def test_library_is_sm100a_only(ups):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", ups._cabi.LIB_PATH], capture_output=True, text=True).stdout
