@@ -303,6 +303,19 @@ size_t ups_parts_conv_bwd_workspace_bytes(int B, int H, int W, int K, int Co);
  * [cx - pw/2, cx - pw/2 + pw) clipped to the image, 0 elsewhere.  No gradient (the call site stops it, model.py:441,449). */
 int ups_draw_rect_fwd(const int* centers, float* out, int N, int ph, int pw, int H, int W, void* stream);
 
+/* Part counts that are not a power of two (the reference ships n_parts = 25, train_cub_subset_tps.yaml:132) run on the
+ * fused kernels of the next power of two Kp: the [.,K] tensors are padded to [.,Kp] rows (logits with -inf: exp_canon
+ * gives exactly 0 and the canonical pair-tree sum is defined on the zero-padded terms, so probabilities, masks and
+ * labels are bit-identical), results are cut back to K.  ups_copy_rows is that row copy: dst[r, 0:n_cols] = src[r, 0:n_cols],
+ * dst[r, n_cols:n_cols+n_fill] = fill (strides in floats).  The *_planes variants of the encode-side kernels take the
+ * number of part planes that really exist in parts / g_parts (Kpl <= K): padding planes are neither written nor read. */
+int ups_copy_rows(const float* src, long long src_stride, float* dst, long long dst_stride, long long n_rows, int n_cols,
+                  int n_fill, float fill, void* stream);
+int ups_step_encode_fwd_planes(const float* l1, const float* img1, float* m1, float* parts_pm, float* pooled, int B, int P,
+                               int K, int Kpl, void* ws, size_t ws_bytes, void* stream);
+int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
+                               const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, int Kpl, void* stream);
+
 /* K1 + K3 of the fused step in ONE launch (csrc/step_fwd_fused.cu): the TPS warp of the views (ups_tps_warp_pair_fwd's
  * arguments: U [N,S,S,3], optional second image set U2 [N2,S,S,3] sharing the first N2 warps, coord, T -> out, out2) and
  * the decode-side forward (ups_step_decode_fwd's arguments) are independent (model.py:282-311 vs :426-447,482-484);

@@ -2,7 +2,7 @@
 """BASELINE.json configs[4]: part-count / resolution sweep K in {8,16,32} x S in {128,256,512}
 (F=64, V=2), timing the fused step with the CUDA-core K4 and, where it applies (K in {16,32}),
 the TMA + tcgen05 K4; plus K=25 (the reference's shipped n_parts, train_cub_subset_tps.yaml:132), which is not a
-power of two and runs on the generic (unfused) kernels.  Prints one JSON line per cell and a markdown table.
+power of two and runs padded to 32 on the fused kernels (and, for comparison, on the generic unfused kernels).  Prints one JSON line per cell and a markdown table.
 
     python scripts/sweep.py [--out gpurun_out/sweep.json]
 """
@@ -47,11 +47,13 @@ def main():
             g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
             prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234), device=dev, **PENN_TPS)
             coord, tv = ups_b200.make_input_tps_param(prm)
-            for variant in (("generic",) if K == 25 else ("simt", "tc")):
+            for variant in (("padded", "generic") if K == 25 else ("simt", "tc")):
                 if variant == "tc" and K == 8:
                     continue
-                step = PartStep(B, S, K, F, n_views=V, decode_bwd="auto" if variant == "generic" else variant, device=dev)
-                assert step.fused == (variant != "generic")
+                # K = 25: "padded" = the fused kernels of Kp = 32 on -inf padded logits (default), "generic" = the unfused kernels
+                os.environ["UPS_PAD_K"] = "0" if variant == "generic" else "1"
+                step = PartStep(B, S, K, F, n_views=V, decode_bwd=variant if variant in ("simt", "tc") else "auto", device=dev)
+                assert step.fused == (variant != "generic") and bool(step.Kp) == (variant == "padded")
 
                 def one():
                     step.forward(views, coord, tv, l0, l1, feat)

@@ -74,13 +74,31 @@ def test_fused_shapes(ups, B, S, K, F, V):
     _check(out, grad, out_o, grad_o)
 
 
-@pytest.mark.parametrize("B,S,K,F", [(2, 24, 25, 64), (1, 20, 16, 10), (2, 32, 4, 8)])
+@pytest.mark.parametrize("B,S,K,F", [(1, 20, 16, 10), (2, 32, 4, 8), (1, 18, 25, 64)])
 def test_unfused_fallback_shapes(ups, B, S, K, F):
-    """n_parts=25 is what the reference ships (train_cub_subset_tps.yaml:132): handled by the
-    generic kernels, same parity bar."""
+    """Shapes outside the fused kernels (feature sizes other than 16/32/64, pixel counts that are not a multiple of
+    32): the generic kernels, same parity bar."""
     step, out, grad, out_o, grad_o = _run(B, S, K, F, 3, ties=True, seed=K)
-    assert not step.fused
+    assert not step.fused and not step.Kp
     _check(out, grad, out_o, grad_o)
+
+
+@pytest.mark.parametrize("B,S,K,F,V", [(2, 24, 25, 64, 3), (8, 128, 25, 64, 3), (3, 32, 12, 32, 2), (2, 64, 5, 16, 3),
+                                       (2, 32, 31, 64, 2)])
+def test_padded_part_counts(ups, B, S, K, F, V):
+    """n_parts = 25 is what the reference ships (train_cub_subset_tps.yaml:132).  Part counts that are not a power of
+    two run on the fused kernels of the next power of two (logits padded with -inf): same parity bar as the fused path,
+    probabilities / masks / labels bit-exact."""
+    step, out, grad, out_o, grad_o = _run(B, S, K, F, V, ties=True, seed=K, tps=PENN_TPS if V == 2 else None)
+    assert step.fused and step.Kp in (8, 16, 32) and step.Kp >= K
+    assert out["parts"].shape[0] == K * B and out["inj"].shape[-1] == F + K
+    _check(out, grad, out_o, grad_o)
+
+
+def test_padded_part_count_with_views_grad(ups):
+    step, out, grad, out_o, grad_o = _run(2, 64, 25, 64, 3, views_grad=True, seed=8)
+    assert step.Kp == 32
+    _check(out, grad, out_o, grad_o, views_grad=True)
 
 
 def test_views_grad_tps_backward(ups):

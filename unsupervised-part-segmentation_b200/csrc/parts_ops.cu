@@ -454,6 +454,29 @@ extern "C" int ups_part_softmax_bwd(const float* probs, const float* g, float* d
     return ups_part_softmax_bwd2(probs, g, nullptr, nullptr, dlogits, n_pix, K, stream);
 }
 
+// dst[r, 0:n_cols] = src[r, 0:n_cols]; dst[r, n_cols:n_cols+n_fill] = fill.  Row strides in floats.
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst,
+                                 long long dst_stride, long long n_rows, int n_cols, int n_fill, float fill) {
+    const int wd = n_cols + n_fill;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * wd) return;
+    const long long r = i / wd;
+    const int c = (int)(i - r * wd);
+    dst[r * dst_stride + c] = c < n_cols ? __ldcs(src + r * src_stride + c) : fill;
+}
+
+extern "C" int ups_copy_rows(const float* src, long long src_stride, float* dst, long long dst_stride, long long n_rows,
+                             int n_cols, int n_fill, float fill, void* stream) {
+    UPS_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_fill >= 0, "copy_rows: bad sizes");
+    const long long n = n_rows * (n_cols + n_fill);
+    if (n == 0) return UPS_OK;
+    UPS_REQUIRE(dst && (src || n_cols == 0), "copy_rows: null pointer");
+    UPS_REQUIRE(src_stride >= n_cols && dst_stride >= n_cols + n_fill, "copy_rows: row strides smaller than the rows");
+    UPS_GRID_OK(n, TPB);
+    copy_rows_kernel<<<nblk(n, TPB), TPB, 0, as_stream(stream)>>>(src, src_stride, dst, dst_stride, n_rows, n_cols, n_fill, fill);
+    return after_launch("copy_rows_kernel");
+}
+
 extern "C" int ups_axpy(const float* x, float* y, long long n, float a, void* stream) {
     UPS_REQUIRE(x && y && n >= 0, "axpy: null pointer");
     if (n == 0) return UPS_OK;

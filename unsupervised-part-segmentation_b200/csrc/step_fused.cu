@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float
                                                                const float* __restrict__ img1,
                                                                float* __restrict__ m1, float* __restrict__ parts,
                                                                float* __restrict__ partial, int B, int P,
-                                                               int pix_per_cta) {
+                                                               int pix_per_cta, int Kpl) {
+    // Kpl <= K: number of part planes that exist in `parts` (planes Kpl..K-1 are padding of a K that is not a power
+    // of two: their mask is identically zero and they are neither written nor allocated)
     using L = EncFwdSmem<LPP>;
     constexpr int K = L::K, PW = 32 / LPP;
     extern __shared__ float4 smem4[];
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float
             o.y = i4.y * (sft == 2 ? mb : ma);
             o.z = i4.z * (sft >= 1 ? mb : ma);
             o.w = i4.w * mb;
-            st4_stream(parts + (((size_t)k * B + b) * P + pg) * 3 + r0, o);
+            if (k < Kpl) st4_stream(parts + (((size_t)k * B + b) * P + pg) * 3 + r0, o);
         }
         // mean pooling (model.py:50-52 tail): lane = pixel, lane-private accumulators
         {
@@ -277,7 +279,8 @@ __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __re
                                                                const float* __restrict__ m1,
                                                                const float* __restrict__ g_m1,
                                                                float* __restrict__ dl1, float* __restrict__ dimg1,
-                                                               int B, int P, int pix_per_cta) {
+                                                               int B, int P, int pix_per_cta, int Kpl) {
+    // Kpl <= K: planes of g_parts that exist (see step_encode_fwd_kernel); the cotangent of a padding plane is zero
     using L = EncBwdSmem<LPP>;
     constexpr int K = L::K, PW = 32 / LPP;
     extern __shared__ float4 smem4[];
@@ -298,7 +301,8 @@ __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __re
         // async: K planes x 96 floats of g_parts + 96 floats of the image
         for (int i = lane; i < K * 24; i += 32) {
             const int k = i / 24, q = i - 24 * k;
-            cp_async16(Gs + k * 96 + 4 * q, g_parts + (((size_t)k * B + b) * P + pg) * 3 + 4 * q);
+            if (k < Kpl) cp_async16(Gs + k * 96 + 4 * q, g_parts + (((size_t)k * B + b) * P + pg) * 3 + 4 * q);
+            else *reinterpret_cast<float4*>(Gs + k * 96 + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (lane < 24) cp_async16(Iw + 4 * lane, img1 + ((size_t)b * P + pg) * 3 + 4 * lane);
         cp_async_commit();
@@ -430,7 +434,13 @@ extern "C" int ups_step_decode_fwd(const float* l0, const float* feat, float* m0
 
 extern "C" int ups_step_encode_fwd(const float* l1, const float* img1, float* m1, float* parts_pm, float* pooled,
                                    int B, int P, int K, void* ws, size_t ws_bytes, void* stream) {
+    return ups_step_encode_fwd_planes(l1, img1, m1, parts_pm, pooled, B, P, K, K, ws, ws_bytes, stream);
+}
+
+extern "C" int ups_step_encode_fwd_planes(const float* l1, const float* img1, float* m1, float* parts_pm, float* pooled,
+                                          int B, int P, int K, int Kpl, void* ws, size_t ws_bytes, void* stream) {
     UPS_REQUIRE(l1 && img1 && m1 && parts_pm && pooled, "step_encode_fwd: null pointer");
+    UPS_REQUIRE(Kpl >= 1 && Kpl <= K, "step_encode_fwd: %d part planes of K=%d", Kpl, K);
     if (int rc = fused_common_checks("step_encode_fwd", B, P, K)) return rc;
     UPS_REQUIRE(aligned16(l1) && aligned16(img1) && aligned16(m1) && aligned16(parts_pm), "step_encode_fwd: 16-byte alignment");
     if (B == 0) return UPS_OK;
@@ -446,7 +456,7 @@ extern "C" int ups_step_encode_fwd(const float* l1, const float* img1, float* m1
     {                                                                                                         \
         const size_t sm = (size_t)FW * EncFwdSmem<LPP>::WREG * sizeof(float);                                 \
         if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB>, sm)) return rc;                                \
-        step_encode_fwd_kernel<LPP, MB><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per);   \
+        step_encode_fwd_kernel<LPP, MB><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
     }
 #define UPS_ENC_FWD(LPP) \
     { if (minb == 4) UPS_ENC_FWD2(LPP, 4) else if (minb == 5) UPS_ENC_FWD2(LPP, 5) else UPS_ENC_FWD2(LPP, 6) }
@@ -494,7 +504,14 @@ extern "C" int ups_step_decode_bwd(const float* g_inj, const float* m0, const fl
 
 extern "C" int ups_step_encode_bwd(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
                                    const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, void* stream) {
+    return ups_step_encode_bwd_planes(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, K, K, stream);
+}
+
+extern "C" int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
+                                          const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, int Kpl,
+                                          void* stream) {
     UPS_REQUIRE(g_parts_pm && img1 && m1 && dl1, "step_encode_bwd: null pointer");
+    UPS_REQUIRE(Kpl >= 1 && Kpl <= K, "step_encode_bwd: %d part planes of K=%d", Kpl, K);
     if (int rc = fused_common_checks("step_encode_bwd", B, P, K)) return rc;
     UPS_REQUIRE(aligned16(g_parts_pm) && aligned16(img1) && aligned16(m1) && aligned16(dl1) && (!g_m1 || aligned16(g_m1)) &&
                     (!dimg1 || aligned16(dimg1)), "step_encode_bwd: 16-byte alignment");
@@ -507,10 +524,10 @@ extern "C" int ups_step_encode_bwd(const float* g_parts_pm, const float* g_poole
         const size_t sm = ((size_t)FW * EncBwdSmem<LPP>::WREG + 4 * LPP * 3 + 4) * sizeof(float);                     \
         if (dimg1) {                                                                                                  \
             if (int rc = set_smem(step_encode_bwd_kernel<LPP, true>, sm)) return rc;                                  \
-            step_encode_bwd_kernel<LPP, true><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per); \
+            step_encode_bwd_kernel<LPP, true><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
         } else {                                                                                                      \
             if (int rc = set_smem(step_encode_bwd_kernel<LPP, false>, sm)) return rc;                                 \
-            step_encode_bwd_kernel<LPP, false><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per); \
+            step_encode_bwd_kernel<LPP, false><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
         }                                                                                                             \
     }
     if (K == 4) UPS_ENC_BWD(1) else if (K == 8) UPS_ENC_BWD(2) else if (K == 16) UPS_ENC_BWD(4) else UPS_ENC_BWD(8)

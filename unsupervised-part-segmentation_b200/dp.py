@@ -336,7 +336,10 @@ class DataParallelPartStep:
         after_k4 = self.main_after_k4
         if not after_k4:
             red.launch(0)                  # side stream, behind what is queued on the main stream so far
-        out = st.backward_decode(g_inj, g_m0)
+        if st.Kp:   # padded part count: the step's backward is one call (K4 and K5 inside)
+            out = st.backward(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
+        else:
+            out = st.backward_decode(g_inj, g_m0)
         if after_k4:
             red.launch(0)
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
@@ -345,5 +348,7 @@ class DataParallelPartStep:
                 C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
                        self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
         red.launch(1)
+        if st.Kp:
+            return out
         out.update(st.backward_encode(g_parts, g_pooled, g_m1, g_warped))
         return out

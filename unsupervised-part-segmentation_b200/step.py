@@ -39,10 +39,12 @@ def _on_device(fn):
 
 class PartStep:
     def __init__(self, batch_size, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, device="cuda", decode_bwd="auto", first_conv=0):
+                 views_grad=False, device="cuda", decode_bwd="auto", first_conv=0, _planes=None):
         B, S, K, F, V = int(batch_size), int(spatial_size), int(n_parts), int(local_app_size), int(n_views)
         self.B, self.S, self.K, self.F, self.V = B, S, K, F, V
         self.P = S * S
+        # _planes (internal): part planes that really exist when this step runs a padded part count (see below)
+        self.Kpl = K if _planes is None else int(_planes)
         self.use_tps = bool(use_tps) and V >= 2
         self.views_grad = bool(views_grad)
         self.device = torch.device(device)
@@ -51,6 +53,19 @@ class PartStep:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.fused = K in (8, 16, 32) and F in (16, 32, 64) and self.P % 32 == 0
+        # A part count that is not a power of two (the reference ships n_parts = 25, train_cub_subset_tps.yaml:132) runs on
+        # the fused kernels of the next power of two Kp: logits padded with -inf, everything else with zeros.  exp_canon
+        # maps -inf to exactly 0 and the canonical K-way sum is a pair tree over the zero-padded terms, so
+        # probabilities, masks and labels are bit-identical to the K-part evaluation; padding planes of the part images
+        # are neither written nor read (csrc: *_planes entry points).  UPS_PAD_K=0 keeps the generic kernels.
+        self.Kp = 0
+        if (not self.fused and _planes is None and not first_conv and 1 <= K < 32 and F in (16, 32, 64)
+                and self.P % 32 == 0 and os.environ.get("UPS_PAD_K", "1") != "0"):
+            self.Kp = 8 if K <= 8 else 16 if K <= 16 else 32
+            self._inner = PartStep(B, S, self.Kp, F, n_views=V, use_tps=use_tps, views_grad=views_grad, device=self.device,
+                                   decode_bwd=decode_bwd, _planes=K)
+            self._init_padded()
+            return
         # K4 variant: "tc" = persistent TMA + tcgen05/TMEM pipeline, "simt" = CUDA-core kernel
         tc_ok = self.fused and K in (16, 32) and F == 64 and self.P % 128 == 0
         assert decode_bwd in ("auto", "tc", "simt")
@@ -63,7 +78,7 @@ class PartStep:
         self.warped = e(max(V, 2), B, S, S, 3, **f32) if self.use_tps else None
         self.m0, self.m1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
         self.labels0 = e(B, S, S, dtype=torch.int64, device=self.device)
-        self.parts = e(K * B, S, S, 3, **f32)
+        self.parts = e(self.Kpl * B, S, S, 3, **f32)
         self.pooled = e(B, K, 3, **f32)
         # first_conv = Co > 0: the decode side ends in the decoder's first 3x3 convolution (h0 [B,S,S,Co]) instead of
         # the injected map; forward takes the filter (conv_V [3,3,F+K,Co], conv_b [Co]), backward g_h0
@@ -104,6 +119,72 @@ class PartStep:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # ------------------------------------------------------------------ padded part count (K -> Kp)
+    def _init_padded(self):
+        B, S, K, F, Kp = self.B, self.S, self.K, self.F, self.Kp
+        f32 = dict(dtype=torch.float32, device=self.device)
+        e, inner = torch.empty, self._inner
+        self.fused, self.fuse_fwd, self.decode_bwd, self.Co = True, inner.fuse_fwd, inner.decode_bwd, 0
+        self._l0p, self._l1p = e(B, S, S, Kp, **f32), e(B, S, S, Kp, **f32)
+        self._featp = torch.zeros(B, Kp, F, **f32)
+        self._g_injp = e(B, S, S, F + Kp, **f32)
+        self._g_m0p, self._g_m1p = e(B, S, S, Kp, **f32), e(B, S, S, Kp, **f32)
+        self._g_pooledp = torch.zeros(B, Kp, 3, **f32)
+        self.m0, self.m1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
+        self.inj = e(B, S, S, F + K, **f32)
+        self.dl0, self.dl1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
+        self.pooled, self.dfeat = e(B, K, 3, **f32), e(B, K, F, **f32)
+        self.labels0, self.parts, self.warped = inner.labels0, inner.parts, inner.warped
+        self._labels_u8 = None
+
+    def _rows(self, src, dst, n_rows, n_cols, n_fill, fill, st):
+        C.call("ups_copy_rows", src.data_ptr(), src.shape[-1], dst.data_ptr(), dst.shape[-1], n_rows, n_cols, n_fill, fill, st)
+
+    @_on_device
+    def _forward_padded(self, views, coord, t_vector, l0, l1, feat):
+        B, S, K, F, P, Kp = self.B, self.S, self.K, self.F, self.P, self.Kp
+        st = self._stream()
+        assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
+        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        ninf = float("-inf")
+        self._rows(l0, self._l0p, B * P, K, Kp - K, ninf, st)
+        self._rows(l1, self._l1p, B * P, K, Kp - K, ninf, st)
+        # feat [B,K,F] -> [B,Kp,F]: per sample the first K*F floats of the padded block (the rest stays zero)
+        C.call("ups_copy_rows", feat.data_ptr(), K * F, self._featp.data_ptr(), Kp * F, B, K * F, 0, 0.0, st)
+        o = self._inner.forward(views, coord, t_vector, self._l0p, self._l1p, self._featp)
+        self._rows(o["m0"], self.m0, B * P, K, 0, 0.0, st)
+        self._rows(o["m1"], self.m1, B * P, K, 0, 0.0, st)
+        self._rows(o["inj"], self.inj, B * P, F + K, 0, 0.0, st)        # [F | Kp] -> [F | K]: a prefix of every row
+        C.call("ups_copy_rows", o["pooled"].data_ptr(), Kp * 3, self.pooled.data_ptr(), K * 3, B, K * 3, 0, 0.0, st)
+        self._feat, self._img1 = feat, self._inner._img1
+        return dict(warped=o["warped"], m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts, pooled=self.pooled,
+                    inj=self.inj)
+
+    @_on_device
+    def _backward_padded(self, g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped):
+        B, S, K, F, P, Kp = self.B, self.S, self.K, self.F, self.P, self.Kp
+        st = self._stream()
+        assert tuple(g_inj.shape) == (B, S, S, F + K) and tuple(g_parts.shape) == (K * B, S, S, 3)
+        self._rows(g_inj, self._g_injp, B * P, F + K, Kp - K, 0.0, st)
+        gm0 = gm1 = gpl = None
+        if g_m0 is not None:
+            self._rows(g_m0, self._g_m0p, B * P, K, Kp - K, 0.0, st)
+            gm0 = self._g_m0p
+        if g_m1 is not None:
+            self._rows(g_m1, self._g_m1p, B * P, K, Kp - K, 0.0, st)
+            gm1 = self._g_m1p
+        if g_pooled is not None:
+            C.call("ups_copy_rows", g_pooled.data_ptr(), K * 3, self._g_pooledp.data_ptr(), Kp * 3, B, K * 3, 0, 0.0, st)
+            gpl = self._g_pooledp
+        o = self._inner.backward(self._g_injp, g_parts, gpl, gm0, gm1, g_warped)
+        self._rows(o["dl0"], self.dl0, B * P, K, 0, 0.0, st)
+        self._rows(o["dl1"], self.dl1, B * P, K, 0, 0.0, st)
+        C.call("ups_copy_rows", o["dfeat"].data_ptr(), Kp * F, self.dfeat.data_ptr(), K * F, B, K * F, 0, 0.0, st)
+        out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
+        if "dviews" in o:
+            out["dviews"] = o["dviews"]
+        return out
+
     # ------------------------------------------------------------------ forward
     def _decode_fwd(self, l0, feat, conv_V, conv_b, st):
         """decode side on stream `st`: K3, or with first_conv softmax -> table -> 3x3 conv on the assignment"""
@@ -128,6 +209,8 @@ class PartStep:
         CTAs (ups_step_warp_decode_fwd): the warp's arithmetic hides under the decode side's memory stream.
         forward_warp / forward_parts are the same step as two calls (K1 | K2, K3) for callers that have the views
         before the logits."""
+        if self.Kp:
+            return self._forward_padded(views, coord, t_vector, l0, l1, feat)
         if self.fuse_fwd:
             return self._forward_fused(views, coord, t_vector, l0, l1, feat)
         self.forward_warp(views, coord, t_vector)
@@ -149,8 +232,8 @@ class PartStep:
         self._warped, self._coord = self.warped, coord
         img1 = self.warped[1]
         self._img1, self._feat = img1, feat
-        C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
-               self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
+        C.call("ups_step_encode_fwd_planes", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+               self.pooled.data_ptr(), B, P, K, self.Kpl, self.ws.data_ptr(), self.ws.numel(), st)
         return dict(warped=self.warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
                     pooled=self.pooled, inj=self.inj)
 
@@ -159,6 +242,8 @@ class PartStep:
         """labels0 narrowed to uint8 on the device (n_parts <= 255): the label map a host-side consumer reads back,
         one byte per pixel instead of tf.argmax's eight."""
         assert self.K <= 255
+        if self.Kp:
+            return self._inner.labels_u8()
         if self._labels_u8 is None:
             self._labels_u8 = torch.empty(self.labels0.shape, dtype=torch.uint8, device=self.device)
         C.call("ups_labels_i64_to_u8", self.labels0.data_ptr(), self._labels_u8.data_ptr(), self.labels0.numel(),
@@ -213,8 +298,8 @@ class PartStep:
         img1 = warped[1]
         self._img1, self._feat = img1, feat
         if self.fused:
-            C.call("ups_step_encode_fwd", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
-                   self.pooled.data_ptr(), B, P, K, self.ws.data_ptr(), self.ws.numel(), st)
+            C.call("ups_step_encode_fwd_planes", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+                   self.pooled.data_ptr(), B, P, K, self.Kpl, self.ws.data_ptr(), self.ws.numel(), st)
         else:
             C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
             C.call("ups_mask_parts_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.parts.data_ptr(), B, P, K, 3, 1, st)
@@ -241,6 +326,8 @@ class PartStep:
 
         = backward_decode (K4: dl0, dfeat — what the appearance encoder's backward needs) followed by
         backward_encode (K5 [, K6]: dl1 [, dviews])."""
+        if self.Kp:
+            return self._backward_padded(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
         out = self.backward_decode(g_inj, g_m0)
         out.update(self.backward_encode(g_parts, g_pooled, g_m1, g_warped))
         return out
@@ -283,8 +370,8 @@ class PartStep:
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         want_dimg = self.views_grad
         if self.fused:
-            C.call("ups_step_encode_bwd", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
-                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, st)
+            C.call("ups_step_encode_bwd_planes", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
+                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, self.Kpl, st)
         else:
             C.call("ups_mask_parts_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
                    self.dimg1.data_ptr() if want_dimg else None, self.dm.data_ptr(), B, P, K, 3, 1, st)
