@@ -256,3 +256,19 @@ def test_unpool_features_gathered_backward(ups):
     fc = feat.cuda().requires_grad_(True)
     (d_c,) = torch.autograd.grad(ups.unpool_features_gathered(fc, labels.cuda()), fc, G.cuda())
     assert_close(d_c, d_o, "dfeat of the gathered unpooling")
+
+
+@pytest.mark.parametrize("n_rows,n_cols,n_fill,ss,ds", [(1000, 25, 7, 25, 32), (1000, 25, 0, 32, 25), (77, 89, 7, 89, 96),
+                                                      (77, 89, 0, 96, 89), (5, 3, 2, 6, 7), (64, 48, 0, 96, 48)])
+def test_copy_rows(n_rows, n_cols, n_fill, ss, ds):
+    """ups_copy_rows (padding / cutting the [.,K] rows of a part count that is not a power of two): vector and scalar paths."""
+    from ups_b200 import _cabi as C
+    g = torch.Generator().manual_seed(n_cols)
+    src = torch.randn(n_rows, ss, generator=g).cuda()
+    dst = torch.full((n_rows, ds), 7.0, device="cuda")
+    C.call("ups_copy_rows", src.data_ptr(), ss, dst.data_ptr(), ds, n_rows, n_cols, n_fill, float("-inf"),
+           torch.cuda.current_stream().cuda_stream)
+    want = torch.full((n_rows, ds), 7.0)
+    want[:, :n_cols] = src.cpu()[:, :n_cols]
+    want[:, n_cols:n_cols + n_fill] = float("-inf")
+    assert torch.equal(dst.cpu(), want)

@@ -465,6 +465,32 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_st
     dst[r * dst_stride + c] = c < n_cols ? __ldcs(src + r * src_stride + c) : fill;
 }
 
+// the same copy with 16-byte accesses on the side whose rows are 16-byte aligned (PAD: the destination, row width
+// n_cols + n_fill; !PAD: the source, n_fill == 0): one thread per float4 of the aligned rows, 32-bit index arithmetic
+template <bool PAD>
+__global__ void copy_rows_vec_kernel(const float* __restrict__ src, unsigned src_stride, float* __restrict__ dst,
+                                     unsigned dst_stride, unsigned n_chunks_total, unsigned chunks, int n_cols, float fill) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunks_total) return;
+    const unsigned r = i / chunks, c0 = 4 * (i - r * chunks);
+    if (PAD) {
+        const float* sp = src + (size_t)r * src_stride + c0;
+        float4 v;
+        v.x = (int)c0 < n_cols ? __ldcs(sp) : fill;
+        v.y = (int)c0 + 1 < n_cols ? __ldcs(sp + 1) : fill;
+        v.z = (int)c0 + 2 < n_cols ? __ldcs(sp + 2) : fill;
+        v.w = (int)c0 + 3 < n_cols ? __ldcs(sp + 3) : fill;
+        st4_stream(dst + (size_t)r * dst_stride + c0, v);
+    } else {
+        const float4 v = ld4_stream(src + (size_t)r * src_stride + c0);
+        float* dp = dst + (size_t)r * dst_stride + c0;
+        if ((int)c0 < n_cols) __stcs(dp, v.x);
+        if ((int)c0 + 1 < n_cols) __stcs(dp + 1, v.y);
+        if ((int)c0 + 2 < n_cols) __stcs(dp + 2, v.z);
+        if ((int)c0 + 3 < n_cols) __stcs(dp + 3, v.w);
+    }
+}
+
 extern "C" int ups_copy_rows(const float* src, long long src_stride, float* dst, long long dst_stride, long long n_rows,
                              int n_cols, int n_fill, float fill, void* stream) {
     UPS_REQUIRE(n_rows >= 0 && n_cols >= 0 && n_fill >= 0, "copy_rows: bad sizes");
@@ -472,6 +498,24 @@ extern "C" int ups_copy_rows(const float* src, long long src_stride, float* dst,
     if (n == 0) return UPS_OK;
     UPS_REQUIRE(dst && (src || n_cols == 0), "copy_rows: null pointer");
     UPS_REQUIRE(src_stride >= n_cols && dst_stride >= n_cols + n_fill, "copy_rows: row strides smaller than the rows");
+    {
+        const int wd = n_cols + n_fill;
+        const bool small = src_stride < (1ll << 31) && dst_stride < (1ll << 31);
+        // pad: the destination rows are whole float4s
+        if (small && wd % 4 == 0 && dst_stride % 4 == 0 && aligned16(dst) && n_rows * (wd / 4) < (1ll << 31)) {
+            const unsigned chunks = (unsigned)(wd / 4), total = (unsigned)(n_rows * chunks);
+            copy_rows_vec_kernel<true><<<(total + TPB - 1) / TPB, TPB, 0, as_stream(stream)>>>(
+                src, (unsigned)src_stride, dst, (unsigned)dst_stride, total, chunks, n_cols, fill);
+            return after_launch("copy_rows_vec_kernel");
+        }
+        // cut: the source rows are whole float4s and nothing is filled
+        if (small && n_fill == 0 && src_stride % 4 == 0 && aligned16(src) && n_rows * ((n_cols + 3) / 4) < (1ll << 31)) {
+            const unsigned chunks = (unsigned)((n_cols + 3) / 4), total = (unsigned)(n_rows * chunks);
+            copy_rows_vec_kernel<false><<<(total + TPB - 1) / TPB, TPB, 0, as_stream(stream)>>>(
+                src, (unsigned)src_stride, dst, (unsigned)dst_stride, total, chunks, n_cols, fill);
+            return after_launch("copy_rows_vec_kernel");
+        }
+    }
     UPS_GRID_OK(n, TPB);
     copy_rows_kernel<<<nblk(n, TPB), TPB, 0, as_stream(stream)>>>(src, src_stride, dst, dst_stride, n_rows, n_cols, n_fill, fill);
     return after_launch("copy_rows_kernel");
