@@ -25,10 +25,10 @@ if os.path.exists(lp):
     for r in rows[1:]:
         n = r[i_name].split("(")[0].replace("void ", "")
         agg.setdefault(n, []).append(float(r[i_val].replace(",", "")))
-    ours = {n: v for n, v in agg.items() if n.startswith(("ups::", "tc::", "tma::"))}
+    ours = {n: v for n, v in agg.items() if n.startswith(("ups::", "tc::", "tma::", "pctc::", "standin::", "dp::"))}
     tot = sum(sum(v) for v in ours.values())
     out.append(f"## Launch list ({tag}_launches.csv: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-               "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-n4`)\n")
+               "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-n4 --no-scale-workloads`)\n")
     out.append("Library kernels only (torch's RNG/fill kernels that build the synthetic inputs are excluded from the share).\n")
     out.append("| kernel | launches | mean µs | share of path time |\n|---|---|---|---|")
     for n, v in ours.items():
@@ -92,7 +92,7 @@ if os.path.exists(rp):
               open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 
 # ---- bench lines of the same round
-for name in ("auto", "simt", "df", "penn"):
+for name in ("auto", "simt", "df", "penn", "cub", "deepfashion", "pennaction", "tpsbwd"):
     bp = os.path.join(G, f"{tag}_bench_{name}.json")
     if os.path.exists(bp) and os.path.getsize(bp):
         try:
