@@ -47,17 +47,26 @@ def main():
             g_m1 = torch.randn(B, S, S, K, device=dev, generator=g)
             prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234), device=dev, **PENN_TPS)
             coord, tv = ups_b200.make_input_tps_param(prm)
-            for variant in (("padded", "generic") if K == 25 else ("simt", "tc")):
+            for variant in (("padded", "pitched", "generic") if K == 25 else ("simt", "tc")):
                 if variant == "tc" and K == 8:
                     continue
-                # K = 25: "padded" = the fused kernels of Kp = 32 on -inf padded logits (default), "generic" = the unfused kernels
+                a_l0, a_l1, a_g_inj, a_g_m0, a_g_m1 = l0, l1, g_inj, g_m0, g_m1
+                # K = 25: "padded" = the fused kernels of Kp = 32 on -inf padded logits, contiguous inputs copied into the
+                # row-pitched buffers (default); "pitched" = the producer writes into PartStep.pitched_inputs() (no copies);
+                # "generic" = the unfused kernels
                 os.environ["UPS_PAD_K"] = "0" if variant == "generic" else "1"
                 step = PartStep(B, S, K, F, n_views=V, decode_bwd=variant if variant in ("simt", "tc") else "auto", device=dev)
-                assert step.fused == (variant != "generic") and bool(step.Kp) == (variant == "padded")
+                assert step.fused == (variant != "generic") and bool(step.Kp) == (variant in ("padded", "pitched"))
+                a_l0, a_l1, a_g_inj, a_g_m0, a_g_m1 = l0, l1, g_inj, g_m0, g_m1
+                if variant == "pitched":
+                    pin = step.pitched_inputs()
+                    for nm, src in (("l0", l0), ("l1", l1), ("g_inj", g_inj), ("g_m0", g_m0), ("g_m1", g_m1)):
+                        pin[nm].copy_(src)
+                    a_l0, a_l1, a_g_inj, a_g_m0, a_g_m1 = pin["l0"], pin["l1"], pin["g_inj"], pin["g_m0"], pin["g_m1"]
 
                 def one():
-                    step.forward(views, coord, tv, l0, l1, feat)
-                    step.backward(g_inj, g_parts, g_pooled, g_m0, g_m1)
+                    step.forward(views, coord, tv, a_l0, a_l1, feat)
+                    step.backward(a_g_inj, g_parts, g_pooled, a_g_m0, a_g_m1)
                 for _ in range(3):
                     one()
                 torch.cuda.synchronize()

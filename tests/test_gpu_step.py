@@ -351,3 +351,34 @@ def test_full_size_pennaction_b512_slice_equality(ups):
     assert_close(grad["dl1"][idx], grad_o["dl1"], "dl1")
     assert_close(grad["dfeat"][idx], r64["dfeat"], "dfeat", atol=own_error_atol(grad_o["dfeat"], r64["dfeat"]))
     assert_close(out["pooled"][idx], r64["pooled"], "pooled", atol=own_error_atol(out_o["pooled"], r64["pooled"]))
+
+
+def test_padded_part_count_pitched_inputs_are_zero_copy(ups):
+    """A producer that writes logits / cotangents into PartStep.pitched_inputs() (row pitch Kp floats) gets the same bits
+    as the contiguous-tensor path, without the pad copies."""
+    from ups_b200 import _cabi as C
+    from ups_b200.step import PartStep
+    B, S, K, F, V = 3, 64, 25, 64, 3
+    d = cuda(make_inputs(B, S, K, F, V, seed=2))
+    c = d["cot"]
+    a = PartStep(B, S, K, F, n_views=V)
+    oa = a.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    ga = a.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
+    b = PartStep(B, S, K, F, n_views=V)
+    pin = b.pitched_inputs()
+    for name, src in (("l0", d["l0"]), ("l1", d["l1"]), ("g_inj", c["g_inj"]), ("g_m0", c["g_m0"]), ("g_m1", c["g_m1"])):
+        assert not pin[name].is_contiguous() and pin[name].shape == src.shape
+        pin[name].copy_(src)
+    C.launch_count_reset()
+    ob = b.forward(d["views"], d["coord"], d["t_vector"], pin["l0"], pin["l1"], d["feat"])
+    gb = b.backward(pin["g_inj"], c["g_parts"], c["g_pooled"], pin["g_m0"], pin["g_m1"])
+    n_pitched = C.launch_count()
+    torch.cuda.synchronize()
+    for k in ("m0", "m1", "labels0", "parts", "pooled", "inj"):
+        assert torch.equal(oa[k], ob[k]), k
+    for k in ("dl0", "dl1", "dfeat"):
+        assert torch.equal(ga[k], gb[k]), k
+    C.launch_count_reset()
+    a.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    a.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
+    assert C.launch_count() == n_pitched + 5, "the contiguous path adds exactly the five pad copies"

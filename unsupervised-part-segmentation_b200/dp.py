@@ -345,7 +345,8 @@ class DataParallelPartStep:
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
         if self.standin:
             with torch.cuda.device(dev):
-                C.call("ups_standin_tail_bwd", st.pooled.data_ptr(), st.dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
+                pooled, dfeat = st.pooled.contiguous(), st.dfeat.contiguous()     # views of row-pitched buffers for a padded K
+                C.call("ups_standin_tail_bwd", pooled.data_ptr(), dfeat.data_ptr(), self.grads_tail.data_ptr(), B, K, 3, F,
                        self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
         red.launch(1)
         if st.Kp:

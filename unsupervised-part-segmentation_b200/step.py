@@ -123,39 +123,52 @@ class PartStep:
     def _init_padded(self):
         B, S, K, F, Kp = self.B, self.S, self.K, self.F, self.Kp
         f32 = dict(dtype=torch.float32, device=self.device)
-        e, inner = torch.empty, self._inner
+        inner = self._inner
         self.fused, self.fuse_fwd, self.decode_bwd, self.Co = True, inner.fuse_fwd, inner.decode_bwd, 0
-        self._l0p, self._l1p = e(B, S, S, Kp, **f32), e(B, S, S, Kp, **f32)
+        # padded inputs, pad regions written once: -inf for logits, 0 for everything else
+        self._l0p = torch.full((B, S, S, Kp), float("-inf"), **f32)
+        self._l1p = torch.full((B, S, S, Kp), float("-inf"), **f32)
         self._featp = torch.zeros(B, Kp, F, **f32)
-        self._g_injp = e(B, S, S, F + Kp, **f32)
-        self._g_m0p, self._g_m1p = e(B, S, S, Kp, **f32), e(B, S, S, Kp, **f32)
+        self._g_injp = torch.zeros(B, S, S, F + Kp, **f32)
+        self._g_m0p, self._g_m1p = torch.zeros(B, S, S, Kp, **f32), torch.zeros(B, S, S, Kp, **f32)
         self._g_pooledp = torch.zeros(B, Kp, 3, **f32)
-        self.m0, self.m1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
-        self.inj = e(B, S, S, F + K, **f32)
-        self.dl0, self.dl1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
-        self.pooled, self.dfeat = e(B, K, 3, **f32), e(B, K, F, **f32)
+        # outputs are VIEWS of the inner step's padded buffers (row pitch Kp floats): nothing is copied back
+        self.m0, self.m1 = inner.m0[..., :K], inner.m1[..., :K]
+        self.inj = inner.inj[..., :F + K]
+        self.dl0, self.dl1 = inner.dl0[..., :K], inner.dl1[..., :K]
+        self.pooled, self.dfeat = inner.pooled[:, :K], inner.dfeat[:, :K]
         self.labels0, self.parts, self.warped = inner.labels0, inner.parts, inner.warped
         self._labels_u8 = None
 
-    def _rows(self, src, dst, n_rows, n_cols, n_fill, fill, st):
-        C.call("ups_copy_rows", src.data_ptr(), src.shape[-1], dst.data_ptr(), dst.shape[-1], n_rows, n_cols, n_fill, fill, st)
+    def pitched_inputs(self):
+        """Padded part count only: views [..., :K] of the step's internal row-pitched input buffers (l0, l1, g_inj, g_m0,
+        g_m1).  A producer that writes its logits / cotangents into these (row pitch Kp floats instead of K) hands them
+        to forward / backward without any copy; contiguous tensors are accepted as well and are copied into the buffers."""
+        assert self.Kp, "pitched_inputs() is for part counts that are not a power of two"
+        K, F = self.K, self.F
+        return dict(l0=self._l0p[..., :K], l1=self._l1p[..., :K], g_inj=self._g_injp[..., :F + K],
+                    g_m0=self._g_m0p[..., :K], g_m1=self._g_m1p[..., :K])
+
+    def _into(self, t, buf, n_cols, fill, st):
+        """t [.., n_cols] -> the row-pitched buffer `buf` [.., pitch]; no-op when t already is the buffer's view."""
+        if t.data_ptr() == buf.data_ptr() and t.stride() == buf.stride() and t.shape[-1] == n_cols:
+            return
+        assert t.is_contiguous(), "pass a contiguous tensor or the view from pitched_inputs()"
+        n_rows = t.numel() // n_cols
+        C.call("ups_copy_rows", t.data_ptr(), n_cols, buf.data_ptr(), buf.shape[-1], n_rows, n_cols,
+               buf.shape[-1] - n_cols, fill, st)
 
     @_on_device
     def _forward_padded(self, views, coord, t_vector, l0, l1, feat):
         B, S, K, F, P, Kp = self.B, self.S, self.K, self.F, self.P, self.Kp
         st = self._stream()
-        assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
+        assert feat.is_contiguous()
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
-        ninf = float("-inf")
-        self._rows(l0, self._l0p, B * P, K, Kp - K, ninf, st)
-        self._rows(l1, self._l1p, B * P, K, Kp - K, ninf, st)
+        self._into(l0, self._l0p, K, float("-inf"), st)
+        self._into(l1, self._l1p, K, float("-inf"), st)
         # feat [B,K,F] -> [B,Kp,F]: per sample the first K*F floats of the padded block (the rest stays zero)
         C.call("ups_copy_rows", feat.data_ptr(), K * F, self._featp.data_ptr(), Kp * F, B, K * F, 0, 0.0, st)
         o = self._inner.forward(views, coord, t_vector, self._l0p, self._l1p, self._featp)
-        self._rows(o["m0"], self.m0, B * P, K, 0, 0.0, st)
-        self._rows(o["m1"], self.m1, B * P, K, 0, 0.0, st)
-        self._rows(o["inj"], self.inj, B * P, F + K, 0, 0.0, st)        # [F | Kp] -> [F | K]: a prefix of every row
-        C.call("ups_copy_rows", o["pooled"].data_ptr(), Kp * 3, self.pooled.data_ptr(), K * 3, B, K * 3, 0, 0.0, st)
         self._feat, self._img1 = feat, self._inner._img1
         return dict(warped=o["warped"], m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts, pooled=self.pooled,
                     inj=self.inj)
@@ -165,21 +178,18 @@ class PartStep:
         B, S, K, F, P, Kp = self.B, self.S, self.K, self.F, self.P, self.Kp
         st = self._stream()
         assert tuple(g_inj.shape) == (B, S, S, F + K) and tuple(g_parts.shape) == (K * B, S, S, 3)
-        self._rows(g_inj, self._g_injp, B * P, F + K, Kp - K, 0.0, st)
+        self._into(g_inj, self._g_injp, F + K, 0.0, st)
         gm0 = gm1 = gpl = None
         if g_m0 is not None:
-            self._rows(g_m0, self._g_m0p, B * P, K, Kp - K, 0.0, st)
+            self._into(g_m0, self._g_m0p, K, 0.0, st)
             gm0 = self._g_m0p
         if g_m1 is not None:
-            self._rows(g_m1, self._g_m1p, B * P, K, Kp - K, 0.0, st)
+            self._into(g_m1, self._g_m1p, K, 0.0, st)
             gm1 = self._g_m1p
         if g_pooled is not None:
             C.call("ups_copy_rows", g_pooled.data_ptr(), K * 3, self._g_pooledp.data_ptr(), Kp * 3, B, K * 3, 0, 0.0, st)
             gpl = self._g_pooledp
         o = self._inner.backward(self._g_injp, g_parts, gpl, gm0, gm1, g_warped)
-        self._rows(o["dl0"], self.dl0, B * P, K, 0, 0.0, st)
-        self._rows(o["dl1"], self.dl1, B * P, K, 0, 0.0, st)
-        C.call("ups_copy_rows", o["dfeat"].data_ptr(), Kp * F, self.dfeat.data_ptr(), K * F, B, K * F, 0, 0.0, st)
         out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
         if "dviews" in o:
             out["dviews"] = o["dviews"]
