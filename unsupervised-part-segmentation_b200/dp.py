@@ -162,14 +162,10 @@ class GradAllReducer:
         self._done = None
         if self.impl == "nccl" and self.world > 1:
             self.grad_scale = 1.0 / self.world
+        self._range_tables = {}
         if self.impl == "peer":
-            self._tables = []
             for o, n in self.bounds:
                 assert n % 4 == 0 or o + n == n_floats, "peer buckets are multiples of 4 floats"
-                bufs = (ctypes.c_void_p * self.world)(*[p + 4 * o for p in self._buf_ptrs])
-                sigs = (ctypes.c_void_p * self.world)(*self._sig_ptrs)
-                mc = (self._mc_ptr + 4 * o) if self._mc_ptr else None
-                self._tables.append((bufs, sigs, mc, (n + 3) // 4 * 4))
 
     def _setup_symmetric(self, n_floats, device):
         import torch.distributed._symmetric_memory as symm
@@ -207,9 +203,19 @@ class GradAllReducer:
             return "nvls-multicast" if self._mc_ptr else "nvlink-peer"
         return self.impl
 
-    def launch(self, bucket=None, after=None):
+    def _table(self, off, n):
+        """Pointer tables of the sub-range [off, off+n) floats of the flat buffer (cached)."""
+        key = (off, n)
+        if key not in self._range_tables:
+            bufs = (ctypes.c_void_p * self.world)(*[p + 4 * off for p in self._buf_ptrs])
+            sigs = (ctypes.c_void_p * self.world)(*self._sig_ptrs)
+            self._range_tables[key] = (bufs, sigs, (self._mc_ptr + 4 * off) if self._mc_ptr else None, (n + 3) // 4 * 4)
+        return self._range_tables[key]
+
+    def launch(self, bucket=None, after=None, part=None, n_ctas=None):
         """Enqueue the all-reduce of one bucket (default: all) on the side stream, behind everything already
-        queued on the current stream (or behind the event `after`)."""
+        queued on the current stream (or behind the event `after`).  part = (i, n): only the i-th of n equal pieces
+        of the bucket; n_ctas overrides the reducer's CTA count for this launch."""
         if self.world == 1:
             if self.cuda:   # nothing to exchange, but whatever the caller queued on the side stream is still waited for
                 if after is not None:
@@ -230,13 +236,19 @@ class GradAllReducer:
             self.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
             for i in idx:
+                o, n = self.bounds[i]
+                if part is not None:
+                    pi, pn = part
+                    lo = o + (n * pi // pn) // 4 * 4
+                    hi = o + n if pi == pn - 1 else o + (n * (pi + 1) // pn) // 4 * 4
+                    o, n = lo, hi - lo
                 if self.impl == "peer":
-                    bufs, sigs, mc, n = self._tables[i]
+                    bufs, sigs, mc, n4 = self._table(o, n)
                     C.call("ups_dp_allreduce", ctypes.cast(bufs, ctypes.c_void_p), mc, ctypes.cast(sigs, ctypes.c_void_p),
-                           self.rank, self.world, n, 1.0 / self.world, self.n_ctas, self.stream.cuda_stream)
+                           self.rank, self.world, n4, 1.0 / self.world, int(n_ctas or self.n_ctas), self.stream.cuda_stream)
                 else:
                     # SUM (not AVG): NCCL's in-switch algorithms exist for sum only; the consumer applies grad_scale
-                    dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(self.flat[o:o + n], op=dist.ReduceOp.SUM, group=self.group)
             self._done = torch.cuda.Event()
             self._done.record(self.stream)
 
@@ -289,6 +301,9 @@ class DataParallelPartStep:
             main_bucket = default_main_bucket(self.world)
         assert main_bucket in ("before_k4", "after_k4"), main_bucket
         self.main_after_k4 = main_bucket == "after_k4"
+        # experiment knob: UPS_DP_SPLIT=<ctas>: first half of the main bucket before K4, second half after K4 with <ctas> CTAs
+        self.split_ctas = int(os.environ.get("UPS_DP_SPLIT", "0"))
+        self.main_split = self.split_ctas > 0
         self.step = PartStep(per_gpu_batch, spatial_size, n_parts, local_app_size, n_views, use_tps, views_grad, device,
                              decode_bwd=decode_bwd)
         dev = self.step.device
@@ -310,8 +325,13 @@ class DataParallelPartStep:
 
     # ---------------------------------------------------------------- forward
     def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None):
-        # the parameters (hence the averaged gradients of the previous step) are needed from the first kernel on
-        self.reducer.wait()
+        # the parameters (hence the averaged gradients of the previous step) are needed from the first kernel that consumes
+        # logits or features; the 11x11 TPS solves in front of it depend on the batch's warp parameters only
+        inner = self.step._inner if self.step.Kp else self.step
+        if inner.fuse_fwd:
+            inner.before_params = self.reducer.wait
+        else:
+            self.reducer.wait()
         return self.step.forward(views, coord, t_vector, l0, l1, feat, conv_V, conv_b)
 
     def wait_grads(self):
@@ -334,13 +354,18 @@ class DataParallelPartStep:
                 C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
                        self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
         after_k4 = self.main_after_k4
-        if not after_k4:
+        split = self.main_split            # (fraction index pieces) e.g. 2: first half beside K4, second half beside K5
+        if split:
+            red.launch(0, part=(0, 2))
+        elif not after_k4:
             red.launch(0)                  # side stream, behind what is queued on the main stream so far
         if st.Kp:   # padded part count: the step's backward is one call (K4 and K5 inside)
             out = st.backward(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
         else:
             out = st.backward_decode(g_inj, g_m0)
-        if after_k4:
+        if split:
+            red.launch(0, part=(1, 2), n_ctas=self.split_ctas)
+        elif after_k4:
             red.launch(0)
         # tail bucket: the encoder tail's gradient needs dfeat (K4)
         if self.standin:

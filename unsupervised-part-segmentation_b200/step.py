@@ -109,6 +109,8 @@ class PartStep:
         # K1 and K3 in one launch (csrc/step_fwd_fused.cu); UPS_FUSE_FWD=0 keeps them as two kernels
         self.fuse_fwd = (self.fused and self.use_tps and not self.Co and K in (8, 16, 32) and F in (16, 32, 64)
                          and os.environ.get("UPS_FUSE_FWD", "1") != "0")
+        self.before_params = None   # optional callable, invoked in forward just before the first kernel that depends on
+        #                             the surrounding model's parameters (logits / features)
         self._labels_u8 = None
         self._views_f32 = None   # allocated on first use: fp32 copy of uint8 views (data.py:134 on the device)
         self._img1 = None
@@ -235,6 +237,8 @@ class PartStep:
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
         assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
         C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
+        if self.before_params is not None:
+            self.before_params()     # data-parallel wrapper: wait for the averaged gradients (the TPS solve needs none)
         C.call("ups_step_warp_decode_fwd", views.data_ptr(), views[2].data_ptr() if V > 2 else None, coord.data_ptr(),
                self.T.data_ptr(), self.warped.data_ptr(), self.warped[2].data_ptr() if V > 2 else None, 2 * B,
                B if V > 2 else 0, S, l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
