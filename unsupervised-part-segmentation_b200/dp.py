@@ -47,16 +47,16 @@ def two_buckets(n_floats):
 
 
 def default_allreduce_ctas(world):
-    """CTAs (128 threads each) of the all-reduce kernel.  With the in-switch reduction of >= 4 ranks 16 CTAs already run
-    at the fabric's rate (profiles/r02d_allreduce_n8.json) and disturb K4 least; two ranks need more loads in flight."""
-    return 16 if world >= 4 else 128
+    """CTAs (128 threads each) of the all-reduce kernel, from the in-step measurements of profiles/r02_tuning.md."""
+    return 16 if world >= 8 else 64 if world >= 4 else 128
 
 
 def default_main_bucket(world):
-    """>= 4 ranks: the main bucket's all-reduce starts before K4 and runs beside K4 and K5 (N=8: 1.600 vs 1.640 ms);
-    2 ranks need 128 CTAs to fill the link, which slows the persistent K4 by 0.16 ms when they share its SMs, so there
-    the all-reduce starts after K4, beside K5 (1.605 vs 1.666 ms).  profiles/r02_tuning.md."""
-    return "before_k4" if world >= 4 else "after_k4"
+    """8 ranks: the main bucket's all-reduce starts before K4 and runs beside K4 and K5 with 16 CTAs (1.600 vs 1.640 ms);
+    2 and 4 ranks need 128 / 64 CTAs to fill the links, which slows the persistent K4 by 0.14-0.16 ms when they share its
+    SMs, so there the all-reduce starts after K4, beside K5 (N=2: 1.605 vs 1.666 ms, N=4: 1.578 vs 1.605 ms).
+    profiles/r02_tuning.md."""
+    return "before_k4" if world >= 8 else "after_k4"
 
 
 def shard_bounds(global_batch, rank, world_size):
