@@ -34,7 +34,8 @@ using namespace tma;
 constexpr int TILE = 128;   // pixels per tile = UMMA M
 constexpr int CO = 32;      // reduction length = one SW128 row
 constexpr int NTC = 32;     // (tap, channel) columns: 27 used
-constexpr int NST = 4;      // TMA stages
+constexpr int MAX_NST = 8;  // TMA stages: as many 16 KB tiles as fit (the kernel is bound by bytes in flight: ncu shows every
+                            // role waiting on mbarriers at 44 % DRAM with 4 stages = 64 KB per SM; TMA latency under load ~3 us)
 constexpr int G_BYTES = TILE * 128;          // 16 KB per tile
 constexpr int B_BYTES = 2 * NTC * 128;       // [V_hi | V_lo] rows
 constexpr int TPB = 576;
@@ -45,7 +46,7 @@ constexpr unsigned FULLM = 0xffffffffu;
 struct Layout {
     int stage0, lo0, b0, ring, red, bar, total;
 };
-__host__ __device__ inline Layout layout(int W) {
+__host__ __device__ inline Layout layout(int W, int NST) {
     Layout L;
     int o = 0;
     L.stage0 = o; o += NST * G_BYTES;
@@ -54,7 +55,7 @@ __host__ __device__ inline Layout layout(int W) {
     L.ring = o;   o += 4 * (W + 2) * 27 * 4;
     o = (o + 15) & ~15;
     L.red = o;    o += 128 * 16;
-    L.bar = o;    o += 256;
+    L.bar = o;    o += 512;
     L.total = o;
     return L;
 }
@@ -64,19 +65,19 @@ __global__ void __launch_bounds__(TPB, 1) parts_conv_bwd_tc_kernel(const __grid_
                                                                  const float* __restrict__ V,
                                                                  float* __restrict__ dm_planes,
                                                                  float* __restrict__ ws_db, int B, int H, int W, int K,
-                                                                 int n_planes) {
+                                                                 int n_planes, int NST) {
     constexpr uint32_t IDESC_32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
-    const Layout L = layout(W);
+    const Layout L = layout(W, NST);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = W / TILE, Wr = W + 2, P = H * W;
     float* sD = reinterpret_cast<float*>(sp + L.ring);     // ring [4][Wr][27]; columns 0 and Wr-1 stay zero
     float* sRed = reinterpret_cast<float*>(sp + L.red);    // [128 splitter threads][4]
-    const uint32_t bar_full = sb + L.bar;                  // [NST]
-    const uint32_t bar_empty = bar_full + 8 * NST;         // [NST]
-    const uint32_t bar_lo_ready = bar_empty + 8 * NST;     // [2]
+    const uint32_t bar_full = sb + L.bar;                  // [MAX_NST]
+    const uint32_t bar_empty = bar_full + 8 * MAX_NST;     // [MAX_NST]
+    const uint32_t bar_lo_ready = bar_empty + 8 * MAX_NST; // [2]
     const uint32_t bar_lo_free = bar_lo_ready + 16;        // [2]
     const uint32_t bar_tm_full = bar_lo_free + 16;         // [2]
     const uint32_t bar_tm_empty = bar_tm_full + 16;        // [2]
@@ -337,7 +338,9 @@ int parts_conv_bwd_tc_launch(const float* g_h, const float* img, const float* V,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("parts_conv_bwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return UPS_E_CUDA; }
-    const pctc::Layout L = pctc::layout(W);
+    int nst = pctc::MAX_NST;
+    while (nst > 2 && (size_t)pctc::layout(W, nst).total + 1024 > 227 * 1024) --nst;
+    const pctc::Layout L = pctc::layout(W, nst);
     const size_t sm = (size_t)L.total + 1024;
     UPS_REQUIRE(sm <= 227 * 1024, "parts_conv_bwd: W=%d needs %zu bytes of shared memory", W, sm);
     static const cudaError_t attr = cudaFuncSetAttribute(pctc::parts_conv_bwd_tc_kernel,
@@ -345,7 +348,7 @@ int parts_conv_bwd_tc_launch(const float* g_h, const float* img, const float* V,
     UPS_CUDA(attr);
     const int n_planes = K * B;
     const int grid = n_planes < NUM_SMS ? n_planes : NUM_SMS;
-    pctc::parts_conv_bwd_tc_kernel<<<grid, pctc::TPB, sm, st>>>(tmap, img, V, dm_planes, ws_db, B, H, W, K, n_planes);
+    pctc::parts_conv_bwd_tc_kernel<<<grid, pctc::TPB, sm, st>>>(tmap, img, V, dm_planes, ws_db, B, H, W, K, n_planes, nst);
     return after_launch("parts_conv_bwd_tc_kernel");
 }
 

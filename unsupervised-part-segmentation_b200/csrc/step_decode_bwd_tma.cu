@@ -23,6 +23,7 @@
 // Hand-offs are mbarriers; tcgen05.commit releases the smem stage, the lo buffer and publishes the
 // accumulator.  dfeat partials are reduced in a fixed order (bit-reproducible run to run).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_helpers.cuh"
@@ -36,9 +37,13 @@ constexpr int CHUNK_TILES = 16;
 constexpr int SPL_WARP0 = 4;
 constexpr unsigned FULLM = 0xffffffffu;
 
-template <int K>
+// DEEP = 1: one more TMA stage and a single lo buffer instead of two.  The kernel is bound by bytes in flight (TMA
+// latency under load is ~3 us: 3 x 32 KB per SM sustain ~32 GB/s per SM of the 44 GB/s the roofline needs); the second lo
+// buffer only lets the splitter run one tile ahead of the MMA, which is not the bottleneck.
+template <int K, int DEEP = 0>
 struct Cfg {
-    static constexpr int NST = (K == 16) ? 3 : 2;
+    static constexpr int NST = ((K == 16) ? 3 : 2) + DEEP;
+    static constexpr int NLO = DEEP ? 1 : 2;
     static constexpr int NSPL = (K == 16) ? 8 : 4;     // splitter warps
     static constexpr int W_TMA = SPL_WARP0 + NSPL, W_MMA = W_TMA + 1;
     static constexpr int TPB = (W_MMA + 1) * 32;
@@ -51,7 +56,7 @@ struct Cfg {
     static constexpr int ACC_BYTES = NSPL * K * F * 4;  // warp-private dfeat accumulators
     static constexpr int STAGE0 = 0;
     static constexpr int LO0 = NST * G_BYTES;
-    static constexpr int B0 = LO0 + 2 * G_BYTES;
+    static constexpr int B0 = LO0 + NLO * G_BYTES;
     static constexpr int DM = B0 + 2 * B_BYTES;
     static constexpr int ACC = DM + DM_BYTES;
     static constexpr int RINFO = ACC + ACC_BYTES;       // 128 rows x (mask, mon)
@@ -120,12 +125,13 @@ struct TileIter {
     }
 };
 
-template <int K>
-__global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
+template <int K, int DEEP>
+__global__ void __launch_bounds__(Cfg<K, DEEP>::TPB, 1) step_decode_bwd_tma_kernel(
     const __grid_constant__ CUtensorMap tmap_g, const float* __restrict__ g_inj, const float* __restrict__ m0,
     const float* __restrict__ g_m0, const float* __restrict__ feat, float* __restrict__ dl0,
     float* __restrict__ partial, unsigned int* __restrict__ chunk_counter, int n_chunks, int splits, int tps) {
-    using L = Cfg<K>;
+    using L = Cfg<K, DEEP>;
+    constexpr int NLO = L::NLO;
     constexpr int NST = L::NST, FK = F + K, NSPL = L::NSPL, W_TMA = L::W_TMA, W_MMA = L::W_MMA;
     constexpr int LPP = K / 4;            // lanes per pixel in the coalesced [px][K] mapping
     constexpr int PW = 32 / LPP;          // pixels per warp pass
@@ -208,11 +214,12 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 if (ti.first_in_chunk() && it > 0) ++chunk_n;
                 const uint32_t bsel = chunk_n & 1;
                 mbar_wait(bar_full + 8 * s, n & 1);
-                mbar_wait(bar_lo_ready + 8 * j, u);
+                const uint32_t jl = NLO == 2 ? j : 0u, ul = NLO == 2 ? u : (it & 1);   // lo buffer and its phase parity
+                mbar_wait(bar_lo_ready + 8 * jl, ul);
                 mbar_wait(bar_tm_empty + 8 * j, u ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + j * (2 * K);
-                const uint32_t a_hi = sb + L::STAGE0 + s * L::G_BYTES, a_lo = sb + L::LO0 + j * L::G_BYTES;
+                const uint32_t a_hi = sb + L::STAGE0 + s * L::G_BYTES, a_lo = sb + L::LO0 + jl * L::G_BYTES;
                 const uint32_t bb = sb + L::B0 + bsel * L::B_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                     umma_tf32(d, sw128_desc(a_lo + ao), bd, IDESC_K, 1u);                   // lo.hi
                 }
                 umma_commit(bar_empty + 8 * s);
-                umma_commit(bar_lo_free + 8 * j);
+                umma_commit(bar_lo_free + 8 * jl);
                 umma_commit(bar_tm_full + 8 * j);
             }
         }
@@ -274,7 +281,8 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 if (c == 0) sts2(rinfo + (p * PW + q) * 8, make_float2(__uint_as_float(mloc), st_value(1.0f, pmax)));
             }
             __syncwarp();
-            mbar_wait(bar_lo_free + 8 * j, u ^ 1);      // MMA of tile it-2 has finished reading LO[j] (and older B buffers)
+            const uint32_t jl = NLO == 2 ? j : 0u, ul = NLO == 2 ? u : (it & 1);
+            mbar_wait(bar_lo_free + 8 * jl, ul ^ 1);    // the MMA of the previous user of this lo buffer has finished (and older B buffers)
             if (first) {
                 // B operand of this chunk: [feat_hi (rows 0..K-1) | feat_lo (rows K..2K-1)], K-major SW128
                 const uint32_t bb = sb + L::B0 + (chunk_n & 1) * L::B_BYTES;
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
                 }
             }
             mbar_wait(bar_full + 8 * s, n & 1);
-            const uint32_t hi_base = sb + L::STAGE0 + s * L::G_BYTES, lo_base = sb + L::LO0 + j * L::G_BYTES;
+            const uint32_t hi_base = sb + L::STAGE0 + s * L::G_BYTES, lo_base = sb + L::LO0 + jl * L::G_BYTES;
             // lane -> floats (2*lane, 2*lane+1) of the row: block lane/16, chunk (lane%16)/2, half lane%2
             const uint32_t lane_off = (lane >> 4) * L::BLK + (lane & 1) * 8;
             const int lch = (lane & 15) >> 1;
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(Cfg<K>::TPB, 1) step_decode_bwd_tma_kernel(
             }
             __syncwarp();                              // rinfo is rewritten by the next tile
             fence_proxy_async();
-            mbar_arrive(bar_lo_ready + 8 * j);
+            mbar_arrive(bar_lo_ready + 8 * jl);
             if (last) {
                 // dfeat partial of this chunk: fixed-order sum over the splitter warps -> workspace
                 asm volatile("bar.sync 1, %0;\n" ::"n"(NSPL * 32) : "memory");
@@ -532,16 +540,18 @@ extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const
     const size_t counter_off = (((size_t)B * splits * K * F * sizeof(float)) + 255) & ~(size_t)255;
     unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + counter_off);
     UPS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-#define UPS_K4(KK)                                                                                                           \
+    static const int deep = []() { const char* e = getenv("UPS_K4_DEEP"); return e ? atoi(e) : 1; }();
+#define UPS_K4(KK, DD)                                                                                                       \
     {                                                                                                                        \
-        const size_t sm = tma::Cfg<KK>::TOTAL + 1024;                                                                        \
-        static const cudaError_t attr = cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<KK>,                            \
+        const size_t sm = tma::Cfg<KK, DD>::TOTAL + 1024;                                                                    \
+        static const cudaError_t attr = cudaFuncSetAttribute(tma::step_decode_bwd_tma_kernel<KK, DD>,                        \
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);          \
         UPS_CUDA(attr);   /* set once per process and kernel instance, not per call */                                       \
-        tma::step_decode_bwd_tma_kernel<KK><<<grid, tma::Cfg<KK>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0, partial,    \
-                                                                              counter, n_chunks, splits, tps);              \
+        tma::step_decode_bwd_tma_kernel<KK, DD><<<grid, tma::Cfg<KK, DD>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0,     \
+                                                                                      partial, counter, n_chunks, splits,   \
+                                                                                      tps);                                 \
     }
-    if (K == 16) UPS_K4(16) else UPS_K4(32)
+    if (K == 16) { if (deep) UPS_K4(16, 1) else UPS_K4(16, 0) } else { if (deep) UPS_K4(32, 1) else UPS_K4(32, 0) }
 #undef UPS_K4
     if (int rc = after_launch("step_decode_bwd_tma_kernel")) return rc;
     const long long n = (long long)B * K * F;
