@@ -34,8 +34,7 @@ using namespace tma;
 constexpr int TILE = 128;   // pixels per tile = UMMA M
 constexpr int CO = 32;      // reduction length = one SW128 row
 constexpr int NTC = 32;     // (tap, channel) columns: 27 used
-constexpr int MAX_NST = 8;  // TMA stages: as many 16 KB tiles as fit (the kernel is bound by bytes in flight: ncu shows every
-                            // role waiting on mbarriers at 44 % DRAM with 4 stages = 64 KB per SM; TMA latency under load ~3 us)
+constexpr int MAX_NST = 4;  // TMA stages of 16 KB (8 stages measured slower: 4.77 vs 4.36 ms for the whole call, profiles/r02_tuning.md)
 constexpr int G_BYTES = TILE * 128;          // 16 KB per tile
 constexpr int B_BYTES = 2 * NTC * 128;       // [V_hi | V_lo] rows
 constexpr int TPB = 576;

@@ -37,9 +37,9 @@ constexpr int CHUNK_TILES = 16;
 constexpr int SPL_WARP0 = 4;
 constexpr unsigned FULLM = 0xffffffffu;
 
-// DEEP = 1: one more TMA stage and a single lo buffer instead of two.  The kernel is bound by bytes in flight (TMA
-// latency under load is ~3 us: 3 x 32 KB per SM sustain ~32 GB/s per SM of the 44 GB/s the roofline needs); the second lo
-// buffer only lets the splitter run one tile ahead of the MMA, which is not the bottleneck.
+// DEEP = 1 (experiment, UPS_K4_DEEP=1): one more TMA stage and a single lo buffer instead of two.  Measured SLOWER
+// (0.519 vs 0.440 ms at CUB B=256): letting the splitter run one tile ahead of the MMA matters more than a fourth tile in
+// flight.  profiles/r02_tuning.md.
 template <int K, int DEEP = 0>
 struct Cfg {
     static constexpr int NST = ((K == 16) ? 3 : 2) + DEEP;
@@ -540,7 +540,7 @@ extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const
     const size_t counter_off = (((size_t)B * splits * K * F * sizeof(float)) + 255) & ~(size_t)255;
     unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + counter_off);
     UPS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-    static const int deep = []() { const char* e = getenv("UPS_K4_DEEP"); return e ? atoi(e) : 1; }();
+    static const int deep = []() { const char* e = getenv("UPS_K4_DEEP"); return e ? atoi(e) : 0; }();
 #define UPS_K4(KK, DD)                                                                                                       \
     {                                                                                                                        \
         const size_t sm = tma::Cfg<KK, DD>::TOTAL + 1024;                                                                    \
