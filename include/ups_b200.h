@@ -316,6 +316,14 @@ int ups_step_encode_fwd_planes(const float* l1, const float* img1, float* m1, fl
 int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
                                const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, int Kpl, void* stream);
 
+/* ups_tps_warp_pair_bwd with the cotangent formed on the fly: sample b of the N warped samples receives
+ * g_out[b] (zeros when g_out is NULL) + extra[b - x0] for b in [x0, x0 + xn); g_out2 / dU2 as in the pair variant (may be
+ * NULL).  The fused step uses it to add the encode side's cotangent of warped view 1 (dimg1) to the caller's g_warped
+ * without materialising the sum; samples whose cotangent is identically zero are skipped. */
+int ups_tps_warp_bwd_sum(const float* g_out, const float* g_out2, const float* extra, int x0, int xn, const float* coord,
+                         const float* T, float* dU, float* dU2, int N, int N2, int H, int W, int C, int out_h, int out_w,
+                         void* stream);
+
 /* K1 + K3 of the fused step in ONE launch (csrc/step_fwd_fused.cu): the TPS warp of the views (ups_tps_warp_pair_fwd's
  * arguments: U [N,S,S,3], optional second image set U2 [N2,S,S,3] sharing the first N2 warps, coord, T -> out, out2) and
  * the decode-side forward (ups_step_decode_fwd's arguments) are independent (model.py:282-311 vs :426-447,482-484);

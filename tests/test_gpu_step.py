@@ -382,3 +382,25 @@ def test_padded_part_count_pitched_inputs_are_zero_copy(ups):
     a.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
     a.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
     assert C.launch_count() == n_pitched + 5, "the contiguous path adds exactly the five pad copies"
+
+
+@pytest.mark.parametrize("V", [3, 2])
+def test_views_grad_without_external_cotangent(ups, V):
+    """views_grad with g_warped = None: only view 1 receives a cotangent (dimg1 from the encode side); K6 forms it on
+    the fly and skips the samples whose cotangent is identically zero."""
+    from ups_b200.step import PartStep
+    B, S, K, F = 2, 64, 16, 64
+    inp = make_inputs(B, S, K, F, V, seed=12, **(dict(tps=PENN_TPS) if V == 2 else {}))
+    c = inp["cot"]
+    cot_o = dict(c, g_warped=[torch.zeros(B, S, S, 3) for _ in range(V)])
+    out_o, grad_o = OS.step_forward_backward([v for v in inp["views"]], inp["coord"], inp["t_vector"], inp["l0"], inp["l1"],
+                                             inp["feat"], cot_o, views_grad=True)
+    r64 = OS.reduction_refs_fp64([v for v in inp["views"]], inp["coord"], inp["t_vector"], out_o, cot_o, views_grad=True)
+    d = cuda(inp)
+    step = PartStep(B, S, K, F, n_views=V, views_grad=True)
+    step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    grad = step.backward(d["cot"]["g_inj"], d["cot"]["g_parts"], d["cot"]["g_pooled"], d["cot"]["g_m0"], d["cot"]["g_m1"], None)
+    torch.cuda.synchronize()
+    for i in range(V):
+        assert_close(grad["dviews"][i], r64["dviews"][i], f"dviews[{i}]", atol=own_error_atol(grad_o["dviews"][i], r64["dviews"][i]))
+    assert float(grad["dviews"][0].abs().max()) == 0.0

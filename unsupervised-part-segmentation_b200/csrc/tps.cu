@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
                                                                 const float* __restrict__ move,
                                                                 const float* __restrict__ scal, float* __restrict__ dU,
                                                                 float* __restrict__ dU2, int N2, int H, int W, int Crt,
-                                                                int oh, int ow) {
+                                                                int oh, int ow, const float* __restrict__ extra, int x0,
+                                                                int xn) {
+    // cotangent of output sample b = g_out[b] (zeros when g_out is null) + extra[b - x0] for b in [x0, x0 + xn): the
+    // fused step adds dimg1 (the encode side's cotangent of warped view 1) to the caller's g_warped here instead of
+    // materialising the sum (model.py:282-311 differentiated)
     __shared__ float sm_const[42];
     extern __shared__ float sm_g[];  // 2 * WARP_TPB * C floats
     const int Cc = (C > 0) ? C : Crt;
@@ -152,14 +156,18 @@ __global__ void __launch_bounds__(WARP_TPB) tps_warp_bwd_kernel(const float* __r
     float* Ub2 = second ? dU2 + (size_t)b * H * W * Cc : nullptr;
     float* sm_g2 = sm_g + WARP_TPB * Cc;
     const bool vec_red = ((reinterpret_cast<uintptr_t>(dU) | reinterpret_cast<uintptr_t>(dU2)) & 7u) == 0;
+    if (g_out == nullptr && !second && !(extra != nullptr && b >= x0 && b < x0 + xn)) return;   // zero cotangent: dU stays 0
     const int tile0 = blockIdx.x * (WARP_TPB * WARP_PPT);
 #pragma unroll 1
     for (int it = 0; it < WARP_PPT; ++it) {
         const int base = tile0 + it * WARP_TPB;
         if (base >= OP) break;
         const int n_live = min(WARP_TPB, OP - base) * Cc;
-        const float* gb = g_out + ((size_t)b * OP + base) * Cc;
-        for (int e = threadIdx.x; e < n_live; e += WARP_TPB) sm_g[e] = __ldcs(gb + e);
+        const bool has_x = extra != nullptr && b >= x0 && b < x0 + xn;
+        const float* gb = g_out ? g_out + ((size_t)b * OP + base) * Cc : nullptr;
+        const float* xb = has_x ? extra + ((size_t)(b - x0) * OP + base) * Cc : nullptr;
+        for (int e = threadIdx.x; e < n_live; e += WARP_TPB)
+            sm_g[e] = (gb ? __ldcs(gb + e) : 0.f) + (xb ? __ldcs(xb + e) : 0.f);
         if (second) {
             const float* gb2 = g_out2 + ((size_t)b * OP + base) * Cc;
             for (int e = threadIdx.x; e < n_live; e += WARP_TPB) sm_g2[e] = __ldcs(gb2 + e);
@@ -299,8 +307,10 @@ static int launch_warp_fwd(const float* U, const float* U2, const float* coord, 
 
 static int launch_warp_bwd(const float* g_out, const float* g_out2, const float* coord, const float* T,
                            const float* move, const float* scal, float* dU, float* dU2, int N, int N2, int H, int W,
-                           int C, int out_h, int out_w, void* stream) {
-    int rc = check_warp_args(g_out, coord, T, move, scal, dU, N, H, W, C, out_h, out_w);
+                           int C, int out_h, int out_w, void* stream, const float* extra = nullptr, int x0 = 0, int xn = 0) {
+    int rc = check_warp_args(g_out ? (const void*)g_out : (const void*)dU, coord, T, move, scal, dU, N, H, W, C, out_h, out_w);
+    UPS_REQUIRE(g_out || extra || g_out2, "tps_warp_bwd: no cotangent at all");
+    UPS_REQUIRE(!extra || (x0 >= 0 && xn >= 0 && x0 + xn <= N), "tps_warp_bwd: extra range [%d, %d) outside [0, %d)", x0, x0 + xn, N);
     if (rc) return rc;
     UPS_REQUIRE((g_out2 == nullptr) == (dU2 == nullptr), "tps_warp_bwd: g_out2 and dU2 must be given together");
     UPS_REQUIRE(N2 >= 0 && N2 <= N, "tps_warp_bwd: N2=%d not in [0, N=%d]", N2, N);
@@ -310,9 +320,9 @@ static int launch_warp_bwd(const float* g_out, const float* g_out2, const float*
     dim3 grid((unsigned)cdiv((long long)out_h * out_w, WARP_TPB * WARP_PPT), (unsigned)N);
     const size_t sm = (size_t)2 * WARP_TPB * C * sizeof(float);
     if (C == 3)
-        tps_warp_bwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w);
+        tps_warp_bwd_kernel<3><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w, extra, x0, xn);
     else
-        tps_warp_bwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w);
+        tps_warp_bwd_kernel<0><<<grid, WARP_TPB, sm, as_stream(stream)>>>(g_out, g_out2, coord, T, move, scal, dU, dU2, N2, H, W, C, out_h, out_w, extra, x0, xn);
     return after_launch("tps_warp_bwd_kernel");
 }
 
@@ -340,4 +350,12 @@ extern "C" int ups_tps_warp_pair_bwd(const float* g_out, const float* g_out2, co
                                      void* stream) {
     UPS_REQUIRE(g_out2 && dU2, "tps_warp_pair_bwd: null pointer");
     return launch_warp_bwd(g_out, g_out2, coord, T, nullptr, nullptr, dU, dU2, N, N2, H, W, C, out_h, out_w, stream);
+}
+
+extern "C" int ups_tps_warp_bwd_sum(const float* g_out, const float* g_out2, const float* extra, int x0, int xn,
+                                    const float* coord, const float* T, float* dU, float* dU2, int N, int N2, int H, int W,
+                                    int C, int out_h, int out_w, void* stream) {
+    UPS_REQUIRE((g_out2 == nullptr) == (dU2 == nullptr), "tps_warp_bwd_sum: g_out2 and dU2 must be given together");
+    return launch_warp_bwd(g_out, g_out2, coord, T, nullptr, nullptr, dU, dU2, N, g_out2 ? N2 : 0, H, W, C, out_h, out_w,
+                           stream, extra, x0, xn);
 }

@@ -100,7 +100,6 @@ class PartStep:
         if self.views_grad:
             self.dimg1 = e(B, S, S, 3, **f32)
             self.dviews = e(max(V, 2), B, S, S, 3, **f32)
-            self.gw = e(max(V, 2), B, S, S, 3, **f32)
         if not self.fused:
             self.mh0, self.mh1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
             self.dm = e(B, S, S, K, **f32)
@@ -400,16 +399,16 @@ class PartStep:
         out = dict(dl1=self.dl1)
         if self.views_grad:
             if self.use_tps:
-                # cotangent of the warped views: g_warped (+ dimg1 on view 1), summed by the library
-                C.call("ups_views_cotangent", p(g_warped), self.dimg1.data_ptr(), self.gw.data_ptr(), max(V, 2), 1,
-                       B * P * 3, st)
-                coord = self._coord
-                if V > 2:
-                    C.call("ups_tps_warp_pair_bwd", self.gw.data_ptr(), self.gw[2].data_ptr(), coord.data_ptr(),
-                           self.T.data_ptr(), self.dviews.data_ptr(), self.dviews[2].data_ptr(), 2 * B, B, S, S, 3, S, S, st)
-                else:
-                    C.call("ups_tps_warp_bwd", self.gw.data_ptr(), coord.data_ptr(), self.T.data_ptr(), None, None,
-                           self.dviews.data_ptr(), 2 * B, S, S, 3, S, S, st)
+                # cotangent of the warped views: g_warped (+ dimg1 on view 1), formed inside K6 (never materialised)
+                coord, gw = self._coord, g_warped
+                if gw is not None:
+                    assert gw.is_contiguous() and tuple(gw.shape) == (max(V, 2), B, S, S, 3), list(gw.shape)
+                pair = V > 2 and gw is not None
+                C.call("ups_tps_warp_bwd_sum", p(gw), gw[2].data_ptr() if pair else None, self.dimg1.data_ptr(), B, B,
+                       coord.data_ptr(), self.T.data_ptr(), self.dviews.data_ptr(),
+                       self.dviews[2].data_ptr() if pair else None, 2 * B, B, S, S, 3, S, S, st)
+                if V > 2 and gw is None:
+                    C.call("ups_views_cotangent", None, None, self.dviews[2].data_ptr(), 1, 0, B * P * 3, st)   # zeros
             else:
                 C.call("ups_views_cotangent", p(g_warped), self.dimg1.data_ptr(), self.dviews.data_ptr(), max(V, 2), 1,
                        B * P * 3, st)
