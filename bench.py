@@ -405,6 +405,14 @@ def run_gpu(args):
             line["n4_first_conv"] = {"shape": n4["shape"], "l2": n4["l2"],
                                      "calls": {k: ({"ms": round(v["ms"], 4), "frac_of_measured_hbm": round(v["frac_of_measured_hbm"], 4)}
                                                    if "ms" in v else v) for k, v in n4["calls"].items()}}
+            del n4
+            torch.cuda.empty_cache()
+            fs = bench_inject_conv.measure_folded_step(B, S, K, iters=5)
+            lib = {k: v["ms"] for k, v in line["n4_first_conv"]["calls"].items() if k.startswith("library")}
+            line["n4_first_conv"]["folded_step"] = dict(
+                fs, library_path_ms_per_step=(rec["ms_per_step"] + sum(lib.values())) if lib else None,
+                library_path="the path step above (inj and parts materialised) + the four cuDNN legs (conv fwd / bwd on "
+                             "injected and on the part images)")
         except Exception as e:  # the N4 leg must never cost the headline line
             line["n4_first_conv"] = {"error": repr(e)[:300]}
     if rank == 0:

@@ -127,6 +127,44 @@ def measure(batch=256, size=128, parts=16, library=True, once=False, iters=10):
                 l2="flushed between timed calls (256 MB read)", calls=res)
 
 
+def measure_folded_step(batch=256, size=128, parts=16, iters=10):
+    """The whole step with BOTH first convolutions folded in (PartStep(first_conv=32, encoder_conv=32)): ms per
+    forward+backward, CUDA events over `iters` steps after 3 warm-up steps."""
+    import torch
+    import ups_b200
+    from ups_b200.configs import CUB_TPS
+    from ups_b200.step import PartStep
+    B, S, K, F, Co = batch, size, parts, 64, 32
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
+    views = torch.rand(3, B, S, S, 3, device=dev, generator=g) * 2 - 1
+    l0, l1, feat = rn(B, S, S, K), rn(B, S, S, K), rn(B, K, F)
+    Vd, bd, Ve, be = rn(3, 3, F + K, Co) * 0.04, rn(Co) * 0.04, rn(3, 3, 3, Co) * 0.2, rn(Co) * 0.2
+    g_h0, g_e0 = rn(B, S, S, Co), rn(K * B, S, S, Co)
+    g_m0, g_m1 = rn(B, S, S, K), rn(B, S, S, K)
+    prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234), device=dev, **CUB_TPS)
+    coord, tv = ups_b200.make_input_tps_param(prm)
+    step = PartStep(B, S, K, F, n_views=3, first_conv=Co, encoder_conv=Co, device=dev)
+
+    def one():
+        step.forward(views, coord, tv, l0, l1, feat, Vd, bd, Ve, be)
+        step.backward(g_h0, g_e0, None, g_m0, g_m1)
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3),
+            "what": "fwd+bwd of the step with the decoder's and the appearance encoder's first 3x3 convolutions computed "
+                    "from the part assignment (h0 and e0 instead of inj and parts)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", default="r01d")

@@ -404,3 +404,53 @@ def test_views_grad_without_external_cotangent(ups, V):
     for i in range(V):
         assert_close(grad["dviews"][i], r64["dviews"][i], f"dviews[{i}]", atol=own_error_atol(grad_o["dviews"][i], r64["dviews"][i]))
     assert float(grad["dviews"][0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,S,K,F,Co,Ce", [(2, 128, 16, 64, 32, 32), (2, 32, 8, 16, 16, 8)])
+def test_first_conv_on_both_sides(ups, B, S, K, F, Co, Ce):
+    """SURVEY.md 8f N4, both halves in one step: the decode side ends in `dd`'s first convolution (h0), the encode side in
+    `e_alpha`'s first convolution on the part images (e0 [K*B,S,S,Ce], model.py:40,478); neither `inj` nor `parts` exists."""
+    import math
+    from oracle import inject_conv as IC
+    from oracle import parts as OP
+    from oracle import parts_conv as PC
+    from oracle import tps as OT
+    from ups_b200.step import PartStep
+    inp = make_inputs(B, S, K, F, 3, seed=Co + Ce)
+    g = torch.Generator().manual_seed(Ce)
+    Vd = (torch.rand(3, 3, F + K, Co, generator=g) * 2 - 1) * math.sqrt(1.0 / ((F + K) * 9))
+    bd = (torch.rand(Co, generator=g) * 2 - 1) * 0.1
+    Ve = (torch.rand(3, 3, 3, Ce, generator=g) * 2 - 1) * math.sqrt(1.0 / 27)
+    be = (torch.rand(Ce, generator=g) * 2 - 1) * 0.1
+    g_h0 = torch.randn(B, S, S, Co, generator=g)
+    g_e0 = torch.randn(K * B, S, S, Ce, generator=g)
+    c = inp["cot"]
+    # oracle
+    warped = OT.make_tps_given([v for v in inp["views"]], inp["coord"], inp["t_vector"])
+    xs = [t.clone().requires_grad_(True) for t in (inp["l0"], inp["l1"], inp["feat"], Vd, bd, Ve, be)]
+    m0_o, m1_o = OP.softmax(xs[0]), OP.softmax(xs[1])
+    h0_o = IC.inject_conv2d(xs[2], OP.hard_max_straight_through(m0_o, 3), xs[3], xs[4])
+    mh1_o = OP.hard_max_straight_through(m1_o, 3)
+    e0_o = PC.parts_conv2d(warped[1], mh1_o, xs[5], xs[6])
+    grads = torch.autograd.grad([h0_o, e0_o, m0_o, m1_o], xs, [g_h0, g_e0, c["g_m0"], c["g_m1"]])
+    # float64 values of the batch-summed filter gradients on the fp32 hard masks
+    x64 = [t.detach().double().requires_grad_(True) for t in (inp["feat"], Vd, bd, Ve, be)]
+    h64 = IC.inject_conv2d(x64[0], OP.hard_max_straight_through(m0_o, 3).detach().double(), x64[1], x64[2])
+    e64 = PC.parts_conv2d(warped[1].double(), mh1_o.detach().double(), x64[3], x64[4])
+    g64 = torch.autograd.grad([h64, e64], x64, [g_h0.double(), g_e0.double()])
+    d = cuda(inp)
+    step = PartStep(B, S, K, F, n_views=3, first_conv=Co, encoder_conv=Ce)
+    out = step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"], Vd.cuda(), bd.cuda(), Ve.cuda(),
+                       be.cuda())
+    grad = step.backward(g_h0.cuda(), g_e0.cuda(), None, d["cot"]["g_m0"], d["cot"]["g_m1"])
+    torch.cuda.synchronize()
+    assert "inj" not in out and "parts" not in out
+    assert_bitexact(out["m1"], m1_o.detach(), "m1")
+    assert_close(out["h0"], h0_o.detach(), "h0")
+    assert_close(out["e0"], e0_o.detach(), "e0")
+    assert_close(grad["dl0"], grads[0], "dl0")
+    assert_close(grad["dl1"], grads[1], "dl1")
+    for name, got, o32, o64 in (("dfeat", grad["dfeat"], grads[2], g64[0]), ("dV", grad["dV"], grads[3], g64[1]),
+                                ("db", grad["db"], grads[4], g64[2]), ("dVe", grad["dVe"], grads[5], g64[3]),
+                                ("dbe", grad["dbe"], grads[6], g64[4])):
+        assert_close(got, o64, name, atol=own_error_atol(o32, o64))

@@ -39,7 +39,7 @@ def _on_device(fn):
 
 class PartStep:
     def __init__(self, batch_size, spatial_size, n_parts, local_app_size=64, n_views=3, use_tps=True,
-                 views_grad=False, device="cuda", decode_bwd="auto", first_conv=0, _planes=None):
+                 views_grad=False, device="cuda", decode_bwd="auto", first_conv=0, encoder_conv=0, _planes=None):
         B, S, K, F, V = int(batch_size), int(spatial_size), int(n_parts), int(local_app_size), int(n_views)
         self.B, self.S, self.K, self.F, self.V = B, S, K, F, V
         self.P = S * S
@@ -59,7 +59,7 @@ class PartStep:
         # probabilities, masks and labels are bit-identical to the K-part evaluation; padding planes of the part images
         # are neither written nor read (csrc: *_planes entry points).  UPS_PAD_K=0 keeps the generic kernels.
         self.Kp = 0
-        if (not self.fused and _planes is None and not first_conv and 1 <= K < 32 and F in (16, 32, 64)
+        if (not self.fused and _planes is None and not first_conv and not encoder_conv and 1 <= K < 32 and F in (16, 32, 64)
                 and self.P % 32 == 0 and os.environ.get("UPS_PAD_K", "1") != "0"):
             self.Kp = 8 if K <= 8 else 16 if K <= 16 else 32
             self._inner = PartStep(B, S, self.Kp, F, n_views=V, use_tps=use_tps, views_grad=views_grad, device=self.device,
@@ -78,7 +78,7 @@ class PartStep:
         self.warped = e(max(V, 2), B, S, S, 3, **f32) if self.use_tps else None
         self.m0, self.m1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
         self.labels0 = e(B, S, S, dtype=torch.int64, device=self.device)
-        self.parts = e(self.Kpl * B, S, S, 3, **f32)
+        self.parts = e(self.Kpl * B, S, S, 3, **f32) if not encoder_conv else None
         self.pooled = e(B, K, 3, **f32)
         # first_conv = Co > 0: the decode side ends in the decoder's first 3x3 convolution (h0 [B,S,S,Co]) instead of
         # the injected map; forward takes the filter (conv_V [3,3,F+K,Co], conv_b [Co]), backward g_h0
@@ -93,6 +93,18 @@ class PartStep:
             self._conv_V = None
         else:
             self.inj = e(B, S, S, F + K, **f32)
+        # encoder_conv = Ce > 0: the encode side ends in the appearance encoder's first 3x3 convolution on the part images
+        # (e0 [K*B,S,S,Ce], model.py:40,478) instead of the part images themselves; forward takes enc_V [3,3,3,Ce] and
+        # enc_b [Ce], backward g_e0 in place of g_parts.  Neither `parts` nor `pooled` is formed
+        self.Ce = int(encoder_conv)
+        if self.Ce:
+            assert not self.views_grad, "encoder_conv: the part images' convolution gives the image no gradient"
+            self.parts = self.pooled = None
+            self.e0 = e(K * B, S, S, self.Ce, **f32)
+            self.mh1c = e(B, S, S, K, **f32)
+            self.dVe, self.dbe = e(3, 3, 3, self.Ce, **f32), e(self.Ce, **f32)
+            self.ws_pc = e(C.parts_conv_bwd_workspace_bytes(B, S, S, K, self.Ce), dtype=torch.uint8, device=self.device)
+            self._enc_V = None
         self.dl0, self.dl1 = e(B, S, S, K, **f32), e(B, S, S, K, **f32)
         self.dfeat = e(B, K, F, **f32)
         nws = C.workspace_bytes(C.OP_STEP, B, self.P, K, F)
@@ -106,7 +118,7 @@ class PartStep:
             self.dm2 = e(B, S, S, K, **f32)
             self.dfm = e(B, S, S, 3, **f32)
         # K1 and K3 in one launch (csrc/step_fwd_fused.cu); UPS_FUSE_FWD=0 keeps them as two kernels
-        self.fuse_fwd = (self.fused and self.use_tps and not self.Co and K in (8, 16, 32) and F in (16, 32, 64)
+        self.fuse_fwd = (self.fused and self.use_tps and not self.Co and not self.Ce and K in (8, 16, 32) and F in (16, 32, 64)
                          and os.environ.get("UPS_FUSE_FWD", "1") != "0")
         self.before_params = None   # optional callable, invoked in forward just before the first kernel that depends on
         #                             the surrounding model's parameters (logits / features)
@@ -210,7 +222,7 @@ class PartStep:
         C.call("ups_inject_conv_fwd", self.mh0c.data_ptr(), self.G.data_ptr(), conv_b.data_ptr(), self.h0.data_ptr(),
                B, S, S, K, self.Co, st)
 
-    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None):
+    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None):
         """views [V,B,S,S,3] (view0, view1[, view0_target]), fp32 in [-1, 1] or the dataset's uint8
         (normalised on the device exactly as cub/code/data/data.py:134 does on the host); coord,
         t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
@@ -225,7 +237,7 @@ class PartStep:
         if self.fuse_fwd:
             return self._forward_fused(views, coord, t_vector, l0, l1, feat)
         self.forward_warp(views, coord, t_vector)
-        return self.forward_parts(l0, l1, feat, conv_V, conv_b)
+        return self.forward_parts(l0, l1, feat, conv_V, conv_b, enc_V, enc_b)
 
     @_on_device
     def _forward_fused(self, views, coord, t_vector, l0, l1, feat):
@@ -296,7 +308,7 @@ class PartStep:
         return self._warped
 
     @_on_device
-    def forward_parts(self, l0, l1, feat, conv_V=None, conv_b=None):
+    def forward_parts(self, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None):
         """K2 (encode side: l1, warped view 1) and K3 (decode side: l0, feat) on the current stream."""
         B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
         st = self._stream()
@@ -310,7 +322,15 @@ class PartStep:
         warped = self._warped
         img1 = warped[1]
         self._img1, self._feat = img1, feat
-        if self.fused:
+        if self.Ce:
+            assert enc_V is not None and enc_b is not None, "encoder_conv: pass enc_V [3,3,3,Ce] and enc_b [Ce]"
+            assert tuple(enc_V.shape) == (3, 3, 3, self.Ce) and tuple(enc_b.shape) == (self.Ce,)
+            assert enc_V.is_contiguous() and enc_b.is_contiguous()
+            self._enc_V = enc_V
+            C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1c.data_ptr(), B * P, K, st)
+            C.call("ups_parts_conv_fwd", img1.data_ptr(), self.mh1c.data_ptr(), enc_V.data_ptr(), enc_b.data_ptr(),
+                   self.e0.data_ptr(), B, S, S, K, 3, self.Ce, st)
+        elif self.fused:
             C.call("ups_step_encode_fwd_planes", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
                    self.pooled.data_ptr(), B, P, K, self.Kpl, self.ws.data_ptr(), self.ws.numel(), st)
         else:
@@ -324,7 +344,11 @@ class PartStep:
             C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
                    self.mh0.data_ptr(), B * P, K, st)
             C.call("ups_part_inject_fwd", feat.data_ptr(), self.mh0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
-        out = dict(warped=warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts, pooled=self.pooled)
+        out = dict(warped=warped, m0=self.m0, m1=self.m1, labels0=self.labels0)
+        if self.Ce:
+            out["e0"] = self.e0
+        else:
+            out["parts"], out["pooled"] = self.parts, self.pooled
         if self.Co:
             out["h0"] = self.h0
         else:
@@ -382,6 +406,12 @@ class PartStep:
         img1 = self._img1
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         want_dimg = self.views_grad
+        if self.Ce:
+            assert tuple(g_parts.shape) == (K * B, S, S, self.Ce), list(g_parts.shape)      # g_e0 in the place of g_parts
+            C.call("ups_parts_conv_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1c.data_ptr(), self._enc_V.data_ptr(),
+                   self.m1.data_ptr(), p(g_m1), self.dl1.data_ptr(), self.dVe.data_ptr(), self.dbe.data_ptr(), B, S, S, K, 3,
+                   self.Ce, self.ws_pc.data_ptr(), self.ws_pc.numel(), st)
+            return dict(dl1=self.dl1, dVe=self.dVe, dbe=self.dbe)
         if self.fused:
             C.call("ups_step_encode_bwd_planes", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
                    p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, self.Kpl, st)
