@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest.log
 tail -4 $O/${TAG}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -2 $O/${TAG}_smoke.log
 timeout 600 python bench.py --steps 100 --warmup 5 > $O/${TAG}_bench_cub.json 2> $O/${TAG}_bench_cub.err
 timeout 600 python bench.py --steps 50 --warmup 5 --workload deepfashion --no-cpu --no-n4 --no-scale-workloads > $O/${TAG}_bench_deepfashion.json 2> $O/${TAG}_bench_df.err
 timeout 600 python bench.py --steps 50 --warmup 5 --workload pennaction --no-cpu --no-n4 --no-scale-workloads > $O/${TAG}_bench_pennaction.json 2> $O/${TAG}_bench_penn.err
