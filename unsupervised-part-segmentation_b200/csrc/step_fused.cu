@@ -53,7 +53,7 @@ struct EncFwdSmem {
 };
 
 // MINB: resident CTAs per SM asked of ptxas (an explicit value also keeps the exp chains interleaved)
-template <int LPP, int MINB>
+template <int LPP, int MINB, bool PAD>
 __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float* __restrict__ l1,
                                                                const float* __restrict__ img1,
                                                                float* __restrict__ m1, float* __restrict__ parts,
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float
             o.y = i4.y * (sft == 2 ? mb : ma);
             o.z = i4.z * (sft >= 1 ? mb : ma);
             o.w = i4.w * mb;
-            if (k < Kpl) st4_stream(parts + (((size_t)k * B + b) * P + pg) * 3 + r0, o);
+            if (!PAD || k < Kpl) st4_stream(parts + (((size_t)k * B + b) * P + pg) * 3 + r0, o);
         }
         // mean pooling (model.py:50-52 tail): lane = pixel, lane-private accumulators
         {
@@ -272,7 +272,7 @@ struct EncBwdSmem {
     static constexpr int WREG = GS + IW + DW + MW;
 };
 
-template <int LPP, bool DIMG>
+template <int LPP, bool DIMG, bool PAD>
 __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __restrict__ g_parts,
                                                                const float* __restrict__ g_pooled,
                                                                const float* __restrict__ img1,
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __re
         // async: K planes x 96 floats of g_parts + 96 floats of the image
         for (int i = lane; i < K * 24; i += 32) {
             const int k = i / 24, q = i - 24 * k;
-            if (k < Kpl) cp_async16(Gs + k * 96 + 4 * q, g_parts + (((size_t)k * B + b) * P + pg) * 3 + 4 * q);
+            if (!PAD || k < Kpl) cp_async16(Gs + k * 96 + 4 * q, g_parts + (((size_t)k * B + b) * P + pg) * 3 + 4 * q);
             else *reinterpret_cast<float4*>(Gs + k * 96 + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (lane < 24) cp_async16(Iw + 4 * lane, img1 + ((size_t)b * P + pg) * 3 + 4 * lane);
@@ -455,8 +455,13 @@ extern "C" int ups_step_encode_fwd_planes(const float* l1, const float* img1, fl
 #define UPS_ENC_FWD2(LPP, MB)                                                                                 \
     {                                                                                                         \
         const size_t sm = (size_t)FW * EncFwdSmem<LPP>::WREG * sizeof(float);                                 \
-        if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB>, sm)) return rc;                                \
-        step_encode_fwd_kernel<LPP, MB><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
+        if (Kpl < K) {                                                                                        \
+            if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB, true>, sm)) return rc;                      \
+            step_encode_fwd_kernel<LPP, MB, true><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
+        } else {                                                                                              \
+            if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB, false>, sm)) return rc;                     \
+            step_encode_fwd_kernel<LPP, MB, false><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
+        }                                                                                                     \
     }
 #define UPS_ENC_FWD(LPP) \
     { if (minb == 4) UPS_ENC_FWD2(LPP, 4) else if (minb == 5) UPS_ENC_FWD2(LPP, 5) else UPS_ENC_FWD2(LPP, 6) }
@@ -519,18 +524,19 @@ extern "C" int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* 
     const int per = fused_pix_per_cta(B, P);
     dim3 grid((unsigned)cdiv(P, per), B);
     cudaStream_t s = as_stream(stream);
+#define UPS_ENC_BWD3(LPP, DI, PD)                                                                                     \
+    {                                                                                                                 \
+        if (int rc = set_smem(step_encode_bwd_kernel<LPP, DI, PD>, sm)) return rc;                                    \
+        step_encode_bwd_kernel<LPP, DI, PD><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
+    }
 #define UPS_ENC_BWD(LPP)                                                                                              \
     {                                                                                                                 \
         const size_t sm = ((size_t)FW * EncBwdSmem<LPP>::WREG + 4 * LPP * 3 + 4) * sizeof(float);                     \
-        if (dimg1) {                                                                                                  \
-            if (int rc = set_smem(step_encode_bwd_kernel<LPP, true>, sm)) return rc;                                  \
-            step_encode_bwd_kernel<LPP, true><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
-        } else {                                                                                                      \
-            if (int rc = set_smem(step_encode_bwd_kernel<LPP, false>, sm)) return rc;                                 \
-            step_encode_bwd_kernel<LPP, false><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
-        }                                                                                                             \
+        if (dimg1) { if (Kpl < K) UPS_ENC_BWD3(LPP, true, true) else UPS_ENC_BWD3(LPP, true, false) }                 \
+        else { if (Kpl < K) UPS_ENC_BWD3(LPP, false, true) else UPS_ENC_BWD3(LPP, false, false) }                     \
     }
     if (K == 4) UPS_ENC_BWD(1) else if (K == 8) UPS_ENC_BWD(2) else if (K == 16) UPS_ENC_BWD(4) else UPS_ENC_BWD(8)
 #undef UPS_ENC_BWD
+#undef UPS_ENC_BWD3
     return after_launch("step_encode_bwd_kernel");
 }
