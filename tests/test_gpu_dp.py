@@ -114,9 +114,8 @@ def test_dp_world1_equals_partstep_and_holds_standin_grads():
     t64 = OSI.tail_grads(o_ref["pooled"].cpu(), g_ref["dfeat"].cpu(), dp.mod.Wlin.cpu(), dp.mod.blin.cpu())
     assert_close(dp.grads_tail, t64, "grads_tail", atol=1e-4)
     used = dp.grads.clone()
-    used[:dp.mod.n_head] = 0
-    n_dec = dp.reducer.bounds[1][0]
-    used[n_dec:n_dec + dp.mod.n_tail] = 0
+    used[dp.head_off:dp.head_off + dp.mod.n_head] = 0
+    used[dp.tail_off:dp.tail_off + dp.mod.n_tail] = 0
     assert float(used.abs().max()) == 0.0, "the padding of the gradient buffer stays zero"
 
 
@@ -196,12 +195,11 @@ def _t4_worker(rank, world, port, q, allreduce):
         from ups_b200 import _cabi as C
         mine = pad.clone()
         st = torch.cuda.current_stream(dev).cuda_stream
-        n_dec = dp.reducer.bounds[1][0]
         ws = torch.empty(C.lib.ups_standin_workspace_bytes(Bl, S * S, K, F), dtype=torch.uint8, device=dev)
         C.call("ups_standin_head_bwd", loc["g_recon"].data_ptr(), out["labels0"].data_ptr(), loc["feat"].data_ptr(),
-               mine[:dp.mod.n_head].data_ptr(), Bl, S * S, K, F, ws.data_ptr(), ws.numel(), st)
+               mine[dp.head_off:dp.head_off + dp.mod.n_head].data_ptr(), Bl, S * S, K, F, ws.data_ptr(), ws.numel(), st)
         C.call("ups_standin_tail_bwd", out["pooled"].data_ptr(), grad["dfeat"].data_ptr(),
-               mine[n_dec:n_dec + dp.mod.n_tail].data_ptr(), Bl, K, 3, F, ws.data_ptr(), ws.numel(), st)
+               mine[dp.tail_off:dp.tail_off + dp.mod.n_tail].data_ptr(), Bl, K, 3, F, ws.data_ptr(), ws.numel(), st)
         gathered = [torch.empty_like(mine) for _ in range(w)]
         dist.all_gather(gathered, mine)
         want = torch.stack(gathered).double().mean(0)

@@ -20,10 +20,10 @@ How the collective is done here
   writes the peers' buffers directly.  If symmetric memory is not available at all the wrapper
   falls back to `ncclAllReduce(SUM)` and hands the consumer the scale (`grad_scale`).
 * Two buckets, launched where their producers finish (the reduction overlaps K4-K6):
-    main bucket — the stand-in decoder head's gradient and all the padding — at the top of backward (everything a
-    decoder-side module contributes exists before the path's backward starts), overlapped with K4 and K5;
-    tail bucket — the stand-in encoder tail's gradient (1024 floats), which needs K4's dfeat — after K4,
-    overlapped with K5/K6.
+    main bucket — the padding that stands for the 33 M parameters of the CNNs this repo does not contain — from the top
+    of backward, overlapped with K4 and K5;
+    small bucket (1024 floats) — the stand-in modules' real gradients: the decoder head's (computed in front of K4) and
+    the encoder tail's (needs K4's dfeat) — after K4, overlapped with K5/K6.
   The next forward (`forward`) waits for both before its first kernel; `wait_grads()` for whoever consumes them earlier.
 * The stand-in gradient kernels (~25 us) run on the main stream in front of K4 / K5; the all-reduce kernels run on the
   reducer's high-priority side stream beside K4 and K5.
@@ -313,12 +313,17 @@ class DataParallelPartStep:
             n = (max(int(n_grad_params), 4 * TAIL_BUCKET_FLOATS) + 3) // 4 * 4
             reducer = GradAllReducer(n, dev, buckets=two_buckets(n), impl=allreduce,
                                      n_ctas=allreduce_ctas or default_allreduce_ctas(self.world))
-        assert len(reducer.bounds) == 2 and reducer.bounds[0][1] >= self.mod.n_head and reducer.bounds[1][1] >= self.mod.n_tail
+        assert len(reducer.bounds) == 2
         n_dec = reducer.bounds[1][0]
         self.reducer = reducer
         self.grads = self.reducer.flat
-        self.grads_head = self.grads[:self.mod.n_head]                     # [dWhead ((F+K)*3), dbhead (3)]
-        self.grads_tail = self.grads[n_dec:n_dec + self.mod.n_tail]        # [dWlin (3*F), dblin (F)]
+        # both stand-in gradients live in the small bucket (reduced after K4, when the tail's gradient exists); the main
+        # bucket is padding only, so its all-reduce starts at the very top of backward, beside the head's gradient kernels
+        self.tail_off = n_dec
+        self.head_off = n_dec + (self.mod.n_tail + 3) // 4 * 4
+        assert self.head_off + self.mod.n_head <= n_dec + reducer.bounds[1][1], "stand-in gradients exceed the small bucket"
+        self.grads_tail = self.grads[self.tail_off:self.tail_off + self.mod.n_tail]        # [dWlin (3*F), dblin (F)]
+        self.grads_head = self.grads[self.head_off:self.head_off + self.mod.n_head]        # [dWhead ((F+K)*3), dbhead (3)]
         B, P = self.step.B, self.step.P
         self._ws = torch.empty(max(int(C.lib.ups_standin_workspace_bytes(B, P, K, F)), 16), dtype=torch.uint8, device=dev)
         self._ev = torch.cuda.Event()
@@ -346,19 +351,20 @@ class DataParallelPartStep:
         dev = st.device
         B, P, K, F = st.B, st.P, st.K, st.F
         main = torch.cuda.current_stream(dev)
-        # main bucket: everything a decoder-side module contributes exists before the path's backward starts.  The
-        # stand-in gradient kernels run on the MAIN stream, in front of K4 (~25 us): on a side stream they shared the SMs
-        # with the persistent K4 grid, took ten times as long and held the all-reduce behind them (profiles/r02_tuning.md)
-        if g_recon is not None and self.standin:
-            with torch.cuda.device(dev):
-                C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
-                       self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
+        # main bucket (padding for the 33 M parameters of the CNNs that are not here): reducible from the top of backward.
         after_k4 = self.main_after_k4
-        split = self.main_split            # (fraction index pieces) e.g. 2: first half beside K4, second half beside K5
+        split = self.main_split            # experiment knob: first half beside K4, second half beside K5
         if split:
             red.launch(0, part=(0, 2))
         elif not after_k4:
             red.launch(0)                  # side stream, behind what is queued on the main stream so far
+        # the stand-in head's gradient (decoder side: exists before the path's backward).  The stand-in kernels run on
+        # the MAIN stream (~35 us): on a side stream they shared the SMs with the persistent K4 grid, took ten times as
+        # long and held the all-reduce behind them (profiles/r02_tuning.md)
+        if g_recon is not None and self.standin:
+            with torch.cuda.device(dev):
+                C.call("ups_standin_head_bwd", g_recon.data_ptr(), st.labels0.data_ptr(), st._feat.data_ptr(),
+                       self.grads_head.data_ptr(), B, P, K, F, self._ws.data_ptr(), self._ws.numel(), main.cuda_stream)
         if st.Kp:   # padded part count: the step's backward is one call (K4 and K5 inside)
             out = st.backward(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
         else:
