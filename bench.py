@@ -226,7 +226,10 @@ def measure_workload(args, torch, dist, ups_b200, name, B, dev, rank, world, red
     Returns (record, dp, tensors); `detailed` adds per-call CUDA events and the launch count."""
     from ups_b200 import _cabi as C
     from ups_b200.dp import DataParallelPartStep
-    wl = WORKLOADS[name]
+    wl = dict(WORKLOADS[name])
+    if args.n_parts:
+        wl["K"] = args.n_parts
+        wl["desc"] = wl["desc"].replace("K=16", "K=%d" % args.n_parts)
     S, K, F, V = wl["S"], wl["K"], wl["F"], wl["V"]
     P = S * S
     dp = DataParallelPartStep(B, S, K, F, n_views=V, use_tps=wl["use_tps"], views_grad=args.tps_bwd, device=dev,
@@ -327,7 +330,10 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if cores:
         torch.set_num_threads(max(1, min(len(cores), 8)))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.n_parts:
+        wl["K"] = args.n_parts
+        wl["desc"] = wl["desc"].replace("K=16", "K=%d" % args.n_parts)
     S, K, F, V, B = wl["S"], wl["K"], wl["F"], wl["V"], args.batch or wl["B"]
     # one flat gradient buffer (symmetric memory when N>1) shared by every workload measured in this process
     n_grad = (int(args.grad_mb * 1e6 / 4) + 3) // 4 * 4
@@ -541,6 +547,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cub", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--n-parts", type=int, default=0, help="part count override (e.g. 25, the reference's shipped n_parts)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tps-bwd", action="store_true", help="also back-propagate into the input views (K6)")
     ap.add_argument("--decode-bwd", default="auto", choices=["auto", "tc", "simt"],

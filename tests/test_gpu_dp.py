@@ -252,3 +252,44 @@ def test_t4_two_ranks_sharded_step_and_allreduce(allreduce):
         if allreduce == "nccl":
             assert res[r]["transport"] == "nccl"
     print("T4 transports:", {r: (res[r]["transport"], res[r]["fallback_reason"]) for r in range(2)})
+
+
+def test_dp_world1_padded_part_count():
+    """The data-parallel wrapper with the reference's shipped n_parts = 25 (padded to 32 inside PartStep): same outputs as
+    the plain step, stand-in gradients against the oracle."""
+    from ups_b200.dp import DataParallelPartStep
+    from ups_b200.step import PartStep
+    B, S, K, F, V = 3, 64, 25, 64, 3
+    inp = make_inputs(B, S, K, F, V, seed=4)
+    d = cuda(inp)
+    c = d["cot"]
+    ref = PartStep(B, S, K, F, n_views=V)
+    assert ref.Kp == 32
+    o_ref = ref.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    g_ref = ref.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
+    dp = DataParallelPartStep(B, S, K, F, n_views=V, n_grad_params=100_000, standin=True)
+    g_recon = torch.randn(B, S, S, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    for _ in range(2):
+        o = dp.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+        g = dp.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"], g_recon=g_recon)
+    dp.wait_grads()
+    torch.cuda.synchronize()
+    for k in ("m0", "m1", "labels0", "parts", "pooled", "inj"):
+        assert torch.equal(o[k], o_ref[k]), k
+    for k in ("dl0", "dl1", "dfeat"):
+        assert torch.equal(g[k], g_ref[k]), k
+    h64 = OSI.head_grads(g_recon.cpu(), o_ref["labels0"].cpu(), inp["feat"], dp.mod.Whead.cpu(), dp.mod.bhead.cpu())
+    assert_close(dp.grads_head, h64, "grads_head", atol=1e-4)
+    t64 = OSI.tail_grads(o_ref["pooled"].cpu(), g_ref["dfeat"].cpu(), dp.mod.Wlin.cpu(), dp.mod.blin.cpu())
+    assert_close(dp.grads_tail, t64, "grads_tail", atol=1e-4)
+
+
+def test_path_config_presets_make_steps():
+    """configs.PathConfig: the reference's config keys (train_cub_subset_tps.yaml:19-20,132,139,187-194) -> a PartStep."""
+    from ups_b200.configs import CUB_SHIPPED, PathConfig
+    cfg = PathConfig.from_dict(dict(CUB_SHIPPED.to_dict(), batch_size=2, spatial_size=64, unknown_key=1))
+    step = cfg.make_step()
+    assert (step.B, step.S, step.K, step.F, step.V) == (2, 64, 25, 64, 3) and step.Kp == 32
+    d = cuda(make_inputs(2, 64, 25, 64, 3, seed=1))
+    out = step.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
+    assert out["m0"].shape == (2, 64, 64, 25) and out["labels0"].max().item() < 25
