@@ -324,6 +324,25 @@ int ups_tps_warp_bwd_sum(const float* g_out, const float* g_out2, const float* e
                          const float* T, float* dU, float* dU2, int N, int N2, int H, int W, int C, int out_h, int out_w,
                          void* stream);
 
+/* The same kernels with an explicit ROW LENGTH (in floats) for the one [.,K]-shaped input each of them can read in place when
+ * K is a padded part count: l0 (decode forward), l1 (encode forward), g_m0 (decode backward), g_m1 (encode backward).
+ * row == K is the ordinary call; row < K (e.g. 25 for K = 32) reads the caller's contiguous [., row] tensor element-wise
+ * (parts >= row are -inf for logits, 0 for cotangents) and saves the padded copy.  All other tensors keep K-float rows. */
+int ups_step_decode_fwd_rows(const float* l0, int l0_row, const float* feat, float* m0, long long* labels0, float* inj, int B,
+                             int P, int K, int F, void* stream);
+int ups_step_encode_fwd_rows(const float* l1, int l1_row, const float* img1, float* m1, float* parts_pm, float* pooled, int B,
+                             int P, int K, int Kpl, void* ws, size_t ws_bytes, void* stream);
+int ups_step_decode_bwd_rows(const float* g_inj, const float* m0, const float* g_m0, int gm_row, const float* feat, float* dl0,
+                             float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+int ups_step_decode_bwd_tc_rows(const float* g_inj, const float* m0, const float* g_m0, int gm_row, const float* feat,
+                                float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes, void* stream);
+int ups_step_encode_bwd_rows(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
+                             const float* g_m1, int gm_row, float* dl1, float* dimg1, int B, int P, int K, int Kpl,
+                             void* stream);
+int ups_step_warp_decode_fwd_rows(const float* U, const float* U2, const float* coord, const float* T, float* out, float* out2,
+                                  int N, int N2, int S, const float* l0, int l0_row, const float* feat, float* m0,
+                                  long long* labels0, float* inj, int B, int K, int F, void* stream);
+
 /* K1 + K3 of the fused step in ONE launch (csrc/step_fwd_fused.cu): the TPS warp of the views (ups_tps_warp_pair_fwd's
  * arguments: U [N,S,S,3], optional second image set U2 [N2,S,S,3] sharing the first N2 warps, coord, T -> out, out2) and
  * the decode-side forward (ups_step_decode_fwd's arguments) are independent (model.py:282-311 vs :426-447,482-484);

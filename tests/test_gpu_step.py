@@ -355,7 +355,7 @@ def test_full_size_pennaction_b512_slice_equality(ups):
 
 def test_padded_part_count_pitched_inputs_are_zero_copy(ups):
     """A producer that writes logits / cotangents into PartStep.pitched_inputs() (row pitch Kp floats) gets the same bits
-    as the contiguous-tensor path, without the pad copies."""
+    as the contiguous-tensor path (whose kernels read the ragged rows in place), without the one pad copy left."""
     from ups_b200 import _cabi as C
     from ups_b200.step import PartStep
     B, S, K, F, V = 3, 64, 25, 64, 3
@@ -381,7 +381,9 @@ def test_padded_part_count_pitched_inputs_are_zero_copy(ups):
     C.launch_count_reset()
     a.forward(d["views"], d["coord"], d["t_vector"], d["l0"], d["l1"], d["feat"])
     a.backward(c["g_inj"], c["g_parts"], c["g_pooled"], c["g_m0"], c["g_m1"])
-    assert C.launch_count() == n_pitched + 5, "the contiguous path adds exactly the five pad copies"
+    # contiguous [.,K] logits and mask cotangents are read in place (row length K); only g_inj is re-pitched, because
+    # the TMA tensor map of the decode backward needs a 16-byte row pitch
+    assert C.launch_count() == n_pitched + 1, "the contiguous path adds exactly one pad copy (g_inj)"
 
 
 @pytest.mark.parametrize("V", [3, 2])

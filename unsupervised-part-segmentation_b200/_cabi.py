@@ -71,6 +71,12 @@ _SIGS = {
     "ups_step_encode_fwd_planes": [c_f] * 5 + [c_i] * 4 + [c_f, c_sz, c_f],
     "ups_step_encode_bwd_planes": [c_f] * 7 + [c_i] * 4 + [c_f],
     "ups_tps_warp_bwd_sum": [c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f],
+    "ups_step_decode_fwd_rows": [c_f, c_i] + [c_f] * 4 + [c_i] * 4 + [c_f],
+    "ups_step_encode_fwd_rows": [c_f, c_i] + [c_f] * 4 + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_step_decode_bwd_rows": [c_f, c_f, c_f, c_i, c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_step_decode_bwd_tc_rows": [c_f, c_f, c_f, c_i, c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_sz, c_f],
+    "ups_step_encode_bwd_rows": [c_f] * 5 + [c_i] + [c_f] * 2 + [c_i] * 4 + [c_f],
+    "ups_step_warp_decode_fwd_rows": [c_f] * 6 + [c_i] * 3 + [c_f, c_i] + [c_f] * 4 + [c_i] * 3 + [c_f],
     "ups_draw_rect_fwd": [c_f, c_f] + [c_i] * 5 + [c_f],
     "ups_step_warp_decode_fwd": [c_f] * 6 + [c_i] * 3 + [c_f] * 5 + [c_i] * 3 + [c_f],
     "ups_dp_allreduce": [c_f, c_f, c_f, c_i, c_i, c_ll, c_fl, c_i, c_f],

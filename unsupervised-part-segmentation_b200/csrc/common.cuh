@@ -63,6 +63,22 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(rei
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
+// Parts 4c .. 4c+3 of pixel `pix` from a row-major [., row] tensor, for the kernels that work on K = 4*LPP lanes: row == K
+// is the ordinary 16-byte load; a shorter row (a part count that is not a power of two, read in place instead of through
+// a padded copy) is read element-wise, parts >= row come back as `pad`.
+template <int LPP>
+__device__ __forceinline__ float4 ld_row4(const float* __restrict__ base, size_t pix, int c, int row, float pad) {
+    if (row == 4 * LPP) return ld4_stream(base + (pix * LPP + c) * 4);
+    const float* p = base + pix * (size_t)row + 4 * c;
+    const int k0 = 4 * c;
+    float4 v;
+    v.x = k0 < row ? __ldcs(p) : pad;
+    v.y = k0 + 1 < row ? __ldcs(p + 1) : pad;
+    v.z = k0 + 2 < row ? __ldcs(p + 2) : pad;
+    v.w = k0 + 3 < row ? __ldcs(p + 3) : pad;
+    return v;
+}
+
 template <int W>
 __device__ __forceinline__ float group_max(float v) {
 #pragma unroll

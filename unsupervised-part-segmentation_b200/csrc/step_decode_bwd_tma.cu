@@ -129,7 +129,7 @@ template <int K, int DEEP>
 __global__ void __launch_bounds__(Cfg<K, DEEP>::TPB, 1) step_decode_bwd_tma_kernel(
     const __grid_constant__ CUtensorMap tmap_g, const float* __restrict__ g_inj, const float* __restrict__ m0,
     const float* __restrict__ g_m0, const float* __restrict__ feat, float* __restrict__ dl0,
-    float* __restrict__ partial, unsigned int* __restrict__ chunk_counter, int n_chunks, int splits, int tps) {
+    float* __restrict__ partial, unsigned int* __restrict__ chunk_counter, int n_chunks, int splits, int tps, int gm_row) {
     using L = Cfg<K, DEEP>;
     constexpr int NLO = L::NLO;
     constexpr int NST = L::NST, FK = F + K, NSPL = L::NSPL, W_TMA = L::W_TMA, W_MMA = L::W_MMA;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(Cfg<K, DEEP>::TPB, 1) step_decode_bwd_tma_kern
             for (int p = 0; p < NPASS; ++p) {
                 const size_t r = (size_t)row0 + warp * 32 + p * PW + q;
                 p4[p] = ld4_stream(m0 + r * K + 4 * c);
-                gm4[p] = g_m0 ? ld4_stream(g_m0 + r * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                gm4[p] = g_m0 ? ld_row4<LPP>(g_m0, r, c, gm_row, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tl4[p] = ld4_stream(g_inj + r * FK + F + 4 * c);
             }
         };
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(Cfg<K, DEEP>::TPB, 1) step_decode_bwd_tma_kern
                 if (more) {
                     const size_t rn = (size_t)row0n + r;
                     p4[p] = ld4_stream(m0 + rn * K + 4 * c);
-                    gm4[p] = g_m0 ? ld4_stream(g_m0 + rn * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gm4[p] = g_m0 ? ld_row4<LPP>(g_m0, rn, c, gm_row, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
                     tl4[p] = ld4_stream(g_inj + rn * FK + F + 4 * c);
                 }
             }
@@ -508,13 +508,20 @@ using namespace ups;
 extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const float* g_m0, const float* feat,
                                       float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes,
                                       void* stream) {
+    return ups_step_decode_bwd_tc_rows(g_inj, m0, g_m0, K, feat, dl0, dfeat, B, P, K, F, ws, ws_bytes, stream);
+}
+
+extern "C" int ups_step_decode_bwd_tc_rows(const float* g_inj, const float* m0, const float* g_m0, int gm_row, const float* feat,
+                                           float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes,
+                                           void* stream) {
     UPS_REQUIRE(g_inj && m0 && feat && dl0 && dfeat, "step_decode_bwd_tc: null pointer");
+    UPS_REQUIRE(gm_row >= 1 && gm_row <= K, "step_decode_bwd_tc: g_m0 rows of %d floats for K=%d", gm_row, K);
     UPS_REQUIRE(B >= 0 && B <= 65535, "step_decode_bwd_tc: B=%d out of range", B);
     UPS_REQUIRE(K == 16 || K == 32, "step_decode_bwd_tc: tensor-core path needs K in {16,32}, got %d", K);
     UPS_REQUIRE(F == 64, "step_decode_bwd_tc: tensor-core path needs F == 64, got %d", F);
     UPS_REQUIRE(P >= 128 && P % 128 == 0, "step_decode_bwd_tc: tensor-core path needs P %% 128 == 0, got %d", P);
     UPS_REQUIRE((long long)B * P < (1ll << 31), "step_decode_bwd_tc: B*P=%lld rows exceed the TMA coordinate range", (long long)B * P);
-    UPS_REQUIRE(aligned16(g_inj) && aligned16(m0) && aligned16(feat) && aligned16(dl0) && (!g_m0 || aligned16(g_m0)),
+    UPS_REQUIRE(aligned16(g_inj) && aligned16(m0) && aligned16(feat) && aligned16(dl0) && (!g_m0 || gm_row < K || aligned16(g_m0)),
                 "step_decode_bwd_tc: 16-byte alignment");
     if (B == 0) return UPS_OK;
     const int tps = P / tma::TILE;
@@ -556,7 +563,7 @@ extern "C" int ups_step_decode_bwd_tc(const float* g_inj, const float* m0, const
         UPS_CUDA(attr);   /* set once per process and kernel instance, not per call */                                       \
         tma::step_decode_bwd_tma_kernel<KK, DD><<<grid, tma::Cfg<KK, DD>::TPB, sm, s>>>(tmap, g_inj, m0, g_m0, feat, dl0,     \
                                                                                       partial, counter, n_chunks, splits,   \
-                                                                                      tps);                                 \
+                                                                                      tps, gm_row);                         \
     }
     if (K == 16) { if (deep) UPS_K4(16, 1) else UPS_K4(16, 0) } else { if (deep) UPS_K4(32, 1) else UPS_K4(32, 0) }
 #undef UPS_K4

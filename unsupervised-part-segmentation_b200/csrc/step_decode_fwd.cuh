@@ -42,7 +42,8 @@ template <int LPP, int FT>
 __device__ __forceinline__ void step_decode_fwd_body(const float* __restrict__ l0, const float* __restrict__ feat,
                                                      float* __restrict__ m0, long long* __restrict__ labels0,
                                                      float* __restrict__ inj, int P, int Frt, int pix_per_cta, int split,
-                                                     int b, float4* fs4) {
+                                                     int b, float4* fs4, int l0_row) {
+    // l0_row: row length of l0 in floats (K, or the real part count when the logits of a padded K are read in place)
     constexpr int K = 4 * LPP, PW = 32 / LPP;
     const int F = FT > 0 ? FT : Frt;
     const int NF4 = F >> 2, FK = F + K;
@@ -56,7 +57,7 @@ __device__ __forceinline__ void step_decode_fwd_body(const float* __restrict__ l
         float4 v[LPP];
 #pragma unroll
         for (int s = 0; s < LPP; ++s)
-            v[s] = ld4_stream(l0 + (((size_t)b * P + pg + s * PW + plq) * LPP + c) * 4);
+            v[s] = ld_row4<LPP>(l0, (size_t)b * P + pg + s * PW + plq, c, l0_row, -INFINITY);
 #pragma unroll
         for (int s = 0; s < LPP; ++s) {
             const size_t pix = (size_t)b * P + pg + s * PW + plq;

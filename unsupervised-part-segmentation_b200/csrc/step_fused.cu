@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(FTPB) step_decode_fwd_kernel(const float* __re
                                                                float* __restrict__ m0,
                                                                long long* __restrict__ labels0,
                                                                float* __restrict__ inj, int P, int Frt,
-                                                               int pix_per_cta) {
+                                                               int pix_per_cta, int l0_row) {
     extern __shared__ float4 fs4[];  // feat[b] as [K][F/4] float4
-    step_decode_fwd_body<LPP, FT>(l0, feat, m0, labels0, inj, P, Frt, pix_per_cta, blockIdx.x, blockIdx.y, fs4);
+    step_decode_fwd_body<LPP, FT>(l0, feat, m0, labels0, inj, P, Frt, pix_per_cta, blockIdx.x, blockIdx.y, fs4, l0_row);
 }
 
 // ============================================================================ K2 encode fwd
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float
                                                                const float* __restrict__ img1,
                                                                float* __restrict__ m1, float* __restrict__ parts,
                                                                float* __restrict__ partial, int B, int P,
-                                                               int pix_per_cta, int Kpl) {
+                                                               int pix_per_cta, int Kpl, int l1_row) {
     // Kpl <= K: number of part planes that exist in `parts` (planes Kpl..K-1 are padding of a K that is not a power
     // of two: their mask is identically zero and they are neither written nor allocated)
     using L = EncFwdSmem<LPP>;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(FTPB, MINB) step_encode_fwd_kernel(const float
         float4 v[LPP];
 #pragma unroll
         for (int s = 0; s < LPP; ++s)
-            v[s] = ld4_stream(l1 + (((size_t)b * P + pg + s * PW + plq) * LPP + c) * 4);
+            v[s] = ld_row4<LPP>(l1, (size_t)b * P + pg + s * PW + plq, c, l1_row, -INFINITY);
         if (lane < 24) st4(Iw + 4 * lane, ld4(img1 + ((size_t)b * P + pg) * 3 + 4 * lane));
 #pragma unroll
         for (int s = 0; s < LPP; ++s) {
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(FTPB) step_decode_bwd_kernel(const float* __re
                                                                const float* __restrict__ g_m0,
                                                                const float* __restrict__ feat,
                                                                float* __restrict__ dl0, float* __restrict__ partial,
-                                                               int P, int pix_per_cta) {
+                                                               int P, int pix_per_cta, int gm_row) {
     using L = DecBwdSmem<K, F>;
     constexpr int PPW = L::PPW, FK = L::FK, NF4 = L::NF4, GROUPS = L::GROUPS, NST = L::NST;
     constexpr int ROW4 = FK / 4, STAGE4 = PPW * ROW4;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(FTPB) step_decode_bwd_kernel(const float* __re
     if (n_steps > 0) {
         const size_t o = ((size_t)b * P + first) * K + lane;
         pr_n = __ldcs(m0 + o);
-        gm_n = g_m0 ? __ldcs(g_m0 + o) : 0.f;
+        gm_n = (g_m0 && k < gm_row) ? __ldcs(g_m0 + ((size_t)b * P + first + pl) * gm_row + k) : 0.f;
     }
     __syncwarp();
     for (int j = 0; j < n_steps; ++j) {
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(FTPB) step_decode_bwd_kernel(const float* __re
         if (j + 1 < n_steps) {
             const size_t on = o + (size_t)FW * PPW * K;
             pr_n = __ldcs(m0 + on);
-            gm_n = g_m0 ? __ldcs(g_m0 + on) : 0.f;
+            gm_n = (g_m0 && k < gm_row)
+                       ? __ldcs(g_m0 + ((size_t)b * P + first + (size_t)(j + 1) * FW * PPW + pl) * gm_row + k) : 0.f;
         }
         cp_async_wait<NST - 1>();
         __syncwarp();
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __re
                                                                const float* __restrict__ m1,
                                                                const float* __restrict__ g_m1,
                                                                float* __restrict__ dl1, float* __restrict__ dimg1,
-                                                               int B, int P, int pix_per_cta, int Kpl) {
+                                                               int B, int P, int pix_per_cta, int Kpl, int gm_row) {
     // Kpl <= K: planes of g_parts that exist (see step_encode_fwd_kernel); the cotangent of a padding plane is zero
     using L = EncBwdSmem<LPP>;
     constexpr int K = L::K, PW = 32 / LPP;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(FTPB) step_encode_bwd_kernel(const float* __re
         for (int s = 0; s < LPP; ++s) {
             const size_t gi = ((size_t)b * P + pg + s * PW + plq) * LPP + c;
             p4[s] = ld4_stream(m1 + 4 * gi);
-            gm4[s] = g_m1 ? ld4_stream(g_m1 + 4 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gm4[s] = g_m1 ? ld_row4<LPP>(g_m1, (size_t)b * P + pg + s * PW + plq, c, gm_row, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (DIMG) {
 #pragma unroll
@@ -406,10 +407,16 @@ static int fused_common_checks(const char* what, int B, int P, int K) {
 
 extern "C" int ups_step_decode_fwd(const float* l0, const float* feat, float* m0, long long* labels0, float* inj,
                                    int B, int P, int K, int F, void* stream) {
+    return ups_step_decode_fwd_rows(l0, K, feat, m0, labels0, inj, B, P, K, F, stream);
+}
+
+extern "C" int ups_step_decode_fwd_rows(const float* l0, int l0_row, const float* feat, float* m0, long long* labels0,
+                                        float* inj, int B, int P, int K, int F, void* stream) {
     UPS_REQUIRE(l0 && feat && m0 && labels0 && inj, "step_decode_fwd: null pointer");
+    UPS_REQUIRE(l0_row >= 1 && l0_row <= K, "step_decode_fwd: l0 rows of %d floats for K=%d", l0_row, K);
     if (int rc = fused_common_checks("step_decode_fwd", B, P, K)) return rc;
     UPS_REQUIRE(F >= 4 && F % 4 == 0 && (size_t)K * F * 4 <= 96 * 1024, "step_decode_fwd: F=%d unsupported", F);
-    UPS_REQUIRE(aligned16(l0) && aligned16(feat) && aligned16(m0) && aligned16(inj), "step_decode_fwd: 16-byte alignment");
+    UPS_REQUIRE((l0_row < K || aligned16(l0)) && aligned16(feat) && aligned16(m0) && aligned16(inj), "step_decode_fwd: 16-byte alignment");
     if (B == 0) return UPS_OK;
     const int per = fused_pix_per_cta(B, P);
     dim3 grid((unsigned)cdiv(P, per), B);
@@ -422,7 +429,7 @@ extern "C" int ups_step_decode_fwd(const float* l0, const float* feat, float* m0
 #define UPS_DEC_FWD2(LPP, FT)                                                                           \
     {                                                                                                   \
         if (int rc = set_smem(step_decode_fwd_kernel<LPP, FT>, sm)) return rc;                          \
-        step_decode_fwd_kernel<LPP, FT><<<grid, FTPB, sm, s>>>(l0, feat, m0, labels0, inj, P, F, per);  \
+        step_decode_fwd_kernel<LPP, FT><<<grid, FTPB, sm, s>>>(l0, feat, m0, labels0, inj, P, F, per, l0_row); \
     }
 #define UPS_DEC_FWD(LPP) \
     { if (F == 64) UPS_DEC_FWD2(LPP, 64) else if (F == 32) UPS_DEC_FWD2(LPP, 32) else if (F == 16) UPS_DEC_FWD2(LPP, 16) else UPS_DEC_FWD2(LPP, 0) }
@@ -439,10 +446,17 @@ extern "C" int ups_step_encode_fwd(const float* l1, const float* img1, float* m1
 
 extern "C" int ups_step_encode_fwd_planes(const float* l1, const float* img1, float* m1, float* parts_pm, float* pooled,
                                           int B, int P, int K, int Kpl, void* ws, size_t ws_bytes, void* stream) {
+    return ups_step_encode_fwd_rows(l1, K, img1, m1, parts_pm, pooled, B, P, K, Kpl, ws, ws_bytes, stream);
+}
+
+extern "C" int ups_step_encode_fwd_rows(const float* l1, int l1_row, const float* img1, float* m1, float* parts_pm,
+                                        float* pooled, int B, int P, int K, int Kpl, void* ws, size_t ws_bytes,
+                                        void* stream) {
     UPS_REQUIRE(l1 && img1 && m1 && parts_pm && pooled, "step_encode_fwd: null pointer");
+    UPS_REQUIRE(l1_row >= 1 && l1_row <= K, "step_encode_fwd: l1 rows of %d floats for K=%d", l1_row, K);
     UPS_REQUIRE(Kpl >= 1 && Kpl <= K, "step_encode_fwd: %d part planes of K=%d", Kpl, K);
     if (int rc = fused_common_checks("step_encode_fwd", B, P, K)) return rc;
-    UPS_REQUIRE(aligned16(l1) && aligned16(img1) && aligned16(m1) && aligned16(parts_pm), "step_encode_fwd: 16-byte alignment");
+    UPS_REQUIRE((l1_row < K || aligned16(l1)) && aligned16(img1) && aligned16(m1) && aligned16(parts_pm), "step_encode_fwd: 16-byte alignment");
     if (B == 0) return UPS_OK;
     const int per = fused_pix_per_cta(B, P);
     const int splits = (int)cdiv(P, per);
@@ -457,10 +471,10 @@ extern "C" int ups_step_encode_fwd_planes(const float* l1, const float* img1, fl
         const size_t sm = (size_t)FW * EncFwdSmem<LPP>::WREG * sizeof(float);                                 \
         if (Kpl < K) {                                                                                        \
             if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB, true>, sm)) return rc;                      \
-            step_encode_fwd_kernel<LPP, MB, true><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
+            step_encode_fwd_kernel<LPP, MB, true><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl, l1_row); \
         } else {                                                                                              \
             if (int rc = set_smem(step_encode_fwd_kernel<LPP, MB, false>, sm)) return rc;                     \
-            step_encode_fwd_kernel<LPP, MB, false><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl); \
+            step_encode_fwd_kernel<LPP, MB, false><<<grid, FTPB, sm, s>>>(l1, img1, m1, parts_pm, partial, B, P, per, Kpl, l1_row); \
         }                                                                                                     \
     }
 #define UPS_ENC_FWD(LPP) \
@@ -477,7 +491,14 @@ extern "C" int ups_step_encode_fwd_planes(const float* l1, const float* img1, fl
 extern "C" int ups_step_decode_bwd(const float* g_inj, const float* m0, const float* g_m0, const float* feat,
                                    float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes,
                                    void* stream) {
+    return ups_step_decode_bwd_rows(g_inj, m0, g_m0, K, feat, dl0, dfeat, B, P, K, F, ws, ws_bytes, stream);
+}
+
+extern "C" int ups_step_decode_bwd_rows(const float* g_inj, const float* m0, const float* g_m0, int gm_row, const float* feat,
+                                        float* dl0, float* dfeat, int B, int P, int K, int F, void* ws, size_t ws_bytes,
+                                        void* stream) {
     UPS_REQUIRE(g_inj && m0 && feat && dl0 && dfeat, "step_decode_bwd: null pointer");
+    UPS_REQUIRE(gm_row >= 1 && gm_row <= K, "step_decode_bwd: g_m0 rows of %d floats for K=%d", gm_row, K);
     if (int rc = fused_common_checks("step_decode_bwd", B, P, K)) return rc;
     UPS_REQUIRE(K >= 8, "step_decode_bwd: fused path needs K in {8,16,32}, got %d", K);
     UPS_REQUIRE(F == 16 || F == 32 || F == 64, "step_decode_bwd: fused path needs F in {16,32,64}, got %d", F);
@@ -494,7 +515,7 @@ extern "C" int ups_step_decode_bwd(const float* g_inj, const float* m0, const fl
     {                                                                                                        \
         const size_t sm = (size_t)FW * DecBwdSmem<KK, FF>::WREG * sizeof(float);                             \
         if (int rc = set_smem(step_decode_bwd_kernel<KK, FF>, sm)) return rc;                                \
-        step_decode_bwd_kernel<KK, FF><<<grid, FTPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per);  \
+        step_decode_bwd_kernel<KK, FF><<<grid, FTPB, sm, s>>>(g_inj, m0, g_m0, feat, dl0, partial, P, per, gm_row); \
     }
 #define UPS_DEC_BWD_F(KK) \
     { if (F == 16) UPS_DEC_BWD(KK, 16) else if (F == 32) UPS_DEC_BWD(KK, 32) else UPS_DEC_BWD(KK, 64) }
@@ -515,10 +536,17 @@ extern "C" int ups_step_encode_bwd(const float* g_parts_pm, const float* g_poole
 extern "C" int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
                                           const float* g_m1, float* dl1, float* dimg1, int B, int P, int K, int Kpl,
                                           void* stream) {
+    return ups_step_encode_bwd_rows(g_parts_pm, g_pooled, img1, m1, g_m1, K, dl1, dimg1, B, P, K, Kpl, stream);
+}
+
+extern "C" int ups_step_encode_bwd_rows(const float* g_parts_pm, const float* g_pooled, const float* img1, const float* m1,
+                                        const float* g_m1, int gm_row, float* dl1, float* dimg1, int B, int P, int K,
+                                        int Kpl, void* stream) {
     UPS_REQUIRE(g_parts_pm && img1 && m1 && dl1, "step_encode_bwd: null pointer");
+    UPS_REQUIRE(gm_row >= 1 && gm_row <= K, "step_encode_bwd: g_m1 rows of %d floats for K=%d", gm_row, K);
     UPS_REQUIRE(Kpl >= 1 && Kpl <= K, "step_encode_bwd: %d part planes of K=%d", Kpl, K);
     if (int rc = fused_common_checks("step_encode_bwd", B, P, K)) return rc;
-    UPS_REQUIRE(aligned16(g_parts_pm) && aligned16(img1) && aligned16(m1) && aligned16(dl1) && (!g_m1 || aligned16(g_m1)) &&
+    UPS_REQUIRE(aligned16(g_parts_pm) && aligned16(img1) && aligned16(m1) && aligned16(dl1) && (!g_m1 || gm_row < K || aligned16(g_m1)) &&
                     (!dimg1 || aligned16(dimg1)), "step_encode_bwd: 16-byte alignment");
     if (B == 0) return UPS_OK;
     const int per = fused_pix_per_cta(B, P);
@@ -527,7 +555,7 @@ extern "C" int ups_step_encode_bwd_planes(const float* g_parts_pm, const float* 
 #define UPS_ENC_BWD3(LPP, DI, PD)                                                                                     \
     {                                                                                                                 \
         if (int rc = set_smem(step_encode_bwd_kernel<LPP, DI, PD>, sm)) return rc;                                    \
-        step_encode_bwd_kernel<LPP, DI, PD><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl); \
+        step_encode_bwd_kernel<LPP, DI, PD><<<grid, FTPB, sm, s>>>(g_parts_pm, g_pooled, img1, m1, g_m1, dl1, dimg1, B, P, per, Kpl, gm_row); \
     }
 #define UPS_ENC_BWD(LPP)                                                                                              \
     {                                                                                                                 \

@@ -20,7 +20,7 @@ struct WarpArgs {
 };
 struct DecodeArgs {
     const float* l0; const float* feat; float* m0; long long* labels0; float* inj;
-    int P, F, pix_per_cta, splits;
+    int P, F, pix_per_cta, splits, l0_row;
 };
 
 static_assert(WARP_TPB == FTPB, "both roles use 128-thread CTAs");
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(FTPB, MINB) step_warp_decode_fwd_kernel(const 
     const unsigned c3n = (unsigned)(((unsigned long long)(i + 1) * n3) / total);
     if (c3n > c3) {
         const int b = (int)(c3 / (unsigned)da.splits), split = (int)(c3 - (unsigned)b * da.splits);
-        step_decode_fwd_body<LPP, FT>(da.l0, da.feat, da.m0, da.labels0, da.inj, da.P, da.F, da.pix_per_cta, split, b, dyn4);
+        step_decode_fwd_body<LPP, FT>(da.l0, da.feat, da.m0, da.labels0, da.inj, da.P, da.F, da.pix_per_cta, split, b, dyn4, da.l0_row);
     } else {
         const unsigned j = i - c3;
         const int b = (int)(j / (unsigned)wa.tiles_per_sample), tile = (int)(j - (unsigned)b * wa.tiles_per_sample);
@@ -53,6 +53,13 @@ using namespace ups;
 extern "C" int ups_step_warp_decode_fwd(const float* U, const float* U2, const float* coord, const float* T, float* out,
                                         float* out2, int N, int N2, int S, const float* l0, const float* feat, float* m0,
                                         long long* labels0, float* inj, int B, int K, int F, void* stream) {
+    return ups_step_warp_decode_fwd_rows(U, U2, coord, T, out, out2, N, N2, S, l0, K, feat, m0, labels0, inj, B, K, F, stream);
+}
+
+extern "C" int ups_step_warp_decode_fwd_rows(const float* U, const float* U2, const float* coord, const float* T, float* out,
+                                             float* out2, int N, int N2, int S, const float* l0, int l0_row, const float* feat,
+                                             float* m0, long long* labels0, float* inj, int B, int K, int F, void* stream) {
+    UPS_REQUIRE(l0_row >= 1 && l0_row <= K, "step_warp_decode_fwd: l0 rows of %d floats for K=%d", l0_row, K);
     UPS_REQUIRE(U && coord && T && out && l0 && feat && m0 && labels0 && inj, "step_warp_decode_fwd: null pointer");
     UPS_REQUIRE((U2 == nullptr) == (out2 == nullptr), "step_warp_decode_fwd: U2 and out2 must be given together");
     UPS_REQUIRE(N > 0 && N <= 65535 && N2 >= 0 && N2 <= N && S > 1, "step_warp_decode_fwd: N=%d N2=%d S=%d", N, N2, S);
@@ -61,10 +68,10 @@ extern "C" int ups_step_warp_decode_fwd(const float* U, const float* U2, const f
     UPS_REQUIRE(F == 16 || F == 32 || F == 64, "step_warp_decode_fwd: needs F in {16,32,64}, got %d", F);
     const int P = S * S;
     UPS_REQUIRE(P % 32 == 0 && (long long)S * S * 3 < (1ll << 31), "step_warp_decode_fwd: S=%d unsupported", S);
-    UPS_REQUIRE(aligned16(l0) && aligned16(feat) && aligned16(m0) && aligned16(inj), "step_warp_decode_fwd: 16-byte alignment");
+    UPS_REQUIRE((l0_row < K || aligned16(l0)) && aligned16(feat) && aligned16(m0) && aligned16(inj), "step_warp_decode_fwd: 16-byte alignment");
     WarpArgs wa{U, U2, coord, T, out, out2, N2, S, S, S, S, (int)cdiv((long long)P, WARP_TPB * WARP_PPT)};
     const int per = fused_pix_per_cta(B, P);
-    DecodeArgs da{l0, feat, m0, labels0, inj, P, F, per, (int)cdiv(P, per)};
+    DecodeArgs da{l0, feat, m0, labels0, inj, P, F, per, (int)cdiv(P, per), l0_row};
     const unsigned long long n1 = (unsigned long long)N * wa.tiles_per_sample, n3 = (unsigned long long)B * da.splits;
     UPS_REQUIRE(n1 + n3 < (1ull << 31), "step_warp_decode_fwd: grid too large");
     const unsigned total = (unsigned)(n1 + n3);

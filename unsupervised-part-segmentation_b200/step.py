@@ -162,6 +162,14 @@ class PartStep:
         return dict(l0=self._l0p[..., :K], l1=self._l1p[..., :K], g_inj=self._g_injp[..., :F + K],
                     g_m0=self._g_m0p[..., :K], g_m1=self._g_m1p[..., :K])
 
+    def _arg(self, t, buf):
+        """(tensor to hand to the kernel, its row length): the pitched buffer itself when `t` is its view, else the
+        caller's contiguous [.,K] tensor, which the kernels read in place."""
+        if t.data_ptr() == buf.data_ptr() and t.stride() == buf.stride():
+            return buf, self.Kp
+        assert t.is_contiguous() and t.shape[-1] == self.K, "pass a contiguous tensor or the view from pitched_inputs()"
+        return t, self.K
+
     def _into(self, t, buf, n_cols, fill, st):
         """t [.., n_cols] -> the row-pitched buffer `buf` [.., pitch]; no-op when t already is the buffer's view."""
         if t.data_ptr() == buf.data_ptr() and t.stride() == buf.stride() and t.shape[-1] == n_cols:
@@ -177,11 +185,13 @@ class PartStep:
         st = self._stream()
         assert feat.is_contiguous()
         assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
-        self._into(l0, self._l0p, K, float("-inf"), st)
-        self._into(l1, self._l1p, K, float("-inf"), st)
+        # logits: a contiguous [.,K] tensor is read in place by the kernels (row length K, parts >= K are -inf); the
+        # pitched view of pitched_inputs() already is the padded buffer
+        a0, n0 = self._arg(l0, self._l0p)
+        a1, n1 = self._arg(l1, self._l1p)
         # feat [B,K,F] -> [B,Kp,F]: per sample the first K*F floats of the padded block (the rest stays zero)
         C.call("ups_copy_rows", feat.data_ptr(), K * F, self._featp.data_ptr(), Kp * F, B, K * F, 0, 0.0, st)
-        o = self._inner.forward(views, coord, t_vector, self._l0p, self._l1p, self._featp)
+        o = self._inner.forward(views, coord, t_vector, a0, a1, self._featp, rows=dict(l0=n0, l1=n1))
         self._feat, self._img1 = feat, self._inner._img1
         return dict(warped=o["warped"], m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts, pooled=self.pooled,
                     inj=self.inj)
@@ -193,27 +203,26 @@ class PartStep:
         assert tuple(g_inj.shape) == (B, S, S, F + K) and tuple(g_parts.shape) == (K * B, S, S, 3)
         self._into(g_inj, self._g_injp, F + K, 0.0, st)
         gm0 = gm1 = gpl = None
+        n0 = n1 = Kp
         if g_m0 is not None:
-            self._into(g_m0, self._g_m0p, K, 0.0, st)
-            gm0 = self._g_m0p
+            gm0, n0 = self._arg(g_m0, self._g_m0p)
         if g_m1 is not None:
-            self._into(g_m1, self._g_m1p, K, 0.0, st)
-            gm1 = self._g_m1p
+            gm1, n1 = self._arg(g_m1, self._g_m1p)
         if g_pooled is not None:
             C.call("ups_copy_rows", g_pooled.data_ptr(), K * 3, self._g_pooledp.data_ptr(), Kp * 3, B, K * 3, 0, 0.0, st)
             gpl = self._g_pooledp
-        o = self._inner.backward(self._g_injp, g_parts, gpl, gm0, gm1, g_warped)
+        o = self._inner.backward(self._g_injp, g_parts, gpl, gm0, gm1, g_warped, rows=dict(g_m0=n0, g_m1=n1))
         out = dict(dl0=self.dl0, dl1=self.dl1, dfeat=self.dfeat)
         if "dviews" in o:
             out["dviews"] = o["dviews"]
         return out
 
     # ------------------------------------------------------------------ forward
-    def _decode_fwd(self, l0, feat, conv_V, conv_b, st):
+    def _decode_fwd(self, l0, feat, conv_V, conv_b, st, l0_row=None):
         """decode side on stream `st`: K3, or with first_conv softmax -> table -> 3x3 conv on the assignment"""
         B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
         if not self.Co:
-            C.call("ups_step_decode_fwd", l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(),
+            C.call("ups_step_decode_fwd_rows", l0.data_ptr(), l0_row or K, feat.data_ptr(), self.m0.data_ptr(),
                    self.labels0.data_ptr(), self.inj.data_ptr(), B, P, K, F, st)
             return
         C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
@@ -222,7 +231,7 @@ class PartStep:
         C.call("ups_inject_conv_fwd", self.mh0c.data_ptr(), self.G.data_ptr(), conv_b.data_ptr(), self.h0.data_ptr(),
                B, S, S, K, self.Co, st)
 
-    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None):
+    def forward(self, views, coord, t_vector, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None, rows=None):
         """views [V,B,S,S,3] (view0, view1[, view0_target]), fp32 in [-1, 1] or the dataset's uint8
         (normalised on the device exactly as cub/code/data/data.py:134 does on the host); coord,
         t_vector [2B,8,2] from make_input_tps_param; l0, l1 [B,S,S,K]; feat [B,K,F].  Returns a dict
@@ -234,30 +243,32 @@ class PartStep:
         before the logits."""
         if self.Kp:
             return self._forward_padded(views, coord, t_vector, l0, l1, feat)
+        # rows (internal, padded part counts): row lengths of l0 / l1 when they are read in place ({"l0": 25, "l1": 25})
         if self.fuse_fwd:
-            return self._forward_fused(views, coord, t_vector, l0, l1, feat)
+            return self._forward_fused(views, coord, t_vector, l0, l1, feat, rows)
         self.forward_warp(views, coord, t_vector)
-        return self.forward_parts(l0, l1, feat, conv_V, conv_b, enc_V, enc_b)
+        return self.forward_parts(l0, l1, feat, conv_V, conv_b, enc_V, enc_b, rows)
 
     @_on_device
-    def _forward_fused(self, views, coord, t_vector, l0, l1, feat):
+    def _forward_fused(self, views, coord, t_vector, l0, l1, feat, rows=None):
         B, S, K, F, P, V = self.B, self.S, self.K, self.F, self.P, self.V
         st = self._stream()
         views = self._ingest(views, st)
+        r0, r1 = (rows or {}).get("l0", K), (rows or {}).get("l1", K)
         assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
-        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        assert tuple(l0.shape) == (B, S, S, r0) and tuple(l1.shape) == (B, S, S, r1) and tuple(feat.shape) == (B, K, F)
         assert tuple(coord.shape) == (2 * B, 8, 2) and tuple(t_vector.shape) == (2 * B, 8, 2)
         C.call("ups_tps_solve", coord.data_ptr(), t_vector.data_ptr(), self.T.data_ptr(), 2 * B, st)
         if self.before_params is not None:
             self.before_params()     # data-parallel wrapper: wait for the averaged gradients (the TPS solve needs none)
-        C.call("ups_step_warp_decode_fwd", views.data_ptr(), views[2].data_ptr() if V > 2 else None, coord.data_ptr(),
+        C.call("ups_step_warp_decode_fwd_rows", views.data_ptr(), views[2].data_ptr() if V > 2 else None, coord.data_ptr(),
                self.T.data_ptr(), self.warped.data_ptr(), self.warped[2].data_ptr() if V > 2 else None, 2 * B,
-               B if V > 2 else 0, S, l0.data_ptr(), feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
+               B if V > 2 else 0, S, l0.data_ptr(), r0, feat.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
                self.inj.data_ptr(), B, K, F, st)
         self._warped, self._coord = self.warped, coord
         img1 = self.warped[1]
         self._img1, self._feat = img1, feat
-        C.call("ups_step_encode_fwd_planes", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+        C.call("ups_step_encode_fwd_rows", l1.data_ptr(), r1, img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
                self.pooled.data_ptr(), B, P, K, self.Kpl, self.ws.data_ptr(), self.ws.numel(), st)
         return dict(warped=self.warped, m0=self.m0, m1=self.m1, labels0=self.labels0, parts=self.parts,
                     pooled=self.pooled, inj=self.inj)
@@ -308,12 +319,14 @@ class PartStep:
         return self._warped
 
     @_on_device
-    def forward_parts(self, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None):
+    def forward_parts(self, l0, l1, feat, conv_V=None, conv_b=None, enc_V=None, enc_b=None, rows=None):
         """K2 (encode side: l1, warped view 1) and K3 (decode side: l0, feat) on the current stream."""
         B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
         st = self._stream()
+        r0, r1 = (rows or {}).get("l0", K), (rows or {}).get("l1", K)
+        assert (r0 == K and r1 == K) or (self.fused and not self.Co and not self.Ce), "in-place rows need the fused kernels"
         assert l0.is_contiguous() and l1.is_contiguous() and feat.is_contiguous()
-        assert tuple(l0.shape) == (B, S, S, K) and tuple(l1.shape) == (B, S, S, K) and tuple(feat.shape) == (B, K, F)
+        assert tuple(l0.shape) == (B, S, S, r0) and tuple(l1.shape) == (B, S, S, r1) and tuple(feat.shape) == (B, K, F)
         if self.Co:
             assert conv_V is not None and conv_b is not None, "first_conv: pass conv_V [3,3,F+K,Co] and conv_b [Co]"
             assert tuple(conv_V.shape) == (3, 3, F + K, self.Co) and tuple(conv_b.shape) == (self.Co,)
@@ -331,7 +344,7 @@ class PartStep:
             C.call("ups_parts_conv_fwd", img1.data_ptr(), self.mh1c.data_ptr(), enc_V.data_ptr(), enc_b.data_ptr(),
                    self.e0.data_ptr(), B, S, S, K, 3, self.Ce, st)
         elif self.fused:
-            C.call("ups_step_encode_fwd_planes", l1.data_ptr(), img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
+            C.call("ups_step_encode_fwd_rows", l1.data_ptr(), r1, img1.data_ptr(), self.m1.data_ptr(), self.parts.data_ptr(),
                    self.pooled.data_ptr(), B, P, K, self.Kpl, self.ws.data_ptr(), self.ws.numel(), st)
         else:
             C.call("ups_part_softmax_fwd", l1.data_ptr(), self.m1.data_ptr(), None, self.mh1.data_ptr(), B * P, K, st)
@@ -339,7 +352,7 @@ class PartStep:
             C.call("ups_part_pool_fwd", img1.data_ptr(), self.mh1.data_ptr(), self.pooled.data_ptr(), B, P, K, 3, 0,
                    1.0 / P, self.ws.data_ptr(), self.ws.numel(), st)
         if self.fused or self.Co:
-            self._decode_fwd(l0, feat, conv_V, conv_b, st)
+            self._decode_fwd(l0, feat, conv_V, conv_b, st, r0)
         else:
             C.call("ups_part_softmax_fwd", l0.data_ptr(), self.m0.data_ptr(), self.labels0.data_ptr(),
                    self.mh0.data_ptr(), B * P, K, st)
@@ -356,7 +369,7 @@ class PartStep:
         return out
 
     # ------------------------------------------------------------------ backward
-    def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None):
+    def backward(self, g_inj, g_parts, g_pooled=None, g_m0=None, g_m1=None, g_warped=None, rows=None):
         """Cotangents: g_inj [B,S,S,F+K] (with first_conv: g_h0 [B,S,S,Co] in its place), g_parts [K*B,S,S,3]
         (part-major), g_pooled [B,K,3], g_m0/g_m1 [B,S,S,K] (from the mask losses), g_warped [V,B,S,S,3]
         (views_grad only).  Returns dict(dl0, dl1, dfeat[, dV, db][, dviews]).
@@ -365,12 +378,12 @@ class PartStep:
         backward_encode (K5 [, K6]: dl1 [, dviews])."""
         if self.Kp:
             return self._backward_padded(g_inj, g_parts, g_pooled, g_m0, g_m1, g_warped)
-        out = self.backward_decode(g_inj, g_m0)
-        out.update(self.backward_encode(g_parts, g_pooled, g_m1, g_warped))
+        out = self.backward_decode(g_inj, g_m0, (rows or {}).get("g_m0"))
+        out.update(self.backward_encode(g_parts, g_pooled, g_m1, g_warped, (rows or {}).get("g_m1")))
         return out
 
     @_on_device
-    def backward_decode(self, g_inj, g_m0=None):
+    def backward_decode(self, g_inj, g_m0=None, gm_row=None):
         """K4: autodiff of the decode side.  g_inj, g_m0 -> dl0 [B,S,S,K], dfeat [B,K,F] [, dV, db]."""
         B, S, K, F, P = self.B, self.S, self.K, self.F, self.P
         st = self._stream()
@@ -384,8 +397,8 @@ class PartStep:
             C.call("ups_inject_conv_table_bwd", self.dG.data_ptr(), feat.data_ptr(), self._conv_V.data_ptr(),
                    self.dfeat.data_ptr(), self.dV.data_ptr(), B, K, F, self.Co, st)
         elif self.fused:
-            C.call("ups_step_decode_bwd_tc" if self.decode_bwd == "tc" else "ups_step_decode_bwd",
-                   g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), feat.data_ptr(),
+            C.call("ups_step_decode_bwd_tc_rows" if self.decode_bwd == "tc" else "ups_step_decode_bwd_rows",
+                   g_inj.data_ptr(), self.m0.data_ptr(), p(g_m0), gm_row or K, feat.data_ptr(),
                    self.dl0.data_ptr(), self.dfeat.data_ptr(), B, P, K, F, self.ws.data_ptr(), self.ws.numel(), st)
         else:
             # dm0 = inject-bwd (+ g_m0, accumulated by the kernel) -> softmax-bwd
@@ -399,7 +412,7 @@ class PartStep:
         return out
 
     @_on_device
-    def backward_encode(self, g_parts, g_pooled=None, g_m1=None, g_warped=None):
+    def backward_encode(self, g_parts, g_pooled=None, g_m1=None, g_warped=None, gm_row=None):
         """K5 (autodiff of the encode side: dl1 [, dimg1]) and, with views_grad, K6 (TPS backward: dviews)."""
         B, S, K, P, V = self.B, self.S, self.K, self.P, self.V
         st = self._stream()
@@ -413,8 +426,8 @@ class PartStep:
                    self.Ce, self.ws_pc.data_ptr(), self.ws_pc.numel(), st)
             return dict(dl1=self.dl1, dVe=self.dVe, dbe=self.dbe)
         if self.fused:
-            C.call("ups_step_encode_bwd_planes", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
-                   p(g_m1), self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, self.Kpl, st)
+            C.call("ups_step_encode_bwd_rows", g_parts.data_ptr(), p(g_pooled), img1.data_ptr(), self.m1.data_ptr(),
+                   p(g_m1), gm_row or K, self.dl1.data_ptr(), self.dimg1.data_ptr() if want_dimg else None, B, P, K, self.Kpl, st)
         else:
             C.call("ups_mask_parts_bwd", g_parts.data_ptr(), img1.data_ptr(), self.mh1.data_ptr(),
                    self.dimg1.data_ptr() if want_dimg else None, self.dm.data_ptr(), B, P, K, 3, 1, st)
