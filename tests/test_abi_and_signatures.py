@@ -67,6 +67,21 @@ def test_workspace_query_and_error_paths(ups):
     assert C.launch_count() == 0
 
 
+def test_row_length_arguments_are_validated_without_a_gpu(ups):
+    """The `_rows` forms of the fused entry points (ragged [.,K'] rows read in place, K' <= K) reject a row length outside
+    1..K, and a tensor of full rows (K' == K) that is not 16-byte aligned, before touching the device."""
+    C = ups._cabi
+    with pytest.raises(C.UpsError, match="rows of 33 floats for K=32"):
+        C.call("ups_step_decode_fwd_rows", 16, 33, 16, 16, 16, 16, 1, 1024, 32, 64, None)
+    with pytest.raises(C.UpsError, match="rows of 0 floats"):
+        C.call("ups_step_encode_fwd_rows", 16, 0, 16, 16, 16, 16, 1, 1024, 32, 25, None, 0, None)
+    with pytest.raises(C.UpsError, match="16-byte alignment"):         # full rows keep the vector-load contract
+        C.call("ups_step_decode_fwd_rows", 20, 32, 16, 16, 16, 16, 1, 1024, 32, 64, None)
+    with pytest.raises(C.UpsError, match="workspace"):                  # ragged rows may start anywhere: next check fires
+        C.call("ups_step_encode_fwd_rows", 20, 25, 16, 16, 16, 16, 1, 1024, 32, 25, None, 0, None)
+    assert C.launch_count() == 0
+
+
 def test_n4_error_paths_without_a_gpu(ups):
     """The first-convolution entry points validate sizes before touching the device."""
     C = ups._cabi
