@@ -147,13 +147,24 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def base_call(name):
+    """The C-ABI call without the suffix of its argument form: `ups_step_decode_bwd_tc_rows` (row-length argument) and
+    `ups_step_encode_fwd_planes` (part-plane count) launch the same kernels as the plain entry points."""
+    for suffix in ("_rows", "_planes"):
+        if name.endswith(suffix):
+            return name[:-len(suffix)]
+    return name
+
+
 def call_bytes(name, K, F, V, B, P):
     """Algorithmic (compulsory) bytes of one C-ABI call of the step, fp32, K parts, F features, 3 channels; None if the
     call is not one of the path kernels.  Per decode/encode pixel there are B*P pixels, per warped pixel V*B*P."""
+    name = base_call(name)
     warp_px, px = V * B * P, B * P
     per = {
         "ups_tps_warp_fwd": (4 * (3 + 3), warp_px), "ups_tps_warp_pair_fwd": (4 * (3 + 3), warp_px),
         "ups_tps_warp_bwd": (4 * (3 + 3), warp_px), "ups_tps_warp_pair_bwd": (4 * (3 + 3), warp_px),
+        "ups_tps_warp_bwd_sum": (4 * (3 + 3) * V + 4 * 3, px),  # + the encode side's dimg1, added on the fly (view 1)
         "ups_step_encode_fwd": (4 * (K + 3 + K + 3 * K), px),
         "ups_step_decode_fwd": (4 * (K + K + 2 + F + K), px),
         "ups_step_decode_bwd": (4 * ((F + K) + K + K + K), px), "ups_step_decode_bwd_tc": (4 * ((F + K) + K + K + K), px),
@@ -171,7 +182,8 @@ CALL_KERNEL = {  # C-ABI call -> the kernel that dominates it (profiles/ncu_traf
     "ups_tps_warp_fwd": "tps_warp_fwd_kernel", "ups_tps_warp_pair_fwd": "tps_warp_fwd_kernel",
     "ups_step_encode_fwd": "step_encode_fwd_kernel", "ups_step_decode_fwd": "step_decode_fwd_kernel",
     "ups_step_decode_bwd": "step_decode_bwd_kernel", "ups_step_decode_bwd_tc": "step_decode_bwd_tma_kernel",
-    "ups_step_encode_bwd": "step_encode_bwd_kernel",
+    "ups_step_encode_bwd": "step_encode_bwd_kernel", "ups_step_warp_decode_fwd": "step_warp_decode_fwd_kernel",
+    "ups_tps_warp_bwd": "tps_warp_bwd_kernel", "ups_tps_warp_bwd_sum": "tps_warp_bwd_kernel",
 }
 
 
@@ -183,7 +195,7 @@ def ncu_traffic(call, workload, B):
     d = json.load(open(p))
     if d.get("workload") != workload or d.get("B") != B:
         return None, None
-    return d["bytes_per_launch"].get(CALL_KERNEL.get(call, "")), d.get("source")
+    return d["bytes_per_launch"].get(CALL_KERNEL.get(base_call(call), "")), d.get("source")
 
 
 def set_rank_affinity(local, world_local):

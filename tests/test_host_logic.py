@@ -86,3 +86,27 @@ def test_dp_tables(ups):
     red = dp.GradAllReducer(flat_grads=torch.ones(64), world_size=1)
     red.launch(0, part=(1, 2))
     assert float(red.flat.sum()) == 64.0
+
+
+def test_bench_knows_the_bytes_of_every_call_of_the_fused_step(ups):
+    """bench.py's roofline is keyed by C-ABI call name: every `ups_step_*` / `ups_tps_warp_*` call that step.py issues
+    (whatever its argument form: plain, `_planes`, `_rows`) must have algorithmic bytes, and the ones with a committed
+    ncu capture must find their kernel in profiles/ncu_traffic.json.  (A renamed entry point once left `roofline.frac`
+    null.)"""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    src = open(os.path.join(root, "unsupervised-part-segmentation_b200", "step.py")).read()
+    names = set(re.findall(r'"(ups_step_[a-z0-9_]+|ups_tps_warp_[a-z0-9_]+)"', src))
+    assert {"ups_step_warp_decode_fwd_rows", "ups_step_encode_fwd_rows", "ups_step_decode_bwd_tc_rows",
+            "ups_step_encode_bwd_rows"} <= names
+    for n in names:
+        assert bench.call_bytes(n, 16, 64, 3, 256, 16384), n
+    assert bench.base_call("ups_step_encode_fwd_planes") == "ups_step_encode_fwd"
+    for n in ("ups_step_warp_decode_fwd_rows", "ups_step_encode_fwd_rows", "ups_step_decode_bwd_tc_rows", "ups_step_encode_bwd_rows"):
+        traffic, source = bench.ncu_traffic(n, "cub", 256)
+        assert traffic and traffic > 0.9 * bench.call_bytes(n, 16, 64, 3, 256, 16384) * 0.5 and source, n
