@@ -26,6 +26,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--parts", type=int, nargs="*", default=[8, 16, 25, 32], help="part counts to run")
+    ap.add_argument("--no-generic", action="store_true", help="skip the unfused K=25 variant (40 ms per step)")
     args = ap.parse_args()
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -34,7 +36,7 @@ def main():
     rows = []
     for S, B in ((128, 64), (256, 16), (512, 4)):      # SURVEY.md 8d config 5 batch sizes ...
         B *= 4                                           # ... x4 so that one step exceeds the 126 MB L2
-        for K in (8, 16, 25, 32):
+        for K in args.parts:
             g = torch.Generator(device=dev).manual_seed(0)
             views = torch.rand(V, B, S, S, 3, device=dev, generator=g) * 2 - 1
             l0 = torch.randn(B, S, S, K, device=dev, generator=g)
@@ -48,11 +50,11 @@ def main():
             prm = ups_b200.tps_parameters(2 * B, generator=torch.Generator().manual_seed(1234), device=dev, **PENN_TPS)
             coord, tv = ups_b200.make_input_tps_param(prm)
             for variant in (("padded", "pitched", "generic") if K == 25 else ("simt", "tc")):
-                if variant == "tc" and K == 8:
+                if (variant == "tc" and K == 8) or (variant == "generic" and args.no_generic):
                     continue
                 a_l0, a_l1, a_g_inj, a_g_m0, a_g_m1 = l0, l1, g_inj, g_m0, g_m1
-                # K = 25: "padded" = the fused kernels of Kp = 32 on -inf padded logits, contiguous inputs copied into the
-                # row-pitched buffers (default); "pitched" = the producer writes into PartStep.pitched_inputs() (no copies);
+                # K = 25: "padded" = the fused kernels of Kp = 32, contiguous [.,25] inputs: logits and mask cotangents read
+                # in place (row length 25, parts >= 25 are -inf / 0), g_inj copied into its row-pitched buffer (default); "pitched" = the producer writes into PartStep.pitched_inputs() (no copies);
                 # "generic" = the unfused kernels
                 os.environ["UPS_PAD_K"] = "0" if variant == "generic" else "1"
                 step = PartStep(B, S, K, F, n_views=V, decode_bwd=variant if variant in ("simt", "tc") else "auto", device=dev)
