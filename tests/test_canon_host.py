@@ -70,6 +70,34 @@ def test_softmax_bitexact(lib, K):
     assert np.array_equal(bits(hard), bits(hr.numpy()))
 
 
+@pytest.mark.parametrize("K", [3, 5, 12, 25, 31])
+def test_minus_infinity_padding_gives_the_same_bits(lib, K):
+    """What the padded part counts rest on: the canonical softmax of [.,K] logits and of the same
+    logits padded with -inf to the next power of two agree bit for bit on the first K parts (exp_canon(-inf) == 0
+    exactly, the pair-tree sum is defined on zero-padded terms), the padding parts get probability 0 and are never the
+    arg-max -- in the oracle and in the host build of the header the kernels compile."""
+    Kp = 1 << (K - 1).bit_length()
+    g = torch.Generator().manual_seed(100 + K)
+    x = torch.randn(2048, K, generator=g) * 3
+    x[:64] = torch.round(x[:64])
+    x[64:96] = x[64:96] * 40
+    xp = torch.full((2048, Kp), float("-inf"))
+    xp[:, :K] = x
+    assert float(canon.exp_canon(torch.tensor([float("-inf")]))[0]) == 0.0
+    pr, prp = P.softmax(x), P.softmax(xp)
+    assert np.array_equal(bits(prp[:, :K].numpy()), bits(pr.numpy())) and bool((prp[:, K:] == 0).all())
+    assert torch.equal(torch.argmax(prp, -1), torch.argmax(pr, -1))
+    xn = np.ascontiguousarray(xp.numpy())
+    p = np.empty_like(xn)
+    hard = np.empty_like(xn)
+    lab = np.empty(xn.shape[0], np.int64)
+    lib.ups_host_softmax(fp(xn), fp(p), fp(lab), fp(hard), ctypes.c_longlong(xn.shape[0]), Kp)
+    assert np.array_equal(bits(p[:, :K]), bits(pr.numpy())) and not p[:, K:].any() and not hard[:, K:].any()
+    assert np.array_equal(lab, torch.argmax(pr, -1).numpy())
+    hr = P.straight_through_estimator(P.hard_max(pr, 1), pr)
+    assert np.array_equal(bits(hard[:, :K]), bits(hr.numpy()))
+
+
 def _params(N, seed, **kw):
     g = torch.Generator().manual_seed(seed)
     base = dict(scal=0.8, tps_scal=0.15, rot_scal=0.2, off_scal=0.2, scal_var=0.1, rescal=1.0)
